@@ -1,0 +1,386 @@
+// K2: constant-Q transform.  Replaces librosa.cqt as reached from
+// /root/reference/util_audio.py:424-429 (slice_C).
+//
+// librosa's recursive-downsampling CQT computes, per octave o,
+//     C_o = fft_basis_o . rfft(rect-windowed frames of y_o)       (y_o: decimated signal)
+// which is linear in y_o, so the host plan builder folds "rect-window FFT then
+// sparse FFT-domain basis" into ONE dense real kernel bank G_o[n_fft, 2*n_filt]
+// (identical numbers; DESIGN.md section "K2") and the device evaluates
+//     C_o[t, :] = sum_n y_o[reflect(t*hop_o + n - n_fft/2)] * G_o[n, :]
+// i.e. a GEMM whose A operand is the strided-frame (Hankel) view of the signal.
+//
+// This file: the kaiser_fast decimation cascade (resampy's integer-ratio case
+// is a fixed symmetric FIR) and the fp32 CUDA-core contraction (impl=1, also the
+// validation path for the tcgen05 kernel in cqt_umma.cu).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "cqt_plan.cuh"
+#include "saga_common.cuh"
+
+namespace saga {
+
+// ---------------------------------------------------------------------------
+// decimation by `factor` with a symmetric FIR (taps[0] = centre), zeros outside
+// the signal, output zero-padded from floor(len/factor) to ceil(len/factor)
+// (librosa.resample fix=True), gain folded into the taps.
+// ---------------------------------------------------------------------------
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_PER_THREAD = 4;
+
+__global__ void __launch_bounds__(DEC_THREADS)
+decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets,
+                int64_t in_stride, const int64_t* __restrict__ clip_lens, int in_shift,
+                int in_factor_total, float* __restrict__ out, int64_t out_stride,
+                const float* __restrict__ taps, int n_taps, int factor) {
+  extern __shared__ float sm[];
+  const int S = n_taps - 1;
+  float* tp = sm;                 // n_taps
+  float* xs = sm + ((n_taps + 3) & ~3);  // tile of input
+  const int clip = blockIdx.y;
+  // length of this clip at the INPUT level of this stage
+  int64_t len = clip_lens[clip];
+  if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;  // early stage
+  for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;                        // halvings
+  const int64_t n_full = len / factor;
+  const int64_t n_out = (len + factor - 1) / factor;
+  const int tile_out = DEC_THREADS * DEC_PER_THREAD;
+  const int64_t o0 = (int64_t)blockIdx.x * tile_out;
+  if (o0 >= n_out) return;
+  const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
+  for (int i = threadIdx.x; i < n_taps; i += DEC_THREADS) tp[i] = taps[i];
+  const int64_t i0 = o0 * factor - S;
+  const int tile_in = tile_out * factor + 2 * S;
+  for (int i = threadIdx.x; i < tile_in; i += DEC_THREADS) {
+    const int64_t s = i0 + i;
+    xs[i] = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+  }
+  __syncthreads();
+  float* y = out + (int64_t)clip * out_stride;
+#pragma unroll
+  for (int u = 0; u < DEC_PER_THREAD; ++u) {
+    const int lo = threadIdx.x + u * DEC_THREADS;
+    const int64_t o = o0 + lo;
+    if (o >= n_out) break;
+    float acc = 0.f;
+    if (o < n_full) {
+      const float* c = xs + lo * factor + S;  // centre sample
+      acc = tp[0] * c[0];
+      for (int m = 1; m <= S; ++m) acc = fmaf(tp[m], c[-m] + c[m], acc);
+    }
+    y[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 contraction: CTA = 128 frames x FC output columns of one (clip, octave)
+// ---------------------------------------------------------------------------
+constexpr int CT_FRAMES = 128;
+constexpr int CT_KC = 32;   // samples of the kernel per staged chunk
+constexpr int CT_FC = 32;   // output columns (re/im interleaved) per CTA
+
+struct ContractArgs {
+  const float* sig;             // level signal base
+  const int64_t* sig_offsets;   // optional per-clip offsets (level 0 without early stage = raw wav)
+  int64_t sig_stride;
+  const int64_t* clip_lens;     // input-rate lengths
+  int early_factor, level;
+  const float* bank;            // [n_fft][ncol]
+  int n_fft, ncol, hop, first_bin, n_bins;
+  int zero_pad;                 // this launch also zeroes the padding columns [n_bins, frame_pitch)
+  float* mag_out;
+  float2* cplx_out;
+  int64_t frame_pitch, out_clip_stride;
+  const int32_t* clip_frames;   // [n_clips] output frame count (min over octaves)
+};
+
+__global__ void __launch_bounds__(CT_FRAMES)
+cqt_contract_kernel(const ContractArgs a) {
+  __shared__ float ys[CT_KC][CT_FRAMES + 1];
+  __shared__ __align__(16) float gs[CT_KC][CT_FC];
+  const int clip = blockIdx.z;
+  const int t0 = blockIdx.x * CT_FRAMES;
+  const int c0 = blockIdx.y * CT_FC;
+  const int T = a.clip_frames[clip];
+  if (t0 >= T) return;
+  int64_t len = a.clip_lens[clip];
+  if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
+  for (int s = 0; s < a.level; ++s) len = (len + 1) >> 1;
+  const float* y = a.sig + (a.sig_offsets ? a.sig_offsets[clip] : (int64_t)clip * a.sig_stride);
+  const int tid = threadIdx.x;
+  float acc[CT_FC];
+#pragma unroll
+  for (int f = 0; f < CT_FC; ++f) acc[f] = 0.f;
+  const int half = a.n_fft >> 1;
+  for (int n0 = 0; n0 < a.n_fft; n0 += CT_KC) {
+    __syncthreads();
+    // stage the Hankel tile ys[kk][t] = y[reflect((t0+t)*hop + n0 + kk - n_fft/2)]
+    for (int i = tid; i < CT_KC * CT_FRAMES; i += CT_FRAMES) {
+      const int kk = i % CT_KC, t = i / CT_KC;
+      int64_t s = (int64_t)(t0 + t) * a.hop + n0 + kk - half;
+      float v = 0.f;
+      if (t0 + t < T) {
+        if (s < 0 || s >= len) s = reflect_index(s, len);
+        v = __ldg(y + s);
+      }
+      ys[kk][t] = v;
+    }
+    for (int i = tid; i < CT_KC * CT_FC; i += CT_FRAMES) {
+      const int kk = i / CT_FC, f = i % CT_FC;
+      gs[kk][f] = (c0 + f < a.ncol) ? __ldg(a.bank + (int64_t)(n0 + kk) * a.ncol + c0 + f) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < CT_KC; ++kk) {
+      const float v = ys[kk][tid];
+      const float4* g4 = reinterpret_cast<const float4*>(gs[kk]);
+#pragma unroll
+      for (int q = 0; q < CT_FC / 4; ++q) {
+        const float4 g = g4[q];
+        acc[4 * q + 0] = fmaf(v, g.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v, g.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, g.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, g.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  const int t = t0 + tid;
+  if (t >= T) return;
+  const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
+#pragma unroll
+  for (int f = 0; f < CT_FC; f += 2) {
+    const int filt = (c0 + f) >> 1;
+    const int bin = a.first_bin + filt;
+    if (c0 + f < a.ncol && bin >= 0 && bin < a.n_bins) {
+      const float re = acc[f], im = acc[f + 1];
+      a.mag_out[row + bin] = sqrtf(re * re + im * im);
+      if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
+    }
+  }
+  if (a.zero_pad && blockIdx.y == 0)
+    for (int64_t k = a.n_bins; k < a.frame_pitch; ++k) {
+      a.mag_out[row + k] = 0.f;
+      if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+    }
+}
+
+// per-clip output frame count = min over octaves of 1 + len_o // hop_o (librosa __trim_stack)
+__global__ void cqt_frames_kernel(const int64_t* clip_lens, int n_clips, int early_factor,
+                                  const int* levels, const int* hops, int n_oct, int32_t* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clips) return;
+  int64_t len0 = clip_lens[c];
+  if (len0 <= 0) { out[c] = 0; return; }
+  if (early_factor > 1) len0 = (len0 + early_factor - 1) / early_factor;
+  int64_t best = INT32_MAX;
+  for (int o = 0; o < n_oct; ++o) {
+    int64_t len = len0;
+    for (int s = 0; s < levels[o]; ++s) len = (len + 1) >> 1;
+    best = min(best, 1 + len / hops[o]);
+  }
+  out[c] = (int32_t)best;
+}
+
+static int64_t level_len(int64_t len, int early_factor, int level) {
+  if (len <= 0) return 0;
+  if (early_factor > 1) len = (len + early_factor - 1) / early_factor;
+  for (int s = 0; s < level; ++s) len = (len + 1) >> 1;
+  return len;
+}
+
+int64_t cqt_level_pitch(const saga_cqt_plan* p, int level, int64_t max_len) {
+  return (level_len(max_len, p->early_factor, level) + 3 + 4) & ~int64_t(3);
+}
+
+}  // namespace saga
+
+using namespace saga;
+
+extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d) {
+  if (!out || !d) return set_error(SAGA_ERR_INVALID, "cqt_plan_create: null argument");
+  *out = nullptr;
+  if (d->n_octaves < 1 || !d->octaves || d->n_bins < 1 || d->hop < 1 || d->early_factor < 1)
+    return set_error(SAGA_ERR_INVALID, "cqt_plan_create: bad descriptor");
+  if (d->early_factor > 1 && (!d->early_taps_host || d->n_early_taps < 1))
+    return set_error(SAGA_ERR_INVALID, "cqt_plan_create: early taps missing");
+  saga_cqt_plan* p = new saga_cqt_plan();
+  p->n_bins = d->n_bins;
+  p->hop = d->hop;
+  p->early_factor = d->early_factor;
+  p->n_early_taps = d->n_early_taps;
+  p->n_half_taps = d->n_half_taps;
+  p->d_early_taps = p->d_half_taps = nullptr;
+  p->d_levels = p->d_hops = nullptr;
+  p->max_level = 0;
+  p->umma = nullptr;
+  auto fail = [&](int rc) { saga_cqt_plan_destroy(p); return rc; };
+  if (d->early_factor > 1) {
+    if (cudaMalloc(&p->d_early_taps, sizeof(float) * d->n_early_taps) != cudaSuccess)
+      return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
+    cudaMemcpy(p->d_early_taps, d->early_taps_host, sizeof(float) * d->n_early_taps, cudaMemcpyHostToDevice);
+  }
+  std::vector<int> levels, hops;
+  for (int o = 0; o < d->n_octaves; ++o) {
+    const saga_cqt_octave& s = d->octaves[o];
+    if (s.level < 0 || s.hop < 1 || s.n_fft < 2 || (s.n_fft & (s.n_fft - 1)) || s.n_filters < 1 || !s.bank_host)
+      return fail(set_error(SAGA_ERR_INVALID, "cqt_plan_create: bad octave %d", o));
+    CqtOctaveDev od;
+    od.level = s.level; od.hop = s.hop; od.n_fft = s.n_fft; od.n_filters = s.n_filters;
+    od.first_bin = s.first_bin; od.bank = nullptr;
+    const size_t n = (size_t)s.n_fft * 2 * s.n_filters;
+    if (cudaMalloc(&od.bank, sizeof(float) * n) != cudaSuccess)
+      return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
+    cudaMemcpy(od.bank, s.bank_host, sizeof(float) * n, cudaMemcpyHostToDevice);
+    od.bank_host.assign(s.bank_host, s.bank_host + n);
+    p->oct.push_back(od);
+    p->max_level = std::max(p->max_level, s.level);
+    levels.push_back(s.level);
+    hops.push_back(s.hop);
+  }
+  if (p->max_level > 0) {
+    if (!d->half_taps_host || d->n_half_taps < 1)
+      return fail(set_error(SAGA_ERR_INVALID, "cqt_plan_create: half-band taps missing"));
+    if (cudaMalloc(&p->d_half_taps, sizeof(float) * d->n_half_taps) != cudaSuccess)
+      return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
+    cudaMemcpy(p->d_half_taps, d->half_taps_host, sizeof(float) * d->n_half_taps, cudaMemcpyHostToDevice);
+  }
+  cudaMalloc(&p->d_levels, sizeof(int) * levels.size());
+  cudaMalloc(&p->d_hops, sizeof(int) * hops.size());
+  cudaMemcpy(p->d_levels, levels.data(), sizeof(int) * levels.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(p->d_hops, hops.data(), sizeof(int) * hops.size(), cudaMemcpyHostToDevice);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(set_error(SAGA_ERR_CUDA, "cqt_plan_create: %s", cudaGetErrorString(e)));
+  cqt_umma_plan_init(p);  // tensor-core side tables (no-op when the plan does not fit that path)
+  *out = p;
+  return SAGA_OK;
+}
+
+extern "C" int saga_cqt_plan_destroy(saga_cqt_plan* p) {
+  if (!p) return SAGA_OK;
+  cqt_umma_plan_free(p);
+  cudaFree(p->d_early_taps);
+  cudaFree(p->d_half_taps);
+  cudaFree(p->d_levels);
+  cudaFree(p->d_hops);
+  for (auto& o : p->oct) cudaFree(o.bank);
+  delete p;
+  return SAGA_OK;
+}
+
+extern "C" int64_t saga_cqt_num_frames(const saga_cqt_plan* p, int64_t len) {
+  if (!p || len <= 0) return 0;
+  int64_t best = INT64_MAX;
+  for (auto& o : p->oct) best = std::min(best, 1 + level_len(len, p->early_factor, o.level) / o.hop);
+  return best;
+}
+
+// workspace layout: [int32 clip_frames[n_clips] padded to 256 B][level 0 (only if early_factor>1)]
+// [level 1] ... [level max_level], each n_clips * pitch(level) floats
+static int64_t ws_header_bytes(int n_clips) { return (((int64_t)n_clips * 4) + 255) & ~int64_t(255); }
+
+extern "C" int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* p, int n_clips, int64_t max_len) {
+  if (!p || n_clips <= 0 || max_len <= 0) return 256;
+  int64_t b = ws_header_bytes(n_clips);
+  for (int l = (p->early_factor > 1 ? 0 : 1); l <= p->max_level; ++l)
+    b += (int64_t)n_clips * cqt_level_pitch(p, l, max_len) * 4;
+  return b + 256;
+}
+
+extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
+                             const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
+                             void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                             void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+  if (!p || !wav || !clip_offsets || !clip_lens || !C_mag_out || !workspace)
+    return set_error(SAGA_ERR_INVALID, "cqt_exec: null argument");
+  if (frame_pitch < p->n_bins) return set_error(SAGA_ERR_INVALID, "cqt_exec: frame_pitch < n_bins");
+  if (n_clips <= 0 || max_len <= 0) return SAGA_OK;
+  if (workspace_bytes < saga_cqt_workspace_bytes(p, n_clips, max_len))
+    return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T_max = saga_cqt_num_frames(p, max_len);
+
+  // ---- carve the workspace -------------------------------------------------------
+  char* ws = (char*)workspace;
+  int32_t* clip_frames = (int32_t*)ws;
+  ws += ws_header_bytes(n_clips);
+  std::vector<float*> lvl(p->max_level + 1, nullptr);
+  std::vector<int64_t> pitch(p->max_level + 1, 0);
+  for (int l = 0; l <= p->max_level; ++l) {
+    pitch[l] = cqt_level_pitch(p, l, max_len);
+    if (l == 0 && p->early_factor == 1) continue;  // level 0 is the caller's wav
+    lvl[l] = (float*)ws;
+    ws += (int64_t)n_clips * pitch[l] * 4;
+  }
+
+  cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, n_clips, p->early_factor,
+                                                           p->d_levels, p->d_hops, (int)p->oct.size(),
+                                                           clip_frames);
+  SAGA_LAUNCH_CHECK();
+
+  // ---- decimation cascade ----------------------------------------------------------
+  const int tile_out = DEC_THREADS * DEC_PER_THREAD;
+  if (p->early_factor > 1) {
+    const int64_t n_out = level_len(max_len, p->early_factor, 0);
+    dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
+    const size_t smem = sizeof(float) * (((p->n_early_taps + 3) & ~3) + tile_out * p->early_factor + 2 * (p->n_early_taps - 1));
+    if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
+    if (smem > 48 * 1024)
+      SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
+                                                     p->d_early_taps, p->n_early_taps, p->early_factor);
+    SAGA_LAUNCH_CHECK();
+  }
+  for (int l = 1; l <= p->max_level; ++l) {
+    const int64_t n_out = level_len(max_len, p->early_factor, l);
+    dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
+    const size_t smem = sizeof(float) * (((p->n_half_taps + 3) & ~3) + tile_out * 2 + 2 * (p->n_half_taps - 1));
+    const bool from_wav = (l == 1 && p->early_factor == 1);
+    decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
+                                                     from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
+                                                     p->early_factor, lvl[l], pitch[l], p->d_half_taps,
+                                                     p->n_half_taps, 2);
+    SAGA_LAUNCH_CHECK();
+  }
+
+  // ---- contraction -------------------------------------------------------------------
+  CqtLevels lv;
+  lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens;
+  lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.clip_frames = clip_frames;
+  if (impl != 1) {
+    int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
+                           out_clip_stride, st);
+    if (rc == SAGA_OK) return SAGA_OK;
+    if (rc != SAGA_ERR_UNSUPPORTED || impl == 2) return rc;
+  }
+  bool first = true;
+  for (auto& o : p->oct) {
+    ContractArgs a;
+    const bool raw = (o.level == 0 && p->early_factor == 1);
+    a.sig = raw ? wav : lvl[o.level];
+    a.sig_offsets = raw ? clip_offsets : nullptr;
+    a.sig_stride = raw ? 0 : pitch[o.level];
+    a.clip_lens = clip_lens;
+    a.early_factor = p->early_factor;
+    a.level = o.level;
+    a.bank = o.bank;
+    a.n_fft = o.n_fft;
+    a.ncol = 2 * o.n_filters;
+    a.hop = o.hop;
+    a.first_bin = o.first_bin;
+    a.n_bins = p->n_bins;
+    a.zero_pad = (first && frame_pitch > p->n_bins) ? 1 : 0;
+    first = false;
+    a.mag_out = C_mag_out;
+    a.cplx_out = (float2*)C_cplx_out;
+    a.frame_pitch = frame_pitch;
+    a.out_clip_stride = out_clip_stride;
+    a.clip_frames = clip_frames;
+    dim3 grid((unsigned)((T_max + CT_FRAMES - 1) / CT_FRAMES), (a.ncol + CT_FC - 1) / CT_FC, n_clips);
+    cqt_contract_kernel<<<grid, CT_FRAMES, 0, st>>>(a);
+    SAGA_LAUNCH_CHECK();
+  }
+  return SAGA_OK;
+}

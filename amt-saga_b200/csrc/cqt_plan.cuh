@@ -1,0 +1,48 @@
+// Internal plan layout shared by cqt.cu (cascade + fp32 contraction) and
+// cqt_umma.cu (tcgen05 contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+struct CqtOctaveDev {
+  int level, hop, n_fft, n_filters, first_bin;
+  float* bank;                    // device [n_fft][2*n_filters]
+  std::vector<float> bank_host;   // same, host copy (tensor-path operand packing)
+};
+
+struct CqtUmmaState;  // opaque to cqt.cu
+
+struct saga_cqt_plan {
+  int n_bins, hop, early_factor;
+  int n_early_taps, n_half_taps;
+  float* d_early_taps;
+  float* d_half_taps;
+  int* d_levels;
+  int* d_hops;
+  int max_level;
+  std::vector<CqtOctaveDev> oct;
+  CqtUmmaState* umma;
+};
+
+namespace saga {
+
+// per-level decimated signals of one exec call
+struct CqtLevels {
+  const float* wav;
+  const int64_t* clip_offsets;
+  const int64_t* clip_lens;
+  float* const* lvl;        // [max_level+1] device buffers (lvl[0]==nullptr when early_factor==1)
+  const int64_t* pitch;     // per-clip pitch of each level buffer
+  const int32_t* clip_frames;
+};
+
+void cqt_umma_plan_init(saga_cqt_plan* p);
+void cqt_umma_plan_free(saga_cqt_plan* p);
+// returns SAGA_ERR_UNSUPPORTED when the plan does not fit the tensor path
+int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t max_len,
+                  int64_t T_max, float* mag_out, float2* cplx_out, int64_t frame_pitch,
+                  int64_t out_clip_stride, cudaStream_t st);
+
+}  // namespace saga

@@ -1,0 +1,538 @@
+// K1: batched windowed real FFT -> magnitude / unit phasor / complex STFT.
+// Replaces librosa.stft + magphase as reached from
+// /root/reference/util_audio.py:127-128, :147, :173.
+//
+// Design (sm_100a, HBM-bound target):
+//  * a CTA owns a run of F consecutive frames of one clip and stages the
+//    contiguous sample span (F-1)*hop + n_fft ONCE in shared memory with
+//    float4 loads (reflect padding = index mirroring at the clip edges), so the
+//    n_fft/hop-fold frame overlap is served from SMEM, not L2/HBM;
+//  * one warp per frame: the real frame is viewed as M = n_fft/2 complex
+//    points, transformed by an in-place decimation-in-frequency FFT whose
+//    passes are register-resident radix-16/32 butterflies with immediate
+//    twiddles (fft_radix.cuh); data crosses lanes through a padded
+//    (conflict-free) per-warp SMEM buffer, inter-pass twiddles come from
+//    float64-generated fp32 tables laid out in access order;
+//  * real-FFT split + |z| (+ phasor / complex) fused in the epilogue, stores
+//    are 128-byte coalesced rows of the frame-major output, per-frame and
+//    per-clip maxima (ref_mag) are a by-product.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "fft_radix.cuh"
+#include "saga_common.cuh"
+
+struct saga_stft_plan {
+  int n_fft, hop, center, M;
+  int n_pass;
+  int radix[3];
+  float* d_window;   // n_fft floats
+  float2* d_tw[3];   // per pass: [R][L/R] inter-pass twiddles (last pass: unused)
+  float2* d_twN;     // M/2 + 1 entries exp(-2*pi*i*k/n_fft)
+  int warps;         // warps per CTA
+  int frames_per_cta;
+  int span_alloc;    // floats reserved for the staged span
+  size_t smem_bytes;
+};
+
+namespace saga {
+
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
+
+struct StftArgs {
+  const float* wav;
+  const int64_t* clip_offsets;
+  const int64_t* clip_lens;
+  float* mag_out;
+  float2* phase_out;
+  float2* cplx_out;
+  float* frame_max_out;
+  float* clip_max_out;
+  const float* window;
+  const float2* tw0;
+  const float2* tw1;
+  const float2* twN;
+  int64_t frame_pitch, out_clip_stride;
+  int hop, center, frames_per_cta, span_alloc, tiles_per_clip, max_frames;
+};
+
+// One DIF pass over blocks of length L with radix R, in place in `buf`.
+// FIRST reads the windowed real samples instead of buf.
+template <int M, int L, int R, bool FIRST, bool LAST>
+__device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const float2* __restrict__ win2,
+                                         const float2* __restrict__ tw, int lane) {
+  constexpr int LS = L / R;       // sub-block length after this pass
+  constexpr int ITEMS = M / R;    // small FFTs in this pass
+  constexpr int ITERS = (ITEMS + 31) / 32;
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = lane + 32 * it;
+    if ((ITEMS % 32) != 0 && q >= ITEMS) break;
+    const int b = q / LS, j = q % LS;
+    const int base = b * L + j;
+    float2 v[R];
+    if (FIRST) {
+      const bool al = ((reinterpret_cast<uintptr_t>(xs) & 7) == 0);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = base + r * LS;
+        float2 x;
+        if (al) {
+          x = *reinterpret_cast<const float2*>(xs + 2 * n);
+        } else {
+          x.x = xs[2 * n];
+          x.y = xs[2 * n + 1];
+        }
+        const float2 w = __ldg(win2 + n);
+        v[r] = make_float2(x.x * w.x, x.y * w.y);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = buf[pidx(base + r * LS)];
+    }
+    fft_reg<R>(v);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int rp = bitrev(i, R);
+      float2 o = v[i];
+      if (!LAST && rp > 0) o = cmul(o, __ldg(tw + rp * LS + j));
+      buf[pidx(base + rp * LS)] = o;
+    }
+  }
+  __syncwarp();
+}
+
+// position of Z[k] in buf after the digit-reversing in-place passes
+template <int M, int R0, int R1, int R2>
+__device__ __forceinline__ int zpos(int k) {
+  constexpr int L1 = M / R0, L2 = L1 / R1;
+  if (R2 == 1) return (k % R0) * L1 + (k / R0);
+  return (k % R0) * L1 + ((k / R0) % R1) * L2 + (k / (R0 * R1));
+}
+
+template <int M, int R0, int R1, int R2, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(const StftArgs a) {
+  constexpr int N = 2 * M;
+  constexpr int BUF = M + M / 32;
+  extern __shared__ __align__(16) float smem[];
+  float* span = smem;
+  float2* bufs = reinterpret_cast<float2*>(smem + a.span_alloc);
+
+  const int clip = blockIdx.x / a.tiles_per_clip;
+  const int tile = blockIdx.x % a.tiles_per_clip;
+  const int64_t len = a.clip_lens[clip];
+  int64_t T;
+  if (len <= 0) T = 0;
+  else if (a.center) T = 1 + len / a.hop;
+  else T = len >= N ? 1 + (len - N) / a.hop : 0;
+  const int64_t t0 = (int64_t)tile * a.frames_per_cta;
+  if (t0 >= T) return;
+  const int nF = (int)min((int64_t)a.frames_per_cta, T - t0);
+  const float* x = a.wav + a.clip_offsets[clip];
+
+  // ---- stage the sample span once per CTA ---------------------------------
+  const int64_t s0 = t0 * a.hop - (a.center ? N / 2 : 0);
+  const int span_len = (nF - 1) * a.hop + N;
+  const bool interior = (s0 >= 0) && (s0 + span_len <= len);
+  if (interior && ((reinterpret_cast<uintptr_t>(x + s0) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(x + s0);
+    float4* dst = reinterpret_cast<float4*>(span);
+    const int n4 = span_len >> 2;
+    for (int i = threadIdx.x; i < n4; i += WARPS * 32) dst[i] = __ldg(src + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < span_len; i += WARPS * 32) span[i] = __ldg(x + s0 + i);
+  } else {
+    for (int i = threadIdx.x; i < span_len; i += WARPS * 32) {
+      int64_t s = s0 + i;
+      if (s < 0 || s >= len) s = reflect_index(s, len);
+      span[i] = __ldg(x + s);
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* buf = bufs + warp * BUF;
+  const float2* win2 = reinterpret_cast<const float2*>(a.window);
+
+  for (int f = warp; f < nF; f += WARPS) {
+    const float* xs = span + f * a.hop;
+    constexpr int L1 = M / R0, L2 = L1 / R1;
+    dif_pass<M, M, R0, true, false>(buf, xs, win2, a.tw0, lane);
+    dif_pass<M, L1, R1, false, (R2 == 1)>(buf, nullptr, nullptr, a.tw1, lane);
+    if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true>(buf, nullptr, nullptr, nullptr, lane);
+
+    // ---- real-FFT split, |X|, outputs -----------------------------------
+    const int64_t t = t0 + f;
+    const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
+    float* mag = a.mag_out + row;
+    float vmax = 0.f;
+#pragma unroll 1
+    for (int k = lane; k <= M / 2; k += 32) {
+      const float2 zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
+      const float2 zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
+      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      const float2 Tw = cmul(__ldg(a.twN + k), O);
+      const float2 Xk = make_float2(E.x + Tw.x, E.y + Tw.y);
+      const float2 Xm = make_float2(E.x - Tw.x, -(E.y - Tw.y));
+      const float mk = sqrtf(Xk.x * Xk.x + Xk.y * Xk.y);
+      const float mm = sqrtf(Xm.x * Xm.x + Xm.y * Xm.y);
+      vmax = fmaxf(vmax, fmaxf(mk, mm));
+      mag[k] = mk;
+      if (k != M / 2) mag[M - k] = mm;
+      if (a.cplx_out) {
+        float2* c = a.cplx_out + row;
+        c[k] = Xk;
+        if (k != M / 2) c[M - k] = Xm;
+      }
+      if (a.phase_out) {
+        float2* p = a.phase_out + row;
+        p[k] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
+        if (k != M / 2)
+          p[M - k] = mm > 0.f ? make_float2(Xm.x / mm, Xm.y / mm) : make_float2(1.f, 0.f);
+      }
+    }
+    // padding columns [M+1, frame_pitch) are defined as zero
+    for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += 32) {
+      mag[k] = 0.f;
+      if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+      if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) {
+      if (a.frame_max_out) a.frame_max_out[(int64_t)clip * a.max_frames + t] = vmax;
+      if (a.clip_max_out) atomic_max_nonneg(a.clip_max_out + clip, vmax);
+    }
+    __syncwarp();
+  }
+}
+
+template <int M, int R0, int R1, int R2, int WARPS>
+static int launch_stft(const saga_stft_plan* p, const StftArgs& a, int n_clips, cudaStream_t st) {
+  auto kern = stft_kernel<M, R0, R1, R2, WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAGA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int64_t blocks = (int64_t)n_clips * a.tiles_per_clip;
+  if (blocks <= 0) return SAGA_OK;
+  if (blocks > 0x7fffffffLL) return set_error(SAGA_ERR_INVALID, "stft: grid too large");
+  kern<<<(unsigned)blocks, WARPS * 32, p->smem_bytes, st>>>(a);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// K4: inverse STFT (librosa.istft, util_audio.py:92-104).
+// A CTA owns FO*hop consecutive output samples (padded coordinates) and runs the
+// inverse FFT of every frame that overlaps them (FO + halo frames, one warp per
+// frame, buffers kept in SMEM); each output sample then gathers its <= n_fft/hop
+// contributions in ascending frame order (the reference's accumulation order),
+// divides by the window sum-of-squares (accumulated the same way) and is stored
+// once -- no atomics, no scratch in HBM, deterministic.
+// ---------------------------------------------------------------------------
+struct IstftArgs {
+  const float2* cplx_in;
+  const float* mag_in;
+  const float2* phase_in;
+  float* wav_out;
+  const float* window;
+  const float2* tw0;
+  const float2* tw1;
+  const float2* twN;
+  int64_t frame_pitch, in_clip_stride, wav_clip_stride;
+  int hop, center, n_frames, FO, nbuf, tiles_per_clip;
+};
+
+template <int M, int R0, int R1, int R2, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(const IstftArgs a) {
+  constexpr int N = 2 * M;
+  constexpr int BUF = M + M / 32;
+  extern __shared__ __align__(16) float smem[];
+  float2* bufs = reinterpret_cast<float2*>(smem);
+  const int clip = blockIdx.x / a.tiles_per_clip;
+  const int tile = blockIdx.x % a.tiles_per_clip;
+  const int T = a.n_frames;
+  const int64_t total = (int64_t)N + (int64_t)a.hop * (T - 1);   // padded signal length
+  const int64_t trim = a.center ? N / 2 : 0;
+  const int64_t out_len = total - 2 * trim;
+  // this CTA's output range in padded coordinates
+  const int64_t p0 = trim + (int64_t)tile * a.FO * a.hop;
+  const int64_t p1 = min(p0 + (int64_t)a.FO * a.hop, trim + out_len);
+  if (p0 >= p1) return;
+  // frames overlapping [p0, p1):  t*hop <= p < t*hop + N
+  int64_t t_lo = (p0 - N + 1 + a.hop - 1) / a.hop;   // ceil((p0 - N + 1)/hop) for positive numerators
+  if (p0 - N + 1 <= 0) t_lo = 0;
+  int64_t t_hi = (p1 - 1) / a.hop;
+  if (t_hi > T - 1) t_hi = T - 1;
+  const int nfr = (int)(t_hi - t_lo + 1);             // <= nbuf by construction
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = warp; f < nfr; f += WARPS) {
+    float2* buf = bufs + f * BUF;
+    const int64_t row = (int64_t)clip * a.in_clip_stride + (t_lo + f) * a.frame_pitch;
+    // rebuild conj(Z[k]),  Z = E + iO  from the half spectrum X[0..M]
+#pragma unroll 1
+    for (int k = lane; k <= M / 2; k += 32) {
+      float2 xk, xm;
+      if (a.cplx_in) {
+        xk = a.cplx_in[row + k];
+        xm = a.cplx_in[row + M - k];
+      } else {
+        const float mk = a.mag_in[row + k], mm = a.mag_in[row + M - k];
+        const float2 pk = a.phase_in[row + k], pm = a.phase_in[row + M - k];
+        xk = make_float2(mk * pk.x, mk * pk.y);
+        xm = make_float2(mm * pm.x, mm * pm.y);
+      }
+      if (k == 0) { xk.y = 0.f; xm.y = 0.f; }          // irfft ignores Im of DC and Nyquist
+      const float2 E = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
+      const float2 D = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));   // W^k O
+      const float2 w = __ldg(a.twN + k);
+      const float2 O = make_float2(D.x * w.x + D.y * w.y, D.y * w.x - D.x * w.y); // D * conj(w)
+      // Z[k] = E + iO ; Z[M-k] = conj(E) + i conj(O);  store conjugates
+      buf[pidx(k)] = make_float2(E.x - O.y, -(E.y + O.x));
+      if (k != 0 && k != M / 2) buf[pidx(M - k)] = make_float2(E.x + O.y, -(O.x - E.y));
+    }
+    __syncwarp();
+    constexpr int L1 = M / R0, L2 = L1 / R1;
+    dif_pass<M, M, R0, false, false>(buf, nullptr, nullptr, a.tw0, lane);
+    dif_pass<M, L1, R1, false, (R2 == 1)>(buf, nullptr, nullptr, a.tw1, lane);
+    if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true>(buf, nullptr, nullptr, nullptr, lane);
+  }
+  __syncthreads();
+
+  // ---- gather / overlap-add in frame order, normalise, store -------------------
+  const float inv_m = 1.0f / (float)M;
+  float* y = a.wav_out + (int64_t)clip * a.wav_clip_stride;
+  for (int64_t p = p0 + threadIdx.x; p < p1; p += WARPS * 32) {
+    int64_t ta = (p - N + a.hop) / a.hop;               // ceil((p - N + 1)/hop)
+    if (p - N + 1 <= 0) ta = 0;
+    int64_t tb = p / a.hop;
+    if (tb > T - 1) tb = T - 1;
+    float acc = 0.f, wss = 0.f;
+    for (int64_t t = ta; t <= tb; ++t) {
+      const int n = (int)(p - t * a.hop);
+      const float wn = __ldg(a.window + n);
+      const float2 z = bufs[(int)(t - t_lo) * BUF + pidx(zpos<M, R0, R1, R2>(n >> 1))];
+      const float xv = ((n & 1) ? -z.y : z.x) * inv_m;
+      acc += wn * xv;
+      wss += wn * wn;
+    }
+    if (wss > 1.17549435e-38f) acc /= wss;
+    y[p - trim] = acc;
+  }
+}
+
+template <int M, int R0, int R1, int R2, int WARPS>
+static int launch_istft(const saga_stft_plan* p, IstftArgs& a, int n_clips, cudaStream_t st) {
+  auto kern = istft_kernel<M, R0, R1, R2, WARPS>;
+  constexpr int BUF = M + M / 32;
+  const int halo = (2 * M + p->hop - 1) / p->hop;  // frames that can overlap a chunk beyond its own FO
+  int nbuf = (int)((200 * 1024) / (BUF * sizeof(float2)));
+  if (M <= 1024) nbuf = std::min(nbuf, (int)((104 * 1024) / (BUF * sizeof(float2))));
+  int FO = nbuf - halo;
+  if (FO < 1) return set_error(SAGA_ERR_UNSUPPORTED, "istft: hop=%d too small for n_fft=%d", p->hop, 2 * M);
+  if (FO > 2 * WARPS) FO = 2 * WARPS;
+  a.FO = FO;
+  a.nbuf = FO + halo;
+  const int64_t total = (int64_t)2 * M + (int64_t)p->hop * (a.n_frames - 1);
+  const int64_t out_len = total - (p->center ? 2 * M : 0);
+  if (out_len <= 0) return SAGA_OK;
+  a.tiles_per_clip = (int)((out_len + (int64_t)FO * p->hop - 1) / ((int64_t)FO * p->hop));
+  const size_t smem = (size_t)a.nbuf * BUF * sizeof(float2);
+  SAGA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int64_t blocks = (int64_t)n_clips * a.tiles_per_clip;
+  if (blocks > 0x7fffffffLL) return set_error(SAGA_ERR_INVALID, "istft: grid too large");
+  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(a);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
+}  // namespace saga
+
+using namespace saga;
+
+static void stft_shape(int n_fft, int* radix, int* n_pass, int* warps) {
+  const int M = n_fft / 2;
+  radix[2] = 1;
+  *n_pass = 2;
+  *warps = 8;
+  switch (M) {
+    case 128: radix[0] = 16; radix[1] = 8; break;
+    case 256: radix[0] = 16; radix[1] = 16; break;
+    case 512: radix[0] = 32; radix[1] = 16; break;
+    case 1024: radix[0] = 32; radix[1] = 32; break;
+    case 2048: radix[0] = 16; radix[1] = 16; radix[2] = 8; *n_pass = 3; *warps = 8; break;
+    case 4096: radix[0] = 16; radix[1] = 16; radix[2] = 16; *n_pass = 3; *warps = 4; break;
+    default: radix[0] = 0;
+  }
+}
+
+extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, int center,
+                                     const float* window_host) {
+  if (!out) return set_error(SAGA_ERR_INVALID, "stft_plan_create: null output");
+  *out = nullptr;
+  if (hop < 1) return set_error(SAGA_ERR_INVALID, "stft_plan_create: hop_length must be >= 1");
+  int radix[3], n_pass, warps;
+  stft_shape(n_fft, radix, &n_pass, &warps);
+  if (n_fft < 256 || n_fft > 8192 || (n_fft & (n_fft - 1)) || radix[0] == 0)
+    return set_error(SAGA_ERR_UNSUPPORTED, "stft_plan_create: n_fft=%d not a power of two in [256, 8192]", n_fft);
+  saga_stft_plan* p = new saga_stft_plan();
+  p->n_fft = n_fft;
+  p->hop = hop;
+  p->center = center ? 1 : 0;
+  p->M = n_fft / 2;
+  p->n_pass = n_pass;
+  for (int i = 0; i < 3; ++i) { p->radix[i] = radix[i]; p->d_tw[i] = nullptr; }
+  p->warps = warps;
+  const int M = p->M;
+  const double PI = 3.14159265358979323846;
+
+  std::vector<float> win(n_fft);
+  for (int n = 0; n < n_fft; ++n)
+    win[n] = window_host ? window_host[n] : (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / n_fft));
+  SAGA_CUDA_OK(cudaMalloc(&p->d_window, sizeof(float) * n_fft));
+  SAGA_CUDA_OK(cudaMemcpy(p->d_window, win.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+
+  // inter-pass twiddles: pass with block length L and radix R multiplies output r' of
+  // the small FFT at in-block offset j by exp(-2*pi*i*j*r'/L); table layout [r'][j].
+  int L = M;
+  for (int ps = 0; ps + 1 < n_pass; ++ps) {
+    const int R = radix[ps], LS = L / R;
+    std::vector<float2> tw((size_t)L);
+    for (int rp = 0; rp < R; ++rp)
+      for (int j = 0; j < LS; ++j) {
+        const double ang = -2.0 * PI * (double)(((int64_t)j * rp) % L) / (double)L;
+        tw[(size_t)rp * LS + j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      }
+    SAGA_CUDA_OK(cudaMalloc(&p->d_tw[ps], sizeof(float2) * L));
+    SAGA_CUDA_OK(cudaMemcpy(p->d_tw[ps], tw.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
+    L = LS;
+  }
+  std::vector<float2> twN(M / 2 + 1);
+  for (int k = 0; k <= M / 2; ++k) {
+    const double ang = -2.0 * PI * k / (double)n_fft;
+    twN[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+  }
+  SAGA_CUDA_OK(cudaMalloc(&p->d_twN, sizeof(float2) * twN.size()));
+  SAGA_CUDA_OK(cudaMemcpy(p->d_twN, twN.data(), sizeof(float2) * twN.size(), cudaMemcpyHostToDevice));
+
+  // frames per CTA: as many as fit a ~100 KB CTA (two CTAs per SM), at most 2 per warp
+  const size_t buf_bytes = (size_t)warps * (M + M / 32) * sizeof(float2);
+  const size_t budget = (M <= 1024 ? 104 * 1024 : 200 * 1024);
+  int F = 1;
+  if (budget > buf_bytes + (size_t)n_fft * 4) {
+    const size_t span_floats = (budget - buf_bytes) / 4;
+    F = (int)((span_floats - n_fft) / hop) + 1;
+  }
+  if (F > 2 * warps) F = 2 * warps;
+  if (F < 1) F = 1;
+  p->frames_per_cta = F;
+  p->span_alloc = (((F - 1) * hop + n_fft) + 3) & ~3;
+  p->smem_bytes = (size_t)p->span_alloc * 4 + buf_bytes;
+  if (p->smem_bytes > 200 * 1024) {
+    saga_stft_plan_destroy(p);
+    return set_error(SAGA_ERR_UNSUPPORTED, "stft_plan_create: hop=%d too large for n_fft=%d staging", hop, n_fft);
+  }
+  *out = p;
+  return SAGA_OK;
+}
+
+extern "C" int saga_stft_plan_destroy(saga_stft_plan* p) {
+  if (!p) return SAGA_OK;
+  cudaFree(p->d_window);
+  for (int i = 0; i < 3; ++i) cudaFree(p->d_tw[i]);
+  cudaFree(p->d_twN);
+  delete p;
+  return SAGA_OK;
+}
+
+extern "C" int64_t saga_stft_num_frames(const saga_stft_plan* p, int64_t len) {
+  if (!p || len <= 0) return 0;
+  if (p->center) return 1 + len / p->hop;
+  return len >= p->n_fft ? 1 + (len - p->n_fft) / p->hop : 0;
+}
+
+extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const int64_t* clip_offsets,
+                              const int64_t* clip_lens, int n_clips, int64_t max_len, float* mag_out,
+                              void* phase_out, void* cplx_out, int64_t frame_pitch,
+                              int64_t out_clip_stride, float* frame_max_out, float* clip_max_out,
+                              void* stream) {
+  if (!p || !wav || !clip_offsets || !clip_lens || !mag_out)
+    return set_error(SAGA_ERR_INVALID, "stft_exec: null argument");
+  if (n_clips < 0) return set_error(SAGA_ERR_INVALID, "stft_exec: n_clips < 0");
+  if (frame_pitch < p->M + 1)
+    return set_error(SAGA_ERR_INVALID, "stft_exec: frame_pitch %lld < n_bins %d", (long long)frame_pitch, p->M + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = saga_stft_num_frames(p, max_len);
+  if (n_clips == 0 || T == 0) return SAGA_OK;
+  if (clip_max_out) SAGA_CUDA_OK(cudaMemsetAsync(clip_max_out, 0, sizeof(float) * n_clips, st));
+
+  StftArgs a;
+  a.wav = wav;
+  a.clip_offsets = clip_offsets;
+  a.clip_lens = clip_lens;
+  a.mag_out = mag_out;
+  a.phase_out = (float2*)phase_out;
+  a.cplx_out = (float2*)cplx_out;
+  a.frame_max_out = frame_max_out;
+  a.clip_max_out = clip_max_out;
+  a.window = p->d_window;
+  a.tw0 = p->d_tw[0];
+  a.tw1 = p->d_tw[1];
+  a.twN = p->d_twN;
+  a.frame_pitch = frame_pitch;
+  a.out_clip_stride = out_clip_stride;
+  a.hop = p->hop;
+  a.center = p->center;
+  a.frames_per_cta = p->frames_per_cta;
+  a.span_alloc = p->span_alloc;
+  a.tiles_per_clip = (int)((T + p->frames_per_cta - 1) / p->frames_per_cta);
+  a.max_frames = (int)T;
+  switch (p->M) {
+    case 128: return launch_stft<128, 16, 8, 1, 8>(p, a, n_clips, st);
+    case 256: return launch_stft<256, 16, 16, 1, 8>(p, a, n_clips, st);
+    case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
+    case 1024: return launch_stft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
+    case 2048: return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
+    case 4096: return launch_stft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
+  }
+  return set_error(SAGA_ERR_UNSUPPORTED, "stft_exec: unsupported n_fft");
+}
+
+extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, const float* mag_in,
+                               const void* phase_in, int n_clips, int n_frames, int64_t frame_pitch,
+                               int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
+                               void* stream) {
+  if (!p || !wav_out || (!cplx_in && !(mag_in && phase_in)))
+    return set_error(SAGA_ERR_INVALID, "istft_exec: null argument");
+  if (frame_pitch < p->M + 1) return set_error(SAGA_ERR_INVALID, "istft_exec: frame_pitch < n_bins");
+  if (n_clips <= 0 || n_frames <= 0) return SAGA_OK;
+  IstftArgs a;
+  a.cplx_in = (const float2*)cplx_in;
+  a.mag_in = mag_in;
+  a.phase_in = (const float2*)phase_in;
+  a.wav_out = wav_out;
+  a.window = p->d_window;
+  a.tw0 = p->d_tw[0];
+  a.tw1 = p->d_tw[1];
+  a.twN = p->d_twN;
+  a.frame_pitch = frame_pitch;
+  a.in_clip_stride = in_clip_stride;
+  a.wav_clip_stride = wav_clip_stride;
+  a.hop = p->hop;
+  a.center = p->center;
+  a.n_frames = n_frames;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->M) {
+    case 128: return launch_istft<128, 16, 8, 1, 8>(p, a, n_clips, st);
+    case 256: return launch_istft<256, 16, 16, 1, 8>(p, a, n_clips, st);
+    case 512: return launch_istft<512, 32, 16, 1, 8>(p, a, n_clips, st);
+    case 1024: return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
+    case 2048: return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
+    case 4096: return launch_istft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
+  }
+  return set_error(SAGA_ERR_UNSUPPORTED, "istft_exec: unsupported n_fft");
+}

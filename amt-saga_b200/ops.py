@@ -1,0 +1,296 @@
+"""Batched entry points over the C ABI (include/saga_b200.h).
+
+torch is the carrier only: it owns device memory and the stream; every
+arithmetic step is a call into libsaga_b200.so.  Tensors returned as
+"[..., bins, frames]" are strided views of FRAME-MAJOR storage
+([..., frames, pitch], bins contiguous) -- i.e. Fortran order, the layout
+librosa.stft itself returns.
+"""
+import ctypes as C
+import functools
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cqt_plan import CqtPlan, ParameterError  # noqa: F401
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (there is no CPU path)" % name)
+
+
+def frame_pitch(n_bins):
+    """Row pitch (floats) of frame-major storage: n_bins rounded up to 16 bytes."""
+    return (n_bins + 3) & ~3
+
+
+def bins_frames_view(storage, n_bins):
+    """[..., T, pitch] frame-major storage -> [..., n_bins, T] view."""
+    return storage[..., :n_bins].transpose(-1, -2)
+
+
+def storage_of(view):
+    """Inverse of bins_frames_view for tensors produced by this module: returns
+    the frame-major [..., T, n_bins(+pad)] tensor sharing memory with `view`,
+    or None when `view` is not laid out that way."""
+    t = view.transpose(-1, -2)
+    if t.stride(-1) != 1:
+        return None
+    return t
+
+
+# ---------------------------------------------------------------------------
+# K1 / K4 plans
+# ---------------------------------------------------------------------------
+class StftPlan:
+    def __init__(self, n_fft, hop_length, center=True, window=None):
+        self.n_fft, self.hop, self.center = int(n_fft), int(hop_length), bool(center)
+        self.n_bins = self.n_fft // 2 + 1
+        win = None
+        if window is not None:
+            w = np.ascontiguousarray(np.asarray(window, dtype=np.float32))
+            if w.shape != (self.n_fft,):
+                raise ValueError("window must have n_fft entries")
+            win = w.ctypes.data_as(C.c_void_p)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().saga_stft_plan_create(C.byref(h), self.n_fft, self.hop,
+                                                    int(self.center), win))
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def num_frames(self, n):
+        if n <= 0:
+            return 0
+        if self.center:
+            return 1 + n // self.hop
+        return 1 + (n - self.n_fft) // self.hop if n >= self.n_fft else 0
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.lib().saga_stft_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+@functools.lru_cache(maxsize=32)
+def get_stft_plan(n_fft, hop_length, center=True):
+    return StftPlan(n_fft, hop_length, center)
+
+
+@functools.lru_cache(maxsize=64)
+def get_cqt_plan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=2):
+    return CqtPlan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=filter_scale)
+
+
+def _clip_table(wav, lens):
+    """(wav2d, offsets int64 dev, lens int64 dev, max_len host)."""
+    _require_cuda(wav, "wav")
+    if wav.dtype != torch.float32:
+        wav = wav.float()
+    if wav.dim() == 1:
+        wav = wav.unsqueeze(0)
+    if wav.dim() != 2 or wav.stride(1) != 1:
+        wav = wav.contiguous()
+    n_clips, width = wav.shape
+    offs = torch.arange(n_clips, device=wav.device, dtype=torch.int64) * wav.stride(0)
+    if lens is None:
+        max_len = width
+        lens_dev = torch.full((n_clips,), width, device=wav.device, dtype=torch.int64)
+    else:
+        lens_host = np.asarray(lens.cpu() if isinstance(lens, torch.Tensor) else lens, dtype=np.int64)
+        if lens_host.shape != (n_clips,) or (lens_host > width).any() or (lens_host < 0).any():
+            raise ValueError("lens must be [n_clips] with 0 <= len <= wav.shape[1]")
+        max_len = int(lens_host.max()) if n_clips else 0
+        lens_dev = torch.as_tensor(lens_host, device=wav.device)
+    return wav, offs, lens_dev, max_len
+
+
+def stft_batch(wav, plan, lens=None, want_phase=False, want_complex=False, want_max=True):
+    """K1.  wav: CUDA float32 [clips, samples] (or [samples]); ragged clips via
+    `lens`.  Returns a dict:
+        mag        [clips, n_bins, T] float32 view (frame-major storage)
+        phase / F  complex64 views when requested
+        frame_max  [clips, T],  clip_max [clips]  (clip_max == reference ref_mag)
+    """
+    wav, offs, lens_dev, max_len = _clip_table(wav, lens)
+    n_clips = wav.shape[0]
+    T = plan.num_frames(max_len)
+    P = frame_pitch(plan.n_bins)
+    dev = wav.device
+    alloc = torch.empty if lens is None else torch.zeros
+    mag = alloc((n_clips, T, P), device=dev, dtype=torch.float32)
+    ph = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_phase else None
+    cx = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_complex else None
+    fmax = alloc((n_clips, max(T, 1)), device=dev, dtype=torch.float32) if want_max else None
+    cmax = torch.zeros((n_clips,), device=dev, dtype=torch.float32) if want_max else None
+    _lib.check(_lib.lib().saga_stft_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev), n_clips,
+                                         max_len, _ptr(mag), _ptr(ph), _ptr(cx), P, T * P,
+                                         _ptr(fmax), _ptr(cmax), _stream()))
+    out = {"mag": bins_frames_view(mag, plan.n_bins), "mag_storage": mag}
+    if want_phase:
+        out["phase_storage"] = torch.view_as_complex(ph)
+        out["phase"] = bins_frames_view(out["phase_storage"], plan.n_bins)
+    if want_complex:
+        out["F_storage"] = torch.view_as_complex(cx)
+        out["F"] = bins_frames_view(out["F_storage"], plan.n_bins)
+    if want_max:
+        out["frame_max"], out["clip_max"] = fmax[:, :T], cmax
+    return out
+
+
+def istft_batch(plan, F=None, mag=None, phase=None, n_bins=None):
+    """K4 on frame-major storage [clips, T, P] (rows = frames).  Either complex
+    `F`, or float `mag` and complex unit-phasor `phase` with identical strides.
+    Returns [clips, hop*(T-1)] (centred) float32."""
+    n_bins = plan.n_bins if n_bins is None else n_bins
+    if n_bins != plan.n_bins:
+        raise ValueError("spectrogram has %d bins, plan expects %d" % (n_bins, plan.n_bins))
+
+    def prep(x, dtype):
+        _require_cuda(x, "spectrogram")
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        if x.stride(2) != 1 or x.shape[2] < n_bins:
+            raise ValueError("expected frame-major storage [clips, T, P>=n_bins]")
+        if x.shape[0] > 1 and x.stride(0) < x.stride(1) * x.shape[1]:
+            x = x.contiguous()
+        return x
+
+    if F is not None:
+        s = prep(F, torch.complex64)
+        args = (_ptr(torch.view_as_real(s)), None, None)
+    else:
+        s = prep(mag, torch.float32)
+        p = prep(phase, torch.complex64)
+        if s.stride() != p.stride():
+            s, p = s.contiguous(), p.contiguous()
+        args = (None, _ptr(s), _ptr(torch.view_as_real(p)))
+    n_clips, T, _ = s.shape
+    pitch = s.stride(1) if T > 1 else s.shape[2]
+    cstride = s.stride(0) if n_clips > 1 else T * pitch
+    out_len = plan.hop * (T - 1) + (0 if plan.center else plan.n_fft)
+    wav = torch.empty((n_clips, max(out_len, 0)), device=s.device, dtype=torch.float32)
+    _lib.check(_lib.lib().saga_istft_exec(plan.handle, args[0], args[1], args[2], n_clips, T, pitch,
+                                          cstride, _ptr(wav), wav.stride(0), _stream()))
+    return wav
+
+
+# ---------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
+        _workspaces[key] = ws
+    return ws
+
+
+def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0):
+    """K2.  Returns dict(mag=[clips, n_bins, T] view, C=complex view if requested)."""
+    wav, offs, lens_dev, max_len = _clip_table(wav, lens)
+    n_clips = wav.shape[0]
+    lib = _lib.lib()
+    T = plan.num_frames(max_len)
+    P = frame_pitch(plan.n_bins)
+    dev = wav.device
+    alloc = torch.empty if lens is None else torch.zeros
+    mag = alloc((n_clips, T, P), device=dev, dtype=torch.float32)
+    cx = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_complex else None
+    nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev), n_clips, max_len,
+                                 _ptr(mag), _ptr(cx), P, T * P, _ptr(ws), ws.numel(), impl, _stream()),
+               ParameterError)
+    out = {"mag": bins_frames_view(mag, plan.n_bins), "mag_storage": mag}
+    if want_complex:
+        out["C"] = bins_frames_view(torch.view_as_complex(cx), plan.n_bins)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# K3
+# ---------------------------------------------------------------------------
+def subtract_db_batch(win, guesses, offset_frames, n_bins, overkill=None, guess_ref=None,
+                      ref_init=None, guess_frames=None, normalize=True, relu=True, want_D=True,
+                      amin=1e-5, top_db=80.0):
+    """K3 on frame-major storage.
+        win      [W, T, P] float32, modified in place (P = frame pitch >= n_bins)
+        guesses  [W, S, Tg, P] float32 (S sequential steps per window)
+        offset_frames [W, S] int32 column offsets
+    Returns (D storage [W, T, P] or None, ref [W] = max of each final window)."""
+    _require_cuda(win, "win")
+    if win.dim() != 3 or win.stride(2) != 1 or win.stride(1) < n_bins or win.dtype != torch.float32:
+        raise ValueError("win must be frame-major float32 storage [W, T, P]")
+    W, T, _ = win.shape
+    P = win.stride(1)
+    if W > 1 and win.stride(0) < T * P:
+        raise ValueError("overlapping windows")
+    S = 0
+    Tg = 0
+    if guesses is not None:
+        _require_cuda(guesses, "guesses")
+        if guesses.dim() != 4 or guesses.stride(3) != 1 or guesses.stride(2) != P or not guesses.is_contiguous():
+            raise ValueError("guesses must be contiguous [W, S, Tg, P] with the window's pitch")
+        S, Tg = guesses.shape[1], guesses.shape[2]
+        offset_frames = offset_frames.to(device=win.device, dtype=torch.int32).contiguous()
+    f32 = lambda x: None if x is None else x.to(device=win.device, dtype=torch.float32).contiguous()
+    overkill, guess_ref, ref_init = f32(overkill), f32(guess_ref), f32(ref_init)
+    if guess_frames is not None:
+        guess_frames = guess_frames.to(device=win.device, dtype=torch.int32).contiguous()
+    D = torch.empty_like(win) if want_D else None
+    if D is not None and D.stride() != win.stride():
+        D = torch.empty_strided(win.shape, win.stride(), device=win.device, dtype=win.dtype)
+    ref = torch.empty((W,), device=win.device, dtype=torch.float32)
+    flags = (_lib.SUB_NORMALIZE if normalize else 0) | (_lib.SUB_RELU if relu else 0)
+    _lib.check(_lib.lib().saga_subtract_db_exec(
+        _ptr(win), None, win.stride(0) if W > 1 else T * P, _ptr(guesses), None,
+        Tg * P, _ptr(guess_frames), Tg, _ptr(offset_frames), _ptr(overkill), _ptr(guess_ref),
+        _ptr(ref_init), flags, _ptr(D), _ptr(ref), W, S, n_bins, T, P,
+        float(amin), float(top_db if top_db is not None else -1.0), _stream()))
+    return D, ref
+
+
+def amplitude_to_db_batch(mag_storage, n_bins, ref=None, amin=1e-5, top_db=80.0):
+    """librosa.amplitude_to_db on frame-major storage [clips, T, P]; ref: [clips]
+    tensor (negative entries => the clip's own max) or None (=> max)."""
+    _require_cuda(mag_storage, "mag")
+    m = mag_storage
+    if m.dim() == 2:
+        m = m.unsqueeze(0)
+    if m.stride(2) != 1 or m.dtype != torch.float32:
+        raise ValueError("mag must be frame-major float32 storage")
+    n_clips, T, _ = m.shape
+    P = m.stride(1)
+    D = torch.empty_strided(m.shape, m.stride(), device=m.device, dtype=torch.float32)
+    if ref is not None:
+        ref = ref.to(device=m.device, dtype=torch.float32).contiguous()
+    _lib.check(_lib.lib().saga_amplitude_to_db_exec(
+        _ptr(m), _ptr(D), _ptr(ref), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P,
+        float(amin), float(top_db if top_db is not None else -1.0), _stream()))
+    return D
+
+
+def launch_count():
+    return int(_lib.lib().saga_launch_count())

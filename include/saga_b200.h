@@ -1,0 +1,182 @@
+/*
+ * saga_b200.h -- C ABI of the B200-native AMT-SAGA feature hot path.
+ *
+ * The reference (RobertKajnak/AMT-SAGA) has no FFI of its own: the boundary of
+ * this path is the Python class util_audio.audio_complete
+ * (/root/reference/util_audio.py:32-527).  These entry points are what a ctypes
+ * binding inside that class would call (INTEGRATION.md shows the stub); each
+ * one names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C: ints, sizes, raw pointers; no torch/STL types cross the ABI.
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the caller owns all buffers; the library only owns opaque plan handles.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - return value: 0 = ok, <0 = error class below; saga_last_error_string()
+ *     gives the thread-local message.  Nothing throws across the boundary.
+ *   - spectrogram layout is FRAME-MAJOR: element (frame t, bin k) of a clip
+ *     lives at  base + t * frame_pitch + k .  Seen as [bins, frames] this is
+ *     Fortran order, which is also how librosa.stft lays out its result, so the
+ *     reference's `[bins, frames]` arrays are strided views of these buffers.
+ *     Columns k in [n_bins, frame_pitch) are padding and are written as 0.
+ */
+#ifndef SAGA_B200_H
+#define SAGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGA_OK 0
+#define SAGA_ERR_INVALID (-1)     /* bad argument (reference: ValueError / ParameterError) */
+#define SAGA_ERR_UNSUPPORTED (-2) /* valid request this build cannot run */
+#define SAGA_ERR_CUDA (-3)        /* CUDA runtime error; message has the cudaError string */
+#define SAGA_ERR_NOMEM (-4)
+
+const char* saga_last_error_string(void);
+/* library/ABI version, bumped on any signature change */
+int saga_abi_version(void);
+/* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
+int64_t saga_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * K1  batched windowed real FFT -> magnitude (/ unit phasor / complex)
+ * replaces librosa.stft + magphase reached from
+ *   util_audio.py:127-128 (F), :147 (mag, ph), :173 (ref_mag = max(mag))
+ * ---------------------------------------------------------------------- */
+typedef struct saga_stft_plan saga_stft_plan;
+
+/* n_fft in {256,...,8192} (power of two); hop >= 1; center: reflect-pad n_fft/2.
+ * window_host: n_fft floats, or NULL for the periodic Hann of librosa.stft. */
+int saga_stft_plan_create(saga_stft_plan** plan, int n_fft, int hop, int center,
+                          const float* window_host);
+int saga_stft_plan_destroy(saga_stft_plan* plan);
+
+/* number of STFT columns librosa produces for a clip of `len` samples */
+int64_t saga_stft_num_frames(const saga_stft_plan* plan, int64_t len);
+
+/* wav:            float32 samples; clip c is wav[clip_offsets[c] .. +clip_lens[c])
+ * max_len:        max over clip_lens (host knows it; sizes the grid)
+ * mag_out:        [n_clips] clips, clip c at mag_out + c*out_clip_stride, frame-major
+ * phase_out:      optional float2 (re,im) unit phasor exp(i*angle(F)), (1,0) where F==0;
+ *                 same indexing in float2 units
+ * cplx_out:       optional float2 complex STFT F
+ * frame_max_out:  optional [n_clips * max_frames] per-frame max of mag
+ *                 (max_frames = saga_stft_num_frames(plan, max_len))
+ * clip_max_out:   optional [n_clips] max of mag per clip (== audio_complete.ref_mag)
+ */
+int saga_stft_exec(const saga_stft_plan* plan, const float* wav,
+                   const int64_t* clip_offsets, const int64_t* clip_lens, int n_clips,
+                   int64_t max_len, float* mag_out, void* phase_out, void* cplx_out,
+                   int64_t frame_pitch, int64_t out_clip_stride, float* frame_max_out,
+                   float* clip_max_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K4  inverse STFT (overlap-add), replaces librosa.istft reached from
+ *   util_audio.py:92-104 (wf rebuilt from mag*ph after a subtraction)
+ * cplx_in frame-major float2 (or mag_in * phase_in when cplx_in is NULL);
+ * wav_out clip c at c*wav_clip_stride, length hop*(T-1) when centred.
+ * ---------------------------------------------------------------------- */
+int saga_istft_exec(const saga_stft_plan* plan, const void* cplx_in, const float* mag_in,
+                    const void* phase_in, int n_clips, int n_frames, int64_t frame_pitch,
+                    int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * K3  generative-subtractive chain + dB epilogue, replaces
+ *   util_audio.py:221-259 (subtract), :170-174 (ref_mag), :176-180 (D)
+ *
+ * For every window w (independent) and step j = 0..n_steps-1 (sequential):
+ *   ref   = (j == 0 && ref_init && ref_init[w] >= 0) ? ref_init[w] : max(win_w)
+ *   scale = normalize ? fl32(ref / guess_ref[w,j]) : 1      (numpy float32 semantics)
+ *   g'    = fl32(fl32(g * scale) * overkill[w,j])
+ *   win_w[:, off : off+Tg'] = relu ? max(win - g', 0) : win - g'   (Tg' clipped to T-off)
+ * then  D_w = amplitude_to_db(win_w, ref = max(win_w), amin, top_db)  if D_out.
+ * ---------------------------------------------------------------------- */
+#define SAGA_SUB_NORMALIZE 1
+#define SAGA_SUB_RELU 2
+/* caller guarantees every win/guess offset is a multiple of 4 elements (16-byte vector path) */
+#define SAGA_SUB_OFFSETS_ALIGNED 4
+
+int saga_subtract_db_exec(
+    float* win_mag,                /* in/out: window w at win_mag + win_offsets[w] (or w*win_stride) */
+    const int64_t* win_offsets,    /* optional [n_windows] element offsets */
+    int64_t win_stride,
+    const float* guess_mag,        /* guess (w,j) at guess_mag + guess_offsets[w*n_steps+j] (or idx*guess_stride) */
+    const int64_t* guess_offsets,  /* optional */
+    int64_t guess_stride,
+    const int32_t* guess_frames,   /* optional [n_windows*n_steps]; default guess_frames_all */
+    int guess_frames_all,
+    const int32_t* offset_frames,  /* [n_windows*n_steps] column offset of each guess (>= 0) */
+    const float* overkill,         /* optional [n_windows*n_steps]; default 1 */
+    const float* guess_ref,        /* optional [n_windows*n_steps] max of each guess; computed if NULL */
+    const float* ref_init,         /* optional [n_windows]; <0 or NULL => max of the window */
+    int flags,
+    float* D_out,                  /* optional, same indexing as win_mag */
+    float* ref_out,                /* optional [n_windows]: max of the final window */
+    int n_windows, int n_steps, int n_bins, int n_frames, int64_t frame_pitch,
+    float amin, float top_db, void* stream);
+
+/* stand-alone amplitude_to_db (util_audio.py:179) with an explicit per-clip ref
+ * (ref[c] < 0 or ref == NULL => ref = max of the clip) */
+int saga_amplitude_to_db_exec(const float* mag, float* D_out, const float* ref, int n_clips,
+                              int n_bins, int n_frames, int64_t frame_pitch,
+                              int64_t clip_stride, float amin, float top_db, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K2  constant-Q transform, replaces librosa.cqt reached from
+ *   util_audio.py:424-429 (slice_C)
+ *
+ * librosa's per-octave "rectangular STFT x sparsified FFT-domain basis" is
+ * linear in the (decimated) signal, so it is folded on the host into a dense
+ * real kernel bank G_o[n_fft, 2*n_filters] per octave (same numbers as
+ * librosa) and evaluated as a strided-frame GEMM
+ *   C_o[t, :] = sum_n  y_o[reflect(t*hop_o + n - n_fft/2)] * G_o[n, :]
+ * after the kaiser_fast decimation cascade.  The host-side plan builder
+ * (amt-saga_b200/cqt_plan.py) produces this descriptor.
+ * ---------------------------------------------------------------------- */
+typedef struct saga_cqt_plan saga_cqt_plan;
+
+typedef struct saga_cqt_octave {
+  int level;            /* number of 2:1 decimations after the early downsample */
+  int hop;              /* hop at this level */
+  int n_fft;            /* kernel length (power of two) */
+  int n_filters;        /* filters in this octave */
+  int first_bin;        /* output row of filter 0 (may be < 0: rows < 0 are dropped) */
+  const float* bank_host; /* [n_fft][2*n_filters] (re,im interleaved per filter), all scales folded */
+} saga_cqt_octave;
+
+typedef struct saga_cqt_desc {
+  int n_bins;
+  int hop;                 /* hop at the input rate */
+  int early_factor;        /* 1,2,4,...: single-stage decimation before the octaves */
+  int n_early_taps;        /* taps[0..n) centre first, symmetric FIR, gain folded */
+  const float* early_taps_host;
+  int n_half_taps;         /* 2:1 decimator between levels, centre first */
+  const float* half_taps_host;
+  int n_octaves;
+  const saga_cqt_octave* octaves;
+} saga_cqt_desc;
+
+int saga_cqt_plan_create(saga_cqt_plan** plan, const saga_cqt_desc* desc);
+int saga_cqt_plan_destroy(saga_cqt_plan* plan);
+/* frames librosa.cqt returns for a clip of `len` samples (min over octaves) */
+int64_t saga_cqt_num_frames(const saga_cqt_plan* plan, int64_t len);
+/* bytes of device scratch saga_cqt_exec needs for this batch shape */
+int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* plan, int n_clips, int64_t max_len);
+
+/* C_mag_out: |C| frame-major: (clip c, frame t, bin k) at c*out_clip_stride + t*frame_pitch + k
+ * C_cplx_out: optional float2 complex CQT, same indexing in float2 units
+ * impl: 0 = default (tcgen05 tensor-core path when the plan fits it), 1 = force the
+ *       fp32 CUDA-core path (validation), 2 = force tensor path (error if unsupported) */
+int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
+                  const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
+                  void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                  void* workspace, int64_t workspace_bytes, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGA_B200_H */

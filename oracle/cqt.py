@@ -98,8 +98,9 @@ def cqt_filter_fft(sr, fmin, n_bins, bins_per_octave, tuning, filter_scale,
     basis, lengths = constant_q(sr, fmin, n_bins, bins_per_octave, tuning,
                                 filter_scale, norm)
     n_fft = basis.shape[1]
-    basis = basis * (lengths[:, np.newaxis] / float(n_fft)).astype(np.float32)
-    fft_basis = np.fft.fft(basis.astype(np.complex64), n=n_fft, axis=1)[:, : (n_fft // 2) + 1]
+    # in-place `basis *= float64` on a complex64 array: computed wide, stored complex64
+    basis = (basis.astype(np.complex128) * (lengths[:, np.newaxis] / float(n_fft))).astype(np.complex64)
+    fft_basis = np.fft.fft(basis, n=n_fft, axis=1)[:, : (n_fft // 2) + 1]
     fft_basis = sparsify_rows(fft_basis, quantile=sparsity)
     return fft_basis, n_fft, lengths
 

@@ -1,0 +1,312 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same inputs.  Tolerances are BASELINE.json's: frame indexing / bin layout exact,
+magnitudes within 1e-4 of the per-clip peak, dB within 0.01 dB above the floor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cqt as ocqt
+from oracle import spectral as osp
+from oracle.audio_oracle import AudioOracle
+from tests.synth import piano_clip
+
+pytestmark = pytest.mark.gpu
+
+MAG_TOL = 1e-4      # relative to the per-clip peak (north_star)
+DB_TOL = 0.01       # dB, where the oracle is above its floor
+
+
+@pytest.fixture(scope="module")
+def saga():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops, util_audio
+    return ops, util_audio
+
+
+def dev(x):
+    return torch.as_tensor(x, device="cuda")
+
+
+def check_mag(got, ref, tol=MAG_TOL):
+    assert got.shape == ref.shape
+    peak = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()) / peak
+    assert err <= tol, "max |err| / peak = %.3e" % err
+    return err
+
+
+def check_db(got, ref, floor_margin=1e-3):
+    above = ref > (ref.max() - 80.0 + floor_margin)
+    err = float(np.abs(got[above].astype(np.float64) - ref[above]).max()) if above.any() else 0.0
+    assert err <= DB_TOL, "max dB err above the floor = %.4f" % err
+    # and the floor itself is reproduced
+    assert np.all(got >= ref.max() - 80.0 - 1e-3)
+
+
+# --------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 1024), (1024, 256), (512, 128), (256, 64), (8192, 2048)])
+def test_stft_mag_phase_cfg1(saga, cfg1, n_fft, hop):
+    ops, _ = saga
+    y, sr = cfg1
+    plan = ops.StftPlan(n_fft, hop, True)
+    r = ops.stft_batch(dev(y), plan, want_phase=True, want_complex=True)
+    F = osp.stft(y, n_fft, hop)
+    mag, ph = osp.magphase(F)
+    assert tuple(r["mag"].shape) == (1,) + mag.shape == (1, n_fft // 2 + 1, 1 + len(y) // hop)
+    check_mag(r["mag"][0].cpu().numpy(), mag)
+    check_mag(r["F"][0].cpu().numpy(), F)
+    # phase only where the magnitude is meaningfully above rounding noise
+    g = r["phase"][0].cpu().numpy()
+    big = mag > 1e-3 * mag.max()
+    assert np.abs(g[big] - ph[big]).max() < 2e-3
+    assert abs(float(r["clip_max"][0]) - float(mag.max())) <= 1e-6 * mag.max()
+    assert np.allclose(r["frame_max"][0].cpu().numpy(), mag.max(axis=0), rtol=1e-5, atol=1e-6 * mag.max())
+
+
+def test_stft_db_within_tolerance(saga, cfg1):
+    ops, _ = saga
+    y, _ = cfg1
+    for n_fft, hop in [(2048, 512), (4096, 1024)]:
+        plan = ops.StftPlan(n_fft, hop, True)
+        r = ops.stft_batch(dev(y), plan)
+        D = ops.amplitude_to_db_batch(r["mag_storage"], plan.n_bins)
+        ref_mag = np.abs(osp.stft(y, n_fft, hop))
+        ref = osp.amplitude_to_db(ref_mag, ref=ref_mag.max())
+        check_db(D[0, :, :plan.n_bins].T.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("center", [True, False])
+def test_stft_ragged_batch_and_edges(saga, center):
+    ops, _ = saga
+    rng = np.random.default_rng(3)
+    n_fft, hop = 2048, 512
+    lens = [5000, 2048, 2049, 1, 300, 44100, 1023, 4095, 0 + 2048 * 3 + 7]
+    if not center:
+        lens = [x for x in lens if x >= n_fft]
+    width = max(lens)
+    wav = np.zeros((len(lens), width), dtype=np.float32)
+    for i, n in enumerate(lens):
+        wav[i, :n] = rng.standard_normal(n).astype(np.float32) * (0.1 + i)
+    plan = ops.StftPlan(n_fft, hop, center)
+    r = ops.stft_batch(dev(wav), plan, lens=lens)
+    for i, n in enumerate(lens):
+        ref = np.abs(osp.stft(wav[i, :n], n_fft, hop, center=center))
+        T = ref.shape[1]
+        assert T == plan.num_frames(n)
+        got = r["mag"][i].cpu().numpy()
+        check_mag(got[:, :T], ref)
+        assert np.all(got[:, T:] == 0)
+
+
+def test_stft_all_zero_clip(saga):
+    ops, _ = saga
+    plan = ops.StftPlan(2048, 512, True)
+    r = ops.stft_batch(torch.zeros(1, 8000, device="cuda"), plan, want_phase=True)
+    assert float(r["mag"].abs().max()) == 0.0
+    ph = r["phase"][0].cpu().numpy()
+    assert np.all(ph == 1.0 + 0.0j)      # angle(0) = 0 -> phase 1+0j (magphase convention)
+    D = ops.amplitude_to_db_batch(r["mag_storage"], plan.n_bins)
+    assert np.all(D[0, :, :plan.n_bins].cpu().numpy() == 0.0)   # max(amin, 0) path: D == 0 everywhere
+
+
+def test_stft_piano_noise_floor_db(saga):
+    ops, _ = saga
+    y = piano_clip(11, 44100 * 2)
+    plan = ops.StftPlan(2048, 512, True)
+    r = ops.stft_batch(dev(y), plan)
+    ref = np.abs(osp.stft(y, 2048, 512))
+    check_mag(r["mag"][0].cpu().numpy(), ref)
+    D = ops.amplitude_to_db_batch(r["mag_storage"], plan.n_bins)
+    check_db(D[0, :, :plan.n_bins].T.cpu().numpy(), osp.amplitude_to_db(ref, ref=ref.max()))
+
+
+# --------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 1024), (1024, 256)])
+def test_istft_matches_oracle(saga, n_fft, hop):
+    ops, _ = saga
+    y = piano_clip(5, 30000)
+    F = osp.stft(y, n_fft, hop)
+    ref = osp.istft(F, hop)
+    plan = ops.StftPlan(n_fft, hop, True)
+    r = ops.stft_batch(dev(y), plan, want_phase=True, want_complex=True)
+    w1 = ops.istft_batch(plan, F=r["F_storage"])
+    w2 = ops.istft_batch(plan, mag=r["mag_storage"], phase=r["phase_storage"])
+    assert w1.shape[1] == ref.shape[0] == hop * (F.shape[1] - 1)
+    for w in (w1, w2):
+        assert np.abs(w[0].cpu().numpy() - ref).max() <= 2e-5 * np.abs(ref).max()
+    # round trip reproduces the interior of the signal
+    n = min(len(y), ref.shape[0])
+    assert np.abs(w1[0, n_fft:n - n_fft].cpu().numpy() - y[n_fft:n - n_fft]).max() < 1e-4
+
+
+# --------------------------------------------------------------------------- K3
+def _numpy_chain(win, guesses, offs, overkill=None):
+    """numpy float32 replay of util_audio.py:236-259 applied S times."""
+    win = win.copy()
+    for j in range(guesses.shape[0]):
+        ref, gref = np.max(win), np.max(guesses[j])
+        g = guesses[j].copy()
+        g *= ref / gref
+        if overkill is not None:
+            g *= np.float32(overkill[j])
+        off = int(offs[j])
+        T = win.shape[1]
+        if off >= T:
+            continue
+        g = g[:, : T - off]
+        pad = np.concatenate((np.zeros((win.shape[0], off)), g,
+                              np.zeros((win.shape[0], T - off - g.shape[1]))), axis=1)
+        win -= pad
+        win = np.maximum(win, 0, win)
+    return win
+
+
+@pytest.mark.parametrize("B,T,Tg,S", [(1025, 516, 128, 16), (2049, 258, 54, 3), (1025, 40, 128, 2), (129, 33, 5, 4)])
+def test_subtract_chain_bit_exact(saga, B, T, Tg, S):
+    ops, _ = saga
+    rng = np.random.default_rng(B + T)
+    W = 5
+    P = ops.frame_pitch(B)
+    win = rng.random((W, B, T), dtype=np.float32) ** 4
+    gs = rng.random((W, S, B, Tg), dtype=np.float32) ** 3
+    offs = rng.integers(0, T, size=(W, S)).astype(np.int32)
+    offs[0, 0] = 0
+    offs[1, 0] = T - 1
+    ok = (1.0 + rng.random((W, S))).astype(np.float32)
+    for overkill in (None, ok):
+        st = torch.zeros((W, T, P), device="cuda")
+        st[:, :, :B] = dev(win).transpose(1, 2)
+        g = torch.zeros((W, S, Tg, P), device="cuda")
+        g[:, :, :, :B] = dev(gs).transpose(2, 3)
+        D, ref = ops.subtract_db_batch(st, g, dev(offs), B, overkill=None if overkill is None else dev(overkill))
+        got = st[:, :, :B].transpose(1, 2).cpu().numpy()
+        for w in range(W):
+            exp = _numpy_chain(win[w], gs[w], offs[w], None if overkill is None else overkill[w])
+            assert np.array_equal(got[w], exp), "window %d differs (max %.3e)" % (w, np.abs(got[w] - exp).max())
+            assert float(ref[w]) == float(exp.max())
+            check_db(D[w, :, :B].T.cpu().numpy(), osp.amplitude_to_db(exp, ref=exp.max()))
+        assert float(st[:, :, B:].abs().max()) == 0.0
+
+
+def test_subtract_matches_oracle_class(saga):
+    """audio_complete.subtract vs the oracle container, incl. the stale song-level
+    ref_mag a `section` hands to its first subtraction (util_audio.py:323)."""
+    _, ua = saga
+    sr, N = 44100, 4096
+    song = piano_clip(21, sr * 8)
+    note = piano_clip(22, sr * 1, n_notes=1)
+    a, o = ua.audio_complete(song, N), AudioOracle(song, N)
+    a.mag, o.mag
+    aw, ow = a.section(0, None, 258), o.section(0, None, 258)
+    for onset in (0.5, 2.25, 5.9):
+        aw.subtract(ua.audio_complete(note, N), offset=onset)
+        ow.subtract(AudioOracle(note, N), offset=onset)
+        check_mag(aw.mag.cpu().numpy(), ow.mag, tol=2e-5)
+        assert abs(float(aw.ref_mag) - float(ow.ref_mag)) <= 2e-5 * float(ow.ref_mag)
+    check_db(aw.D.cpu().numpy(), ow.D)
+
+
+# --------------------------------------------------------------------------- K2
+CQT_CASES = [
+    (16000, 512, "C1", 84, 12, 160000),
+    (44100, 512, "C1", 84, 12, 66150),
+    (44100, 1024, "A0", 87, 12, 88200),
+    (44100, 1024, "A0", 174, 24, 66150),
+    (44100, 1024, "D3", 36, 24, 66150),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("sr,hop,low,n_bins,bpo,n", CQT_CASES)
+def test_cqt_matches_oracle(saga, cfg1, sr, hop, low, n_bins, bpo, n, impl):
+    ops, _ = saga
+    y = cfg1[0][:n] if sr == 16000 else piano_clip(31, n, sr=sr)
+    fmin = osp.note_to_hz(low)
+    ref = ocqt.cqt(y, sr=sr, hop_length=hop, fmin=fmin, n_bins=n_bins, bins_per_octave=bpo, filter_scale=2)
+    plan = ops.CqtPlan(sr, hop, fmin, n_bins, bpo, filter_scale=2)
+    r = ops.cqt_batch(dev(y), plan, want_complex=True, impl=impl)
+    assert tuple(r["mag"].shape) == (1,) + ref.shape
+    check_mag(r["mag"][0].cpu().numpy(), np.abs(ref))
+    check_mag(r["C"][0].cpu().numpy(), ref)
+
+
+def test_cqt_ragged_batch(saga):
+    ops, _ = saga
+    sr, hop = 44100, 512
+    fmin = osp.note_to_hz("C1")
+    plan = ops.CqtPlan(sr, hop, fmin, 84, 12, filter_scale=2)
+    lens = [30000, 44100, 12345, 700]
+    wav = np.zeros((len(lens), max(lens)), dtype=np.float32)
+    for i, n in enumerate(lens):
+        wav[i, :n] = piano_clip(40 + i, n)
+    r = ops.cqt_batch(dev(wav), plan, lens=lens)
+    for i, n in enumerate(lens):
+        ref = np.abs(ocqt.cqt(wav[i, :n], sr=sr, hop_length=hop, fmin=fmin, n_bins=84, filter_scale=2))
+        got = r["mag"][i].cpu().numpy()
+        assert plan.num_frames(n) == ref.shape[1]
+        check_mag(got[:, :ref.shape[1]], ref)
+
+
+# --------------------------------------------------------------------------- class flow
+def test_audio_complete_loop_matches_oracle(saga):
+    """The producer loop's call sequence (training.py:265-449) on both containers."""
+    _, ua = saga
+    sr, N = 44100, 4096
+    song = piano_clip(77, sr * 10)
+    note = piano_clip(78, int(sr * 1.2), n_notes=1)
+    a, o = ua.audio_complete(song, N), AudioOracle(song, N)
+    assert a.shape == o.shape
+    check_mag(a.mag.cpu().numpy(), o.mag)
+    assert abs(a.spectral_flatness() - o.spectral_flatness()) < 1e-4
+    dur = o._frames_to_seconds(o.shape[1])
+    assert a._frames_to_seconds(a.shape[1]) == dur
+    ca = a.slice_C(0, dur, a.shape[1], 8, bins_per_tone=1)
+    co = o.slice_C(0, dur, o.shape[1], 8, bins_per_tone=1)
+    check_mag(ca.cpu().numpy(), co)
+    aw, ow = a.section(0, None, 258), o.section(0, None, 258)
+    # slide half a window (training.py:318-323)
+    an, on = a.section(6, None, 129), o.section(6, None, 129)
+    aw.slice(129, 258); ow.slice(129, 258)
+    aw.concat(an); ow.concat(on)
+    assert aw.shape == ow.shape == (2049, 258)
+    check_mag(aw.mag.cpu().numpy(), ow.mag)
+    assert aw.wf.shape[0] == ow.wf.shape[0]
+    onset, d = 1.3, 0.8
+    for _ in range(2):
+        assert aw._seconds_to_frames(onset) == ow._seconds_to_frames(onset)
+        sa = aw.resize(onset, d, 8, attribs=["mag", "ph"])
+        so = ow.resize(onset, d, 8, attribs=["mag", "ph"])
+        check_mag(sa.mag.cpu().numpy(), so.mag)
+        ct = ua.audio_complete._resize(ua.audio_complete.compress_bands(aw.mag, bands=20), 258)
+        cto = AudioOracle._resize(AudioOracle.compress_bands(ow.mag, bands=20), 258)
+        check_mag(ct.cpu().numpy(), cto, tol=1e-5)
+        cp = aw.slice_C(onset, d, 8, bins_per_tone=2)
+        cpo = ow.slice_C(onset, d, 8, bins_per_tone=2)
+        assert tuple(cp.shape) == cpo.shape == (174, 8)
+        check_mag(cp.cpu().numpy(), cpo)
+        b0 = aw.midi_tone_to_FFT(60)
+        assert b0 == ow.midi_tone_to_FFT(60)
+        check_mag(sa.section_power("mag", b0, b0 + 348).cpu().numpy(), so.section_power("mag", b0, b0 + 348))
+        aw.subtract(ua.audio_complete(note, N), offset=onset)
+        ow.subtract(AudioOracle(note, N), offset=onset)
+        check_mag(aw.mag.cpu().numpy(), ow.mag, tol=2e-5)
+        # after the subtraction wf is rebuilt by an iSTFT of mag*ph: its length changes
+        assert aw.wf.shape[0] == ow.wf.shape[0] == 1024 * 257
+        check_mag(aw.wf.cpu().numpy()[None], ow.wf[None], tol=1e-4)
+        onset, d = 3.7, 1.1
+
+
+def test_numpy_carrier_and_errors(saga):
+    _, ua = saga
+    y = piano_clip(3, 20000)
+    a = ua.audio_complete(y, 2048, hop_length=512, carrier="numpy")
+    assert isinstance(a.mag, np.ndarray) and a.mag.shape == (1025, 40)
+    with pytest.raises(ValueError):
+        a._P("nope")
+    with pytest.raises(ValueError):
+        a.resize(0, 0.1, 8, attribs=["zzz"])
+    with pytest.raises(ValueError):       # librosa ParameterError is a ValueError
+        ua.audio_complete(y, 2048, hop_length=100, carrier="numpy").slice_C(0, 0.2, 8)
