@@ -42,7 +42,7 @@ SIGNATURES = {
     "saga_stft_num_frames": (_L, [_P, _L]),
     "saga_stft_exec": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _L, _P, _P, _P]),
     "saga_istft_exec": (_I, [_P, _P, _P, _P, _I, _I, _L, _L, _P, _L, _P]),
-    "saga_subtract_db_exec": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _P, _P, _P, _P, _I, _P, _P,
+    "saga_subtract_db_exec": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P,
                                    _I, _I, _I, _I, _L, _F, _F, _P]),
     "saga_amplitude_to_db_exec": (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _P]),
     "saga_cqt_plan_create": (_I, [C.POINTER(_P), C.POINTER(CqtDesc)]),

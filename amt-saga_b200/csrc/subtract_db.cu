@@ -33,6 +33,8 @@ struct SubArgs {
   const float* overkill;
   const float* guess_ref;
   const float* ref_init;
+  const float* frame_max_in;
+  int64_t frame_max_stride;
   int flags;
   float* D_out;
   float* ref_out;
@@ -88,9 +90,13 @@ __global__ void __launch_bounds__(SUB_THREADS) subtract_chain_kernel(const SubAr
   const bool normalize = (a.flags & SAGA_SUB_NORMALIZE) != 0;
 
   // ---- per-frame maxima of the incoming window --------------------------------
-  for (int t = warp; t < T; t += SUB_WARPS) {
-    const float m = row_max<VEC>(win + (int64_t)t * P, B, lane);
-    if (lane == 0) fmax_s[t] = m;
+  if (a.frame_max_in) {
+    for (int t = threadIdx.x; t < T; t += SUB_THREADS) fmax_s[t] = a.frame_max_in[(int64_t)w * a.frame_max_stride + t];
+  } else {
+    for (int t = warp; t < T; t += SUB_WARPS) {
+      const float m = row_max<VEC>(win + (int64_t)t * P, B, lane);
+      if (lane == 0) fmax_s[t] = m;
+    }
   }
   __syncthreads();
 
@@ -250,7 +256,8 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
                                      int64_t guess_stride, const int32_t* guess_frames,
                                      int guess_frames_all, const int32_t* offset_frames,
                                      const float* overkill, const float* guess_ref,
-                                     const float* ref_init, int flags, float* D_out, float* ref_out,
+                                     const float* ref_init, const float* frame_max_in,
+                                     int64_t frame_max_stride, int flags, float* D_out, float* ref_out,
                                      int n_windows, int n_steps, int n_bins, int n_frames,
                                      int64_t frame_pitch, float amin, float top_db, void* stream) {
   if (!win_mag) return set_error(SAGA_ERR_INVALID, "subtract_db_exec: null window pointer");
@@ -264,7 +271,7 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   a.guess_mag = guess_mag; a.guess_offsets = guess_offsets; a.guess_stride = guess_stride;
   a.guess_frames = guess_frames; a.guess_frames_all = guess_frames_all;
   a.offset_frames = offset_frames; a.overkill = overkill; a.guess_ref = guess_ref;
-  a.ref_init = ref_init; a.flags = flags; a.D_out = D_out; a.ref_out = ref_out;
+  a.ref_init = ref_init; a.frame_max_in = frame_max_in; a.frame_max_stride = frame_max_stride; a.flags = flags; a.D_out = D_out; a.ref_out = ref_out;
   a.n_steps = n_steps; a.n_bins = n_bins; a.n_frames = n_frames; a.frame_pitch = frame_pitch;
   a.amin = amin; a.top_db = top_db;
   // 16-byte vector path needs aligned bases and pitch; explicit offsets are checked by the caller

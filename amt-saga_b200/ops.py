@@ -234,9 +234,10 @@ def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0):
 # ---------------------------------------------------------------------------
 def subtract_db_batch(win, guesses, offset_frames, n_bins, overkill=None, guess_ref=None,
                       ref_init=None, guess_frames=None, normalize=True, relu=True, want_D=True,
-                      amin=1e-5, top_db=80.0):
+                      amin=1e-5, top_db=80.0, frame_max=None, D_out=None):
     """K3 on frame-major storage.
         win      [W, T, P] float32, modified in place (P = frame pitch >= n_bins)
+        frame_max optional [W, >=T] per-frame maxima of `win` (stft_batch's by-product)
         guesses  [W, S, Tg, P] float32 (S sequential steps per window)
         offset_frames [W, S] int32 column offsets
     Returns (D storage [W, T, P] or None, ref [W] = max of each final window)."""
@@ -259,15 +260,25 @@ def subtract_db_batch(win, guesses, offset_frames, n_bins, overkill=None, guess_
     overkill, guess_ref, ref_init = f32(overkill), f32(guess_ref), f32(ref_init)
     if guess_frames is not None:
         guess_frames = guess_frames.to(device=win.device, dtype=torch.int32).contiguous()
-    D = torch.empty_like(win) if want_D else None
-    if D is not None and D.stride() != win.stride():
-        D = torch.empty_strided(win.shape, win.stride(), device=win.device, dtype=win.dtype)
+    D = None
+    if want_D:
+        D = D_out if D_out is not None else torch.empty_strided(win.shape, win.stride(), device=win.device,
+                                                               dtype=win.dtype)
+        if D.stride() != win.stride() or D.shape != win.shape:
+            raise ValueError("D_out must have the window tensor's shape and strides")
+    fm_stride = 0
+    if frame_max is not None:
+        _require_cuda(frame_max, "frame_max")
+        if frame_max.dim() != 2 or frame_max.shape[0] != W or frame_max.shape[1] < T or \
+                frame_max.stride(1) != 1 or frame_max.dtype != torch.float32:
+            raise ValueError("frame_max must be float32 [W, >=T]")
+        fm_stride = frame_max.stride(0)
     ref = torch.empty((W,), device=win.device, dtype=torch.float32)
     flags = (_lib.SUB_NORMALIZE if normalize else 0) | (_lib.SUB_RELU if relu else 0)
     _lib.check(_lib.lib().saga_subtract_db_exec(
         _ptr(win), None, win.stride(0) if W > 1 else T * P, _ptr(guesses), None,
         Tg * P, _ptr(guess_frames), Tg, _ptr(offset_frames), _ptr(overkill), _ptr(guess_ref),
-        _ptr(ref_init), flags, _ptr(D), _ptr(ref), W, S, n_bins, T, P,
+        _ptr(ref_init), _ptr(frame_max), fm_stride, flags, _ptr(D), _ptr(ref), W, S, n_bins, T, P,
         float(amin), float(top_db if top_db is not None else -1.0), _stream()))
     return D, ref
 

@@ -1,0 +1,140 @@
+"""One pass of the feature hot path over a batch of 6 s analysis windows with
+every buffer preallocated: the unit BASELINE.json's metric counts.
+
+Per window (reference flow, training.py:265-449 restricted to the hot path):
+    K1  STFT magnitude of the window audio          (util_audio.py:127-148)
+    K2  constant-Q magnitudes of the window audio   (util_audio.py:424-429)
+    K1  STFT magnitude of the rendered guessed note (util_audio.py:237)
+    K3  align / scale / subtract / ReLU, then dB    (util_audio.py:238-259, :179)
+
+The window is the first `n_frames` STFT columns of its clip, which is what
+`section(..., duration_in_frames=timing_frames)` (training.py:284) keeps.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .util_audio import note_to_hz
+
+
+def seconds_to_frames(time, n_frames, sr, wf_len):
+    """util_audio.py:264, same float64 operation order."""
+    return int(np.floor(time * n_frames * sr / wf_len))
+
+
+class WindowFeaturePipeline:
+    def __init__(self, n_windows, window_samples=264600, guess_samples=65024, sr=44100,
+                 n_fft=2048, hop=512, cqt_lowest="C1", cqt_bins=84, cqt_bpo=12, n_frames=None,
+                 device=None, cqt_impl=0):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.W, self.ns, self.ng, self.sr = n_windows, window_samples, guess_samples, sr
+        self.stft = ops.get_stft_plan(n_fft, hop, True)
+        self.cqt = ops.get_cqt_plan(sr, hop, note_to_hz(cqt_lowest), cqt_bins, cqt_bpo, 2)
+        self.cqt_impl = cqt_impl
+        self.nb = self.stft.n_bins
+        self.P = ops.frame_pitch(self.nb)
+        self.T_clip = self.stft.num_frames(window_samples)          # 517 for 6 s @ 2048/512
+        self.T = n_frames if n_frames is not None else int(window_samples // hop)   # 516 = int(6*sr/hop)
+        if self.T > self.T_clip:
+            raise ValueError("window frames exceed the clip's STFT columns")
+        self.Tg = self.stft.num_frames(guess_samples)
+        self.Tc = self.cqt.num_frames(window_samples)
+        self.Pc = ops.frame_pitch(cqt_bins)
+        d, f32 = self.dev, torch.float32
+        W = n_windows
+        self.mag = torch.empty((W, self.T_clip, self.P), device=d, dtype=f32)
+        self.D = torch.empty((W, self.T_clip, self.P), device=d, dtype=f32)
+        self.frame_max = torch.empty((W, self.T_clip), device=d, dtype=f32)
+        self.clip_max = torch.empty((W,), device=d, dtype=f32)
+        self.gmag = torch.empty((W, 1, self.Tg, self.P), device=d, dtype=f32)
+        self.gmax = torch.empty((W,), device=d, dtype=f32)
+        self.C = torch.empty((W, self.Tc, self.Pc), device=d, dtype=f32)
+        self.ref = torch.empty((W,), device=d, dtype=f32)
+        self.offs_w = torch.arange(W, device=d, dtype=torch.int64) * window_samples
+        self.lens_w = torch.full((W,), window_samples, device=d, dtype=torch.int64)
+        self.offs_g = torch.arange(W, device=d, dtype=torch.int64) * guess_samples
+        self.lens_g = torch.full((W,), guess_samples, device=d, dtype=torch.int64)
+        lib = _lib.lib()
+        nbytes = lib.saga_cqt_workspace_bytes(self.cqt.handle, W, window_samples)
+        self.ws = torch.empty(((nbytes + 255) // 256) * 256, device=d, dtype=torch.uint8)
+        self._lib = lib
+        # host side of the e2e path (pinned), allocated on demand
+        self._host = None
+
+    # algorithmic work per window (DESIGN.md / SURVEY.md section 8d)
+    def stft_bytes_per_window(self):
+        return 4 * (self.ns + self.T_clip * self.nb) + 4 * (self.ng + self.Tg * self.nb)
+
+    def subtract_bytes_per_window(self):
+        return 4 * self.nb * (2 * self.T + self.Tg)          # read mag + read guess + write one output
+
+    def cqt_flops_per_window(self):
+        return self.Tc * sum(8 * o["n_filters"] * (o["n_fft"] // 2 + 1) for o in self.cqt.octaves)
+
+    def run(self, wav, guess_wav, offset_frames, events=None):
+        """wav [W, window_samples], guess_wav [W, guess_samples] CUDA float32 contiguous,
+        offset_frames [W,1] int32 CUDA.  Results land in self.mag (subtracted,
+        in place), self.D, self.C, self.ref.  `events`: optional list that
+        receives (stage, start_event, end_event) on the current stream."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib, W = self._lib, self.W
+
+        def stage(name, fn):
+            if events is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            events.append((name, a, b))
+
+        stage("stft", lambda: _lib.check(lib.saga_stft_exec(
+            self.stft.handle, p(wav), p(self.offs_w), p(self.lens_w), W, self.ns, p(self.mag), None, None,
+            self.P, self.T_clip * self.P, p(self.frame_max), p(self.clip_max), st)))
+        stage("cqt", lambda: _lib.check(lib.saga_cqt_exec(
+            self.cqt.handle, p(wav), p(self.offs_w), p(self.lens_w), W, self.ns, p(self.C), None,
+            self.Pc, self.Tc * self.Pc, p(self.ws), self.ws.numel(), self.cqt_impl, st)))
+        stage("stft_guess", lambda: _lib.check(lib.saga_stft_exec(
+            self.stft.handle, p(guess_wav), p(self.offs_g), p(self.lens_g), W, self.ng, p(self.gmag), None,
+            None, self.P, self.Tg * self.P, None, p(self.gmax), st)))
+        stage("subtract_db", lambda: _lib.check(lib.saga_subtract_db_exec(
+            p(self.mag), None, self.T_clip * self.P, p(self.gmag), None, self.Tg * self.P, None, self.Tg,
+            p(offset_frames), None, p(self.gmax), p(self.clip_max), p(self.frame_max), self.T_clip,
+            _lib.SUB_NORMALIZE | _lib.SUB_RELU, p(self.D), p(self.ref), W, 1, self.nb, self.T, self.P,
+            1e-5, 80.0, st)))
+
+    # ---- end-to-end: host buffers in, host results out -----------------------------
+    def host_buffers(self):
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = dict(
+                wav=torch.empty((self.W, self.ns), dtype=torch.float32, **pin),
+                guess=torch.empty((self.W, self.ng), dtype=torch.float32, **pin),
+                offs=torch.empty((self.W, 1), dtype=torch.int32, **pin),
+                C=torch.empty((self.W, self.Tc, self.Pc), dtype=torch.float32, **pin),
+                ref=torch.empty((self.W,), dtype=torch.float32, **pin),
+                d_wav=torch.empty((self.W, self.ns), device=self.dev, dtype=torch.float32),
+                d_guess=torch.empty((self.W, self.ng), device=self.dev, dtype=torch.float32),
+                d_offs=torch.empty((self.W, 1), device=self.dev, dtype=torch.int32))
+        return self._host
+
+    def run_host(self):
+        """Pinned host inputs -> device -> hot path -> features back on the host
+        (CQT magnitudes + post-subtraction ref_mag; the subtracted window and its dB
+        image stay resident for the next loop iteration, as in training.py:449)."""
+        h = self.host_buffers()
+        h["d_wav"].copy_(h["wav"], non_blocking=True)
+        h["d_guess"].copy_(h["guess"], non_blocking=True)
+        h["d_offs"].copy_(h["offs"], non_blocking=True)
+        self.run(h["d_wav"], h["d_guess"], h["d_offs"])
+        h["C"].copy_(self.C, non_blocking=True)
+        h["ref"].copy_(self.ref, non_blocking=True)
+
+    def h2d_bytes(self):
+        return 4 * self.W * (self.ns + self.ng + 1)
+
+    def d2h_bytes(self):
+        return 4 * self.W * (self.Tc * self.Pc + 1)

@@ -113,6 +113,10 @@ int saga_subtract_db_exec(
     const float* overkill,         /* optional [n_windows*n_steps]; default 1 */
     const float* guess_ref,        /* optional [n_windows*n_steps] max of each guess; computed if NULL */
     const float* ref_init,         /* optional [n_windows]; <0 or NULL => max of the window */
+    const float* frame_max_in,     /* optional per-frame maxima of the incoming windows (K1's
+                                      frame_max_out): window w, frame t at [w*frame_max_stride + t];
+                                      saves the initial full-window pass */
+    int64_t frame_max_stride,
     int flags,
     float* D_out,                  /* optional, same indexing as win_mag */
     float* ref_out,                /* optional [n_windows]: max of the final window */

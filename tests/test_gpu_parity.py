@@ -33,7 +33,8 @@ def dev(x):
 def check_mag(got, ref, tol=MAG_TOL):
     assert got.shape == ref.shape
     peak = max(float(np.abs(ref).max()), 1e-30)
-    err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()) / peak
+    wide = np.complex128 if (np.iscomplexobj(got) or np.iscomplexobj(ref)) else np.float64
+    err = float(np.abs(got.astype(wide) - ref.astype(wide)).max()) / peak
     assert err <= tol, "max |err| / peak = %.3e" % err
     return err
 
@@ -310,3 +311,32 @@ def test_numpy_carrier_and_errors(saga):
         a.resize(0, 0.1, 8, attribs=["zzz"])
     with pytest.raises(ValueError):       # librosa ParameterError is a ValueError
         ua.audio_complete(y, 2048, hop_length=100, carrier="numpy").slice_C(0, 0.2, 8)
+
+
+# --------------------------------------------------------------------------- pipeline (bench unit)
+def test_window_pipeline_matches_oracle(saga):
+    """The bench's step on 3 full-size 6 s windows vs the oracle, incl. the
+    song-level ref handed to the first subtraction and K1's frame maxima reuse."""
+    from amt_saga_b200.pipeline import WindowFeaturePipeline
+    sr, n_fft, hop, ns, ng = 44100, 2048, 512, 264600, 65024
+    W = 3
+    pipe = WindowFeaturePipeline(W, ns, ng, sr, n_fft, hop)
+    wav = np.stack([piano_clip(500 + i, ns) for i in range(W)])
+    gue = np.stack([piano_clip(600 + i, ng, n_notes=1) for i in range(W)])
+    offs = np.array([[0], [200], [500]], dtype=np.int32)
+    pipe.run(dev(wav), dev(gue), dev(offs))
+    torch.cuda.synchronize()
+    assert (pipe.T, pipe.T_clip, pipe.Tg, pipe.Tc) == (516, 517, 128, 517)
+    for w in range(W):
+        full = np.abs(osp.stft(wav[w], n_fft, hop))
+        mag = full[:, :516].copy()
+        g = np.abs(osp.stft(gue[w], n_fft, hop))
+        g *= full.max() / g.max()
+        g = g[:, :516 - offs[w, 0]]
+        mag[:, offs[w, 0]:offs[w, 0] + g.shape[1]] -= g
+        np.maximum(mag, 0, mag)
+        check_mag(pipe.mag[w, :516, :1025].T.cpu().numpy(), mag, tol=2e-5)
+        check_db(pipe.D[w, :516, :1025].T.cpu().numpy(), osp.amplitude_to_db(mag, ref=mag.max()))
+        assert abs(float(pipe.ref[w]) - mag.max()) <= 2e-5 * mag.max()
+        C = np.abs(ocqt.cqt(wav[w], sr=sr, hop_length=hop, fmin=osp.note_to_hz("C1"), n_bins=84, filter_scale=2))
+        check_mag(pipe.C[w, :, :84].T.cpu().numpy(), C)
