@@ -351,9 +351,9 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.clip_frames = clip_frames;
   if (impl != 1) {
     int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
-                           out_clip_stride, st);
+                           out_clip_stride, impl == 3 ? 1 : 3, st);
     if (rc == SAGA_OK) return SAGA_OK;
-    if (rc != SAGA_ERR_UNSUPPORTED || impl == 2) return rc;
+    if (rc != SAGA_ERR_UNSUPPORTED || impl >= 2) return rc;
   }
   bool first = true;
   for (auto& o : p->oct) {

@@ -43,6 +43,6 @@ void cqt_umma_plan_free(saga_cqt_plan* p);
 // returns SAGA_ERR_UNSUPPORTED when the plan does not fit the tensor path
 int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t max_len,
                   int64_t T_max, float* mag_out, float2* cplx_out, int64_t frame_pitch,
-                  int64_t out_clip_stride, cudaStream_t st);
+                  int64_t out_clip_stride, int n_split, cudaStream_t st);
 
 }  // namespace saga

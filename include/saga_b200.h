@@ -173,8 +173,10 @@ int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* plan, int n_clips, int64_t
 
 /* C_mag_out: |C| frame-major: (clip c, frame t, bin k) at c*out_clip_stride + t*frame_pitch + k
  * C_cplx_out: optional float2 complex CQT, same indexing in float2 units
- * impl: 0 = default (tcgen05 tensor-core path when the plan fits it), 1 = force the
- *       fp32 CUDA-core path (validation), 2 = force tensor path (error if unsupported) */
+ * impl: 0 = default (tcgen05 tensor-core path, 3xTF32 split = fp32-grade accuracy, when the
+ *       plan fits it, else the fp32 CUDA-core path), 1 = force the fp32 CUDA-core path
+ *       (validation), 2 = force the tensor path (SAGA_ERR_UNSUPPORTED if it does not fit),
+ *       3 = tensor path with a single TF32 pass (~3e-5 of peak) */
 int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
                   const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
                   void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,

@@ -220,18 +220,26 @@ CQT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+# impl: 1 = fp32 CUDA-core contraction, 2 = tcgen05 3xTF32 (fp32-grade), 3 = tcgen05 single TF32
+@pytest.mark.parametrize("impl", [1, 2, 3, 0])
 @pytest.mark.parametrize("sr,hop,low,n_bins,bpo,n", CQT_CASES)
 def test_cqt_matches_oracle(saga, cfg1, sr, hop, low, n_bins, bpo, n, impl):
     ops, _ = saga
+    from amt_saga_b200._lib import SagaUnsupported
     y = cfg1[0][:n] if sr == 16000 else piano_clip(31, n, sr=sr)
     fmin = osp.note_to_hz(low)
     ref = ocqt.cqt(y, sr=sr, hop_length=hop, fmin=fmin, n_bins=n_bins, bins_per_octave=bpo, filter_scale=2)
     plan = ops.CqtPlan(sr, hop, fmin, n_bins, bpo, filter_scale=2)
-    r = ops.cqt_batch(dev(y), plan, want_complex=True, impl=impl)
+    try:
+        r = ops.cqt_batch(dev(y), plan, want_complex=True, impl=impl)
+    except SagaUnsupported:
+        pytest.skip("bank does not fit the resident-B tensor path (falls back to fp32 under impl=0)")
     assert tuple(r["mag"].shape) == (1,) + ref.shape
-    check_mag(r["mag"][0].cpu().numpy(), np.abs(ref))
-    check_mag(r["C"][0].cpu().numpy(), ref)
+    # fp32 path ~1e-6; 3xTF32 ~3e-6 (tensor-core accumulation); both far inside the 1e-4 bar.
+    # impl=3 (single TF32 pass) measures ~1.1e-4: NOT parity-grade, opt-in only, checked loosely.
+    tol = {1: 2e-6, 2: 1e-5, 0: 1e-5, 3: 3e-4}[impl]
+    check_mag(r["mag"][0].cpu().numpy(), np.abs(ref), tol=tol)
+    check_mag(r["C"][0].cpu().numpy(), ref, tol=tol)
 
 
 def test_cqt_ragged_batch(saga):
