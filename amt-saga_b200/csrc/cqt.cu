@@ -73,6 +73,84 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   }
 }
 
+// Factor-2 specialisation (the kaiser_fast 2:1 stage: 63 taps, S = 31).  The staged tile is split
+// into its even and odd samples (polyphase form): output o needs xe[o-15 .. o+15] and xo[o-16 .. o+15],
+// i.e. unit-stride windows, so a thread producing 4 consecutive outputs pulls two 9 x float4 register
+// windows at a 16-byte lane stride (bank-conflict free) and the kernel is FMA-bound rather than
+// one shared load per MAC.  Taps live in registers; symmetric pairs are pre-added.
+constexpr int DEC2_THREADS = 256;
+constexpr int DEC2_OUT = 4;                         // outputs per thread
+constexpr int DEC2_S = 31;
+constexpr int DEC2_TILE = DEC2_THREADS * DEC2_OUT;  // outputs per CTA
+constexpr int DEC2_HALF = DEC2_TILE + 32;           // even (or odd) samples staged per CTA
+
+__global__ void __launch_bounds__(DEC2_THREADS)
+decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
+                 const int64_t* __restrict__ clip_lens, int in_shift, int in_factor_total,
+                 float* __restrict__ out, int64_t out_stride, const float* __restrict__ taps) {
+  // tile covers input samples [2*o0 - 32, 2*o0 + 2*TILE + 32)
+  __shared__ __align__(16) float xe[DEC2_HALF + 4];
+  __shared__ __align__(16) float xo[DEC2_HALF + 4];
+  const int clip = blockIdx.y;
+  int64_t len = clip_lens[clip];
+  if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;
+  for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;
+  const int64_t n_full = len >> 1, n_out = (len + 1) >> 1;
+  const int64_t o0 = (int64_t)blockIdx.x * DEC2_TILE;
+  if (o0 >= n_out) return;
+  const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
+  const int64_t i0 = 2 * o0 - 32;
+  constexpr int NIN = 2 * DEC2_HALF;
+  if (i0 >= 0 && i0 + NIN <= len && ((reinterpret_cast<uintptr_t>(x + i0) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(x + i0);
+    for (int i = threadIdx.x; i < NIN / 4; i += DEC2_THREADS) {
+      const float4 v = __ldg(src + i);
+      *reinterpret_cast<float2*>(xe + 2 * i) = make_float2(v.x, v.z);
+      *reinterpret_cast<float2*>(xo + 2 * i) = make_float2(v.y, v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < NIN; i += DEC2_THREADS) {
+      const int64_t s = i0 + i;
+      const float v = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+      if (i & 1) xo[i >> 1] = v; else xe[i >> 1] = v;
+    }
+  }
+  float tp[DEC2_S + 1];
+#pragma unroll
+  for (int m = 0; m <= DEC2_S; ++m) tp[m] = __ldg(taps + m);
+  __syncthreads();
+  // output lo = 4*tid + u has its centre at even index c = lo + 16
+  float we[36], wo[36];
+  const float4* es = reinterpret_cast<const float4*>(xe + 4 * threadIdx.x);
+  const float4* os = reinterpret_cast<const float4*>(xo + 4 * threadIdx.x);
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const float4 a = es[j], b = os[j];
+    we[4 * j] = a.x; we[4 * j + 1] = a.y; we[4 * j + 2] = a.z; we[4 * j + 3] = a.w;
+    wo[4 * j] = b.x; wo[4 * j + 1] = b.y; wo[4 * j + 2] = b.z; wo[4 * j + 3] = b.w;
+  }
+  float acc[DEC2_OUT];
+#pragma unroll
+  for (int u = 0; u < DEC2_OUT; ++u) {
+    const int c = u + 16;
+    float r = tp[0] * we[c];
+#pragma unroll
+    for (int j = 1; j <= 15; ++j) r = fmaf(tp[2 * j], we[c - j] + we[c + j], r);       // even taps m = +-2j
+#pragma unroll
+    for (int j = 0; j <= 15; ++j) r = fmaf(tp[2 * j + 1], wo[c + j] + wo[c - 1 - j], r);  // odd taps m = 2j+1, -(2j+1)
+    acc[u] = r;
+  }
+  float* y = out + (int64_t)clip * out_stride;
+  const int64_t ob = o0 + 4 * (int64_t)threadIdx.x;
+  if (ob + 3 < n_full && ((reinterpret_cast<uintptr_t>(y + ob) & 15) == 0)) {
+    *reinterpret_cast<float4*>(y + ob) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < DEC2_OUT; ++u)
+      if (ob + u < n_out) y[ob + u] = (ob + u < n_full) ? acc[u] : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // fp32 contraction: CTA = 128 frames x FC output columns of one (clip, octave)
 // ---------------------------------------------------------------------------
@@ -329,8 +407,14 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
     if (smem > 48 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
-                                                     p->d_early_taps, p->n_early_taps, p->early_factor);
+    if (p->early_factor == 2 && p->n_early_taps == DEC2_S + 1) {
+      dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
+                                                    p->d_early_taps);
+    } else {
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
+                                                       p->d_early_taps, p->n_early_taps, p->early_factor);
+    }
     SAGA_LAUNCH_CHECK();
   }
   for (int l = 1; l <= p->max_level; ++l) {
@@ -338,10 +422,17 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
     const size_t smem = sizeof(float) * (((p->n_half_taps + 3) & ~3) + tile_out * 2 + 2 * (p->n_half_taps - 1));
     const bool from_wav = (l == 1 && p->early_factor == 1);
-    decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
-                                                     from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
-                                                     p->early_factor, lvl[l], pitch[l], p->d_half_taps,
-                                                     p->n_half_taps, 2);
+    if (p->n_half_taps == DEC2_S + 1) {
+      dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
+                                                    from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
+                                                    p->early_factor, lvl[l], pitch[l], p->d_half_taps);
+    } else {
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
+                                                       from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
+                                                       p->early_factor, lvl[l], pitch[l], p->d_half_taps,
+                                                       p->n_half_taps, 2);
+    }
     SAGA_LAUNCH_CHECK();
   }
 

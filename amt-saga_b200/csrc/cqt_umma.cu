@@ -16,12 +16,20 @@
 // Every sample is fetched from L2 once per tile instead of n_fft/hop times.
 //
 // fp32 accuracy on TF32 tensor cores: operands are split x = hi + lo (both
-// TF32, round-to-nearest) and three MMAs hi*hi + lo*hi + hi*lo accumulate in
-// fp32 TMEM (n_split = 3); n_split = 1 keeps only hi*hi.
+// TF32, round-to-nearest) and hi*hi + hi*lo + lo*hi is accumulated in fp32
+// TMEM (n_split = 3).  The bank is packed [B_hi | B_lo] along N, so per K-slice
+// ONE N=2*npad MMA (A_hi x [B_hi|B_lo]) plus one N=npad MMA (A_lo x B_hi) do the
+// work of three; the epilogue adds the two column groups.  n_split = 1 keeps
+// only hi*hi.  N is tiny here (24 real columns per octave), so the kernel is
+// bound by how fast ONE thread can issue MMAs: descriptors are built once per
+// stage and advanced by adding to their low word.
 //
 // Warp roles per persistent CTA (one per SM): 8 producer warps (global -> split
-// -> planes), 1 MMA issuer (single elected thread), 4 epilogue warps
-// (tcgen05.ld -> |re + i im| -> global).  mbarrier pipelines: smem full/empty per
+// -> planes), 4 MMA issuer warps (one elected thread each; K-slices dealt round
+// robin, each warp accumulating into its own TMEM column group, because with
+// N <= 64 an MMA retires in 16-32 cycles and a single issuing thread cannot keep
+// up -- profiles/microbench/umma_latency.cu), 4 epilogue warps (tcgen05.ld, sum of
+// the column groups, |re + i im| -> global).  mbarrier pipelines: smem full/empty per
 // A stage, TMEM full/empty per accumulator buffer.  The bank G_o (packed for the
 // B descriptor on the host) stays resident in SMEM while the CTA works through
 // items of one octave (items are ordered octave-major).
@@ -37,9 +45,10 @@ namespace saga {
 constexpr int UM_TILE_M = 128;
 constexpr int UM_PRODUCER_WARPS = 8;
 constexpr int UM_EPI_WARPS = 4;
-constexpr int UM_THREADS = 32 * (1 + UM_EPI_WARPS + UM_PRODUCER_WARPS);   // warp0 = MMA, 1-4 epilogue, 5-12 producers
-constexpr int UM_STAGES = 2;
-constexpr int UM_PLANES_PER_STAGE = 8;      // 8 planes x 4 samples = 32 k-values per shift
+constexpr int UM_MMA_WARPS = 4;             // issuer warps: K-slices round-robin, one TMEM column group each
+constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_PRODUCER_WARPS);   // 0-3 MMA, 4-7 epilogue, 8-15 producers
+constexpr int UM_STAGES = 4;
+constexpr int UM_PLANES_PER_STAGE = 4;      // 4 planes x 4 samples = 16 k-values per shift
 constexpr int UM_MAX_OCT = 12;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
 
@@ -47,10 +56,9 @@ struct UmmaOct {
   const float* sig;
   const int64_t* sig_offsets;
   int64_t sig_stride;
-  const float* b_hi;      // packed [n_fft/4][npad][4]
-  const float* b_lo;
+  const float* b_pack;    // packed [n_fft/4][2*npad][4]: rows [0,npad) = TF32 hi, [npad,2npad) = lo
   int level, hop, n_fft, ncol, npad, first_bin;
-  int planes, n_stages, Q, rows, rows_pad;
+  int planes, np_log2, n_stages, Q, rows, rows_pad;
   int64_t item_begin;
 };
 
@@ -63,10 +71,11 @@ struct UmmaArgs {
   float* mag_out;
   float2* cplx_out;
   int64_t frame_pitch, out_clip_stride;
-  uint32_t b_region_bytes;   // one of hi / lo
+  uint32_t b_region_bytes;   // resident bank (hi and lo rows interleaved per K-chunk)
   uint32_t a_region_bytes;   // one of hi / lo, per stage
   uint32_t tmem_cols;        // allocation (power of two >= 2*npad_max)
   uint32_t acc_stride;       // columns between the two accumulator buffers
+  uint32_t grp_stride;       // columns between issuer-warp column groups (2*npad_max)
   int* error_flag;
 };
 
@@ -101,21 +110,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     }
   }
 }
+// MMA-warp variant: returns with the warp converged, so what follows is uniform code
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int* error_flag) {
+  mbar_wait(bar, parity, error_flag);
+  __syncwarp();
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {   // whole warp calls, one lane issues
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xFFFFFFFF;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
+// Issued by ONE elected lane, but called by the whole (converged) MMA warp with warp-uniform
+// operands: that keeps descriptors in uniform registers (UIADD3 + UTCHMMA per MMA) instead of a
+// per-instruction R2UR waterfall -- with N = 32..64 the tensor pipe needs a new MMA every 16-32 cycles.
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xFFFFFFFF;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -165,9 +186,8 @@ __device__ __forceinline__ ItemInfo decode_item(const UmmaArgs& a, int64_t item)
 
 __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* b_hi_s = smem_raw;
-  uint8_t* b_lo_s = b_hi_s + a.b_region_bytes;
-  uint8_t* a_base = b_lo_s + a.b_region_bytes;                  // stages: [hi | lo] x UM_STAGES
+  uint8_t* b_s = smem_raw;
+  uint8_t* a_base = b_s + a.b_region_bytes;                     // stages: [hi | lo] x UM_STAGES
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + 2 * UM_STAGES * a.a_region_bytes);
   uint64_t* full = bars;                    // [UM_STAGES]
   uint64_t* empty = bars + UM_STAGES;       // [UM_STAGES]
@@ -180,10 +200,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < UM_STAGES; ++s) {
       mbar_init(&full[s], UM_PRODUCER_WARPS);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], UM_MMA_WARPS);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull[s], 1);
+      mbar_init(&tfull[s], UM_MMA_WARPS);
       mbar_init(&tempty[s], UM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,78 +217,81 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
   const int64_t G = gridDim.x;
 
-  if (warp == 0) {
-    // =========================== MMA issuer ===========================
+  if (warp < UM_MMA_WARPS) {
+    // =========================== MMA issuers ===========================
     uint32_t it_stage = 0, it_acc = 0;
     for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
       const ItemInfo inf = decode_item(a, item);
       if (inf.t0 >= inf.T) continue;
       const UmmaOct& oc = a.oct[inf.o];
-      // instruction descriptor: D=f32, A=B=tf32, K-major both, N = npad, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(oc.npad >> 3) << 17) |
-                             ((uint32_t)(UM_TILE_M >> 4) << 24);
+      // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128; N = 2*npad (hi|lo) and N = npad
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UM_TILE_M >> 4) << 24);
+      const uint32_t idesc_n1 = idesc_base | ((uint32_t)(oc.npad >> 3) << 17);
+      const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * oc.npad) >> 3) << 17);
       const uint32_t acc = it_acc & 1;
-      mbar_wait(&tempty[acc], ((it_acc >> 1) & 1) ^ 1, a.error_flag);
+      mbar_wait_warp(&tempty[acc], ((it_acc >> 1) & 1) ^ 1, a.error_flag);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * a.acc_stride;
-      const uint32_t plane_bytes = (uint32_t)oc.rows_pad * 16u;
-      const uint32_t b_chunk_bytes = (uint32_t)oc.npad * 16u;
-      uint32_t first = 1;
+      const uint32_t d_tmem = tmem_base + acc * a.acc_stride + (uint32_t)warp * a.grp_stride;
+      const uint32_t plane16 = (uint32_t)oc.rows_pad;          // plane pitch in 16-byte units
+      const uint32_t bchunk16 = 2u * (uint32_t)oc.npad;        // K-chunk pitch of the bank in 16-byte units
+      const bool split = (a.n_split == 3);
+      const uint32_t idesc_main = split ? idesc_n2 : idesc_n1;
+      const uint64_t db0 = smem_desc(smem_u32(b_s), bchunk16 * 16u, 128);
+      uint32_t accum = 0;
+      int rr = warp;      // next K-slice (within the current stage) owned by this warp
       for (int st = 0; st < oc.n_stages; ++st, ++it_stage) {
         const uint32_t s = it_stage % UM_STAGES;
-        mbar_wait(&full[s], (it_stage / UM_STAGES) & 1, a.error_flag);
+        mbar_wait_warp(&full[s], (it_stage / UM_STAGES) & 1, a.error_flag);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t ah = smem_u32(a_base + (2 * s) * a.a_region_bytes);
           const uint32_t al = smem_u32(a_base + (2 * s + 1) * a.a_region_bytes);
-          const uint32_t bh = smem_u32(b_hi_s), bl = smem_u32(b_lo_s);
-          const int g0 = st * UM_PLANES_PER_STAGE;
-          const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
           if (oc.planes >= 2) {
-            for (int q = 0; q < oc.Q; ++q) {
-              for (int p = 0; p < np; p += 2) {
-                const uint32_t a_off = (uint32_t)p * plane_bytes + (uint32_t)q * 16u;
-                const uint32_t ck = (uint32_t)(q * oc.planes + g0 + p);
-                const uint64_t dah = smem_desc(ah + a_off, plane_bytes, 128);
-                const uint64_t dbh = smem_desc(bh + ck * b_chunk_bytes, b_chunk_bytes, 128);
-                tc_mma_tf32(d_tmem, dah, dbh, idesc, first ? 0u : 1u);
-                first = 0;
-                if (a.n_split == 3) {
-                  const uint64_t dal = smem_desc(al + a_off, plane_bytes, 128);
-                  const uint64_t dbl = smem_desc(bl + ck * b_chunk_bytes, b_chunk_bytes, 128);
-                  tc_mma_tf32(d_tmem, dal, dbh, idesc, 1u);
-                  tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                }
-              }
+            const uint64_t dah0 = smem_desc(ah, plane16 * 16u, 128);
+            const uint64_t dal0 = smem_desc(al, plane16 * 16u, 128);
+            const int g0 = st * UM_PLANES_PER_STAGE;
+            const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+            const int np2_log = (np == 4) ? 1 : 0;                  // plane pairs per shift: 2 or 1
+            const int n_slices = oc.Q << np2_log;
+            const uint32_t bq = (uint32_t)oc.planes * bchunk16;
+            // this warp's K-slices: sl = warp, warp + 4, ...;  sl -> (shift q, plane pair p)
+            int sl = rr;
+            for (; sl < n_slices; sl += UM_MMA_WARPS) {
+              const uint32_t q = (uint32_t)(sl >> np2_log);
+              const uint32_t pp = (uint32_t)(sl & ((1 << np2_log) - 1)) * 2u;
+              const uint32_t a_off = pp * plane16 + q;
+              const uint64_t db = db0 + (uint64_t)(q * bq + ((uint32_t)g0 + pp) * bchunk16);
+              tc_mma_tf32(d_tmem, dah0 + a_off, db, idesc_main, accum);
+              accum = 1;
+              if (split) tc_mma_tf32(d_tmem, dal0 + a_off, db, idesc_n1, 1u);
             }
+            rr = sl - n_slices;
           } else {
-            // hop == 4: one plane; the two K-chunks of an MMA are shifts q and q+1
-            for (int q = 0; q < oc.Q; q += 2) {
-              const uint32_t a_off = (uint32_t)q * 16u;
-              const uint64_t dah = smem_desc(ah + a_off, 16, 128);
-              const uint64_t dbh = smem_desc(bh + (uint32_t)q * b_chunk_bytes, b_chunk_bytes, 128);
-              tc_mma_tf32(d_tmem, dah, dbh, idesc, first ? 0u : 1u);
-              first = 0;
-              if (a.n_split == 3) {
-                const uint64_t dal = smem_desc(al + a_off, 16, 128);
-                const uint64_t dbl = smem_desc(bl + (uint32_t)q * b_chunk_bytes, b_chunk_bytes, 128);
-                tc_mma_tf32(d_tmem, dal, dbh, idesc, 1u);
-                tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-              }
+            // hop == 4: one plane; the two K-chunks of an MMA are shifts q and q+1 (LBO = 16 B)
+            const uint64_t dah0 = smem_desc(ah, 16, 128);
+            const uint64_t dal0 = smem_desc(al, 16, 128);
+            int sl = rr;
+            for (; sl < (oc.Q >> 1); sl += UM_MMA_WARPS) {
+              const uint32_t q = 2u * (uint32_t)sl;
+              const uint64_t db = db0 + (uint64_t)(q * bchunk16);
+              tc_mma_tf32(d_tmem, dah0 + q, db, idesc_main, accum);
+              accum = 1;
+              if (split) tc_mma_tf32(d_tmem, dal0 + q, db, idesc_n1, 1u);
             }
+            rr = sl - (oc.Q >> 1);
           }
-          tc_commit(&empty[s]);                       // smem stage reusable once these MMAs retire
-          if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);   // accumulator complete
+          tc_commit(&empty[s]);                                 // smem stage reusable once these MMAs retire
+          if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);    // accumulator complete
         }
         __syncwarp();
       }
       ++it_acc;
     }
-  } else if (warp <= UM_EPI_WARPS) {
+  } else if (warp < UM_MMA_WARPS + UM_EPI_WARPS) {
     // =========================== epilogue ===========================
     const int ew = warp & 3;                 // a warp may only touch TMEM lanes [32*(warp%4), +32)
     uint32_t it_acc = 0;
@@ -281,17 +304,30 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       tc_fence_after();
       const int t = inf.t0 + ew * 32 + lane;
       const int64_t row = (int64_t)inf.clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
+      const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
       for (int c0 = 0; c0 < oc.npad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
+        float sum[16];
+#pragma unroll
+        for (int f = 0; f < 16; ++f) sum[f] = 0.f;
+#pragma unroll
+        for (int g = 0; g < UM_MMA_WARPS; ++g) {
+          uint32_t v[16], u[16];
+          tmem_ld16(tbase + (uint32_t)g * a.grp_stride + (uint32_t)c0, v);
+          if (a.n_split == 3) tmem_ld16(tbase + (uint32_t)g * a.grp_stride + (uint32_t)(oc.npad + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int f = 0; f < 16; ++f) {
+            sum[f] += __uint_as_float(v[f]);
+            if (a.n_split == 3) sum[f] += __uint_as_float(u[f]);
+          }
+        }
         if (t < inf.T) {
 #pragma unroll
           for (int f = 0; f < 16; f += 2) {
             const int col = c0 + f;
             const int bin = oc.first_bin + (col >> 1);
             if (col < oc.ncol && bin >= 0 && bin < a.n_bins) {
-              const float re = __uint_as_float(v[f]), im = __uint_as_float(v[f + 1]);
+              const float re = sum[f], im = sum[f + 1];
               a.mag_out[row + bin] = sqrtf(re * re + im * im);
               if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
             }
@@ -305,7 +341,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
     }
   } else {
     // =========================== producers ===========================
-    const int ptid = threadIdx.x - 32 * (1 + UM_EPI_WARPS);
+    const int ptid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS);
     constexpr int PT = 32 * UM_PRODUCER_WARPS;
     uint32_t it_stage = 0;
     int cur_oct = -1;
@@ -319,15 +355,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
           const uint32_t last = it_stage - 1;
           mbar_wait(&empty[last % UM_STAGES], (last / UM_STAGES) & 1, a.error_flag);
         }
-        const int n16 = (oc.n_fft / 4) * oc.npad;     // 16-byte units per split
-        const float4* gh = reinterpret_cast<const float4*>(oc.b_hi);
-        const float4* gl = reinterpret_cast<const float4*>(oc.b_lo);
-        float4* sh = reinterpret_cast<float4*>(b_hi_s);
-        float4* sl = reinterpret_cast<float4*>(b_lo_s);
-        for (int i = ptid; i < n16; i += PT) {
-          sh[i] = __ldg(gh + i);
-          if (a.n_split == 3) sl[i] = __ldg(gl + i);
-        }
+        const int n16 = (oc.n_fft / 4) * 2 * oc.npad;      // 16-byte units of the packed bank
+        const float4* gb = reinterpret_cast<const float4*>(oc.b_pack);
+        float4* sb = reinterpret_cast<float4*>(b_s);
+        for (int i = ptid; i < n16; i += PT) sb[i] = __ldg(gb + i);
         cur_oct = inf.o;
       }
       const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[inf.clip] : (int64_t)inf.clip * oc.sig_stride);
@@ -341,26 +372,42 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const int g0 = st * UM_PLANES_PER_STAGE;
         const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
         const int total = np * oc.rows;
-        for (int e = ptid; e < total; e += PT) {
-          const int g = e % np, srow = e / np;
-          const int64_t idx = origin + (int64_t)srow * oc.hop + 4 * (g0 + g);
-          float4 x;
-          if (base_al && idx >= 0 && idx + 3 < inf.len) {
-            x = __ldg(reinterpret_cast<const float4*>(y + idx));
-          } else {
-            x.x = __ldg(y + reflect_index(idx, inf.len));
-            x.y = __ldg(y + reflect_index(idx + 1, inf.len));
-            x.z = __ldg(y + reflect_index(idx + 2, inf.len));
-            x.w = __ldg(y + reflect_index(idx + 3, inf.len));
+        const int lg = oc.np_log2 < 2 ? oc.np_log2 : (np == 4 ? 2 : (np == 2 ? 1 : 0));
+        const bool split = (a.n_split == 3);
+        for (int e0 = ptid; e0 < total; e0 += 4 * PT) {
+          float4 x[4];
+          int dst[4];
+          // issue all loads of this batch before converting (keeps several L2 requests in flight)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * PT;
+            dst[u] = -1;
+            if (e < total) {
+              const int g = e & (np - 1), srow = e >> lg;
+              const int64_t idx = origin + (int64_t)srow * oc.hop + 4 * (g0 + g);
+              dst[u] = g * oc.rows_pad + srow;
+              if (base_al && idx >= 0 && idx + 3 < inf.len) {
+                x[u] = __ldg(reinterpret_cast<const float4*>(y + idx));
+              } else {
+                x[u].x = __ldg(y + reflect_index(idx, inf.len));
+                x[u].y = __ldg(y + reflect_index(idx + 1, inf.len));
+                x[u].z = __ldg(y + reflect_index(idx + 2, inf.len));
+                x[u].w = __ldg(y + reflect_index(idx + 3, inf.len));
+              }
+            }
           }
-          float4 h;
-          h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-          const int dst = g * oc.rows_pad + srow;
-          dh[dst] = h;
-          if (a.n_split == 3) {
-            float4 l;
-            l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
-            dl[dst] = l;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (dst[u] < 0) continue;
+            float4 h;
+            h.x = to_tf32(x[u].x); h.y = to_tf32(x[u].y); h.z = to_tf32(x[u].z); h.w = to_tf32(x[u].w);
+            dh[dst[u]] = h;
+            if (split) {
+              float4 l;
+              l.x = to_tf32(x[u].x - h.x); l.y = to_tf32(x[u].y - h.y);
+              l.z = to_tf32(x[u].z - h.z); l.w = to_tf32(x[u].w - h.w);
+              dl[dst[u]] = l;
+            }
           }
         }
         fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -390,8 +437,7 @@ __global__ void cqt_zero_pad_kernel(float* mag, float2* cplx, const int32_t* cli
 
 // ------------------------------------------------------------------ host side
 struct OctPack {
-  float* d_hi = nullptr;
-  float* d_lo = nullptr;
+  float* d_pack = nullptr;
   int npad = 0;
 };
 
@@ -400,7 +446,7 @@ struct OctPack {
 struct CqtUmmaState {
   std::vector<saga::OctPack> packs;
   bool supported = false;
-  uint32_t b_region_bytes = 0, a_region_bytes = 0, tmem_cols = 0, acc_stride = 0;
+  uint32_t b_region_bytes = 0, a_region_bytes = 0, tmem_cols = 0, acc_stride = 0, grp_stride = 0;
   size_t smem_bytes = 0;
   int* d_error = nullptr;
   int num_sms = 0;
@@ -429,48 +475,52 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   for (auto& o : p->oct) {
     const int ncol = 2 * o.n_filters;
     const int npad = (ncol + 15) & ~15;
-    if (npad > 256) return;
+    if (npad > 128) return;   // [hi|lo] operand: N = 2*npad <= 256
     if (o.hop < 4 || (o.hop % 4) != 0 || (o.n_fft % o.hop) != 0 || (o.n_fft % 8) != 0) return;
     const int planes = o.hop / 4;
     if (planes >= 2 && (std::min(planes, UM_PLANES_PER_STAGE) % 2) != 0) return;
     const int Q = o.n_fft / o.hop;
     if (planes == 1 && (Q % 2) != 0) return;
+    const int np0 = std::min(planes, UM_PLANES_PER_STAGE);
+    const int slices = planes >= 2 ? Q * (np0 / 2) : Q / 2;      // K-slices per stage
+    const int n_st = (planes + UM_PLANES_PER_STAGE - 1) / UM_PLANES_PER_STAGE;
+    if (slices * n_st < UM_MMA_WARPS) return;                     // every issuer warp must get work in an item
     const int rows = UM_TILE_M + Q - 1;
     const int rows_pad = rows | 1;
-    bmax = std::max<uint32_t>(bmax, (uint32_t)o.n_fft * npad * 4u);
+    bmax = std::max<uint32_t>(bmax, (uint32_t)o.n_fft * 2u * npad * 4u);
     amax = std::max<uint32_t>(amax, (uint32_t)std::min(planes, UM_PLANES_PER_STAGE) * rows_pad * 16u);
     npad_max = std::max(npad_max, npad);
   }
   amax = (amax + 127u) & ~127u;
   bmax = (bmax + 127u) & ~127u;
-  const size_t smem = 2ull * bmax + 2ull * UM_STAGES * amax + 256;
+  const size_t smem = (size_t)bmax + 2ull * UM_STAGES * amax + 256;
   if (smem > 225 * 1024) return;
   uint32_t cols = 32;
-  while (cols < 2u * npad_max) cols <<= 1;
+  while (cols < 2u * UM_MMA_WARPS * 2u * npad_max) cols <<= 1;   // 2 buffers x issuer groups x (hi|lo)
   if (cols > 512) return;
   st->b_region_bytes = bmax;
   st->a_region_bytes = amax;
   st->tmem_cols = cols;
   st->acc_stride = cols / 2;
+  st->grp_stride = 2u * npad_max;
   st->smem_bytes = smem;
   // pack each bank for the B descriptor: [n_fft/4][npad][4], split into TF32 hi / lo
   for (auto& o : p->oct) {
     OctPack pk;
     const int ncol = 2 * o.n_filters;
     pk.npad = (ncol + 15) & ~15;
-    const size_t n = (size_t)o.n_fft * pk.npad;
-    std::vector<float> hi(n, 0.f), lo(n, 0.f);
+    const size_t n = (size_t)o.n_fft * 2 * pk.npad;
+    std::vector<float> pack(n, 0.f);
     for (int k = 0; k < o.n_fft; ++k)
       for (int c = 0; c < ncol; ++c) {
         const float b = o.bank_host[(size_t)k * ncol + c];
         const float h = tf32_rna_host(b);
-        const size_t dst = ((size_t)(k / 4) * pk.npad + c) * 4 + (k % 4);
-        hi[dst] = h;
-        lo[dst] = tf32_rna_host(b - h);
+        const size_t chunk = (size_t)(k / 4) * 2 * pk.npad;
+        pack[(chunk + c) * 4 + (k % 4)] = h;
+        pack[(chunk + pk.npad + c) * 4 + (k % 4)] = tf32_rna_host(b - h);
       }
-    if (cudaMalloc(&pk.d_hi, n * 4) != cudaSuccess || cudaMalloc(&pk.d_lo, n * 4) != cudaSuccess) return;
-    cudaMemcpy(pk.d_hi, hi.data(), n * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(pk.d_lo, lo.data(), n * 4, cudaMemcpyHostToDevice);
+    if (cudaMalloc(&pk.d_pack, n * 4) != cudaSuccess) return;
+    cudaMemcpy(pk.d_pack, pack.data(), n * 4, cudaMemcpyHostToDevice);
     st->packs.push_back(pk);
   }
   if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) return;
@@ -487,10 +537,7 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
 
 void cqt_umma_plan_free(saga_cqt_plan* p) {
   if (!p->umma) return;
-  for (auto& pk : p->umma->packs) {
-    cudaFree(pk.d_hi);
-    cudaFree(pk.d_lo);
-  }
+  for (auto& pk : p->umma->packs) cudaFree(pk.d_pack);
   cudaFree(p->umma->d_error);
   delete p->umma;
   p->umma = nullptr;
@@ -519,6 +566,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.a_region_bytes = st->a_region_bytes;
   a.tmem_cols = st->tmem_cols;
   a.acc_stride = st->acc_stride;
+  a.grp_stride = st->grp_stride;
   a.error_flag = st->d_error;
   const int64_t per_oct = (int64_t)n_clips * a.tiles_per_clip;
   for (int i = 0; i < a.n_oct; ++i) {
@@ -528,8 +576,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     u.sig = raw ? lv.wav : lv.lvl[o.level];
     u.sig_offsets = raw ? lv.clip_offsets : nullptr;
     u.sig_stride = raw ? 0 : lv.pitch[o.level];
-    u.b_hi = st->packs[i].d_hi;
-    u.b_lo = st->packs[i].d_lo;
+    u.b_pack = st->packs[i].d_pack;
     u.level = o.level;
     u.hop = o.hop;
     u.n_fft = o.n_fft;
@@ -537,6 +584,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     u.npad = st->packs[i].npad;
     u.first_bin = o.first_bin;
     u.planes = o.hop / 4;
+    u.np_log2 = u.planes >= 4 ? 2 : (u.planes == 2 ? 1 : 0);
     u.n_stages = (u.planes + UM_PLANES_PER_STAGE - 1) / UM_PLANES_PER_STAGE;
     u.Q = o.n_fft / o.hop;
     u.rows = UM_TILE_M + u.Q - 1;

@@ -13,6 +13,8 @@
 // One CTA owns one window for the whole chain: per-frame maxima live in shared
 // memory, so a step only touches the guess's column range, and the window max
 // needed by the next step / by the dB floor is a block reduction, not a re-read.
+#include <algorithm>
+
 #include "saga_common.cuh"
 
 namespace saga {
@@ -38,6 +40,7 @@ struct SubArgs {
   int flags;
   float* D_out;
   float* ref_out;
+  float* vmax_scratch;
   int n_steps, n_bins, n_frames;
   int64_t frame_pitch;
   float amin, top_db;
@@ -175,40 +178,59 @@ __global__ void __launch_bounds__(SUB_THREADS) subtract_chain_kernel(const SubAr
   float m = 0.f;
   for (int t = threadIdx.x; t < T; t += SUB_THREADS) m = fmaxf(m, fmax_s[t]);
   const float vmax = block_max(m, red);
-  if (threadIdx.x == 0 && a.ref_out) a.ref_out[w] = vmax;
-  if (!a.D_out) return;
+  if (threadIdx.x == 0) {
+    if (a.ref_out) a.ref_out[w] = vmax;
+    if (a.vmax_scratch) a.vmax_scratch[w] = vmax;
+  }
+}
 
-  float* D = a.D_out + (a.win_offsets ? a.win_offsets[w] : (int64_t)w * a.win_stride);
-  const float amin2 = a.amin * a.amin;
+// dB epilogue as its own flat, perfectly balanced pass (a window per CTA leaves the last
+// wave nearly empty: 600 windows over 296 resident CTAs = 2.03 waves).
+//   D = 10 log10(max(amin^2, w^2)) - 10 log10(max(amin^2, ref^2)),  floor at max(D) - top_db,
+// and max(D) == 0 because ref is the window's own max.
+template <bool VEC>
+__global__ void __launch_bounds__(256) window_db_kernel(const float* __restrict__ win_mag,
+                                                         const int64_t* __restrict__ win_offsets,
+                                                         int64_t win_stride, float* __restrict__ D_out,
+                                                         const float* __restrict__ vmax_w, int n_bins, int n_frames,
+                                                         int64_t P, float amin, float top_db, int chunks_per_window) {
+  const int w = blockIdx.x / chunks_per_window, chunk = blockIdx.x % chunks_per_window;
+  const int64_t base = win_offsets ? win_offsets[w] : (int64_t)w * win_stride;
+  const float* win = win_mag + base;
+  float* D = D_out + base;
+  const float amin2 = amin * amin;
+  const float vmax = vmax_w[w];
   const float ref_db = 10.0f * log10f(fmaxf(amin2, vmax * vmax));
-  // log_spec.max() is attained at the max element: 10log10(max(amin2, vmax^2)) - ref_db = 0
-  const float floor_db = (a.top_db >= 0.f) ? (0.0f - a.top_db) : -INFINITY;
+  const float floor_db = (top_db >= 0.f) ? (0.0f - top_db) : -INFINITY;
+  const int rows = (n_frames + chunks_per_window - 1) / chunks_per_window;
+  const int t0 = chunk * rows, t1 = min(n_frames, t0 + rows);
+  if (t0 >= t1) return;
   if (VEC) {
-    const int64_t n4 = ((int64_t)T * P) >> 2;
     const int Pq = (int)(P >> 2);
-    const float4* w4 = reinterpret_cast<const float4*>(win);
-    float4* d4 = reinterpret_cast<float4*>(D);
+    const float4* w4 = reinterpret_cast<const float4*>(win + (int64_t)t0 * P);
+    float4* d4 = reinterpret_cast<float4*>(D + (int64_t)t0 * P);
+    const int n4 = (t1 - t0) * Pq;
 #pragma unroll 4
-    for (int64_t i = threadIdx.x; i < n4; i += SUB_THREADS) {
-      const float4 x = w4[i];
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 x = __ldcs(w4 + i);
       float4 d;
       d.x = fmaxf(db_of(x.x, amin2, ref_db), floor_db);
       d.y = fmaxf(db_of(x.y, amin2, ref_db), floor_db);
       d.z = fmaxf(db_of(x.z, amin2, ref_db), floor_db);
       d.w = fmaxf(db_of(x.w, amin2, ref_db), floor_db);
-      // keep the padding columns at zero
-      const int c = (int)(i % Pq) << 2;
-      if (c + 3 >= B) {
-        if (c >= B) d.x = 0.f;
-        if (c + 1 >= B) d.y = 0.f;
-        if (c + 2 >= B) d.z = 0.f;
+      const int c = (i % Pq) << 2;          // keep the padding columns at zero
+      if (c + 3 >= n_bins) {
+        if (c >= n_bins) d.x = 0.f;
+        if (c + 1 >= n_bins) d.y = 0.f;
+        if (c + 2 >= n_bins) d.z = 0.f;
         d.w = 0.f;
       }
-      d4[i] = d;
+      __stcs(d4 + i, d);
     }
   } else {
-    for (int t = warp; t < T; t += SUB_WARPS)
-      for (int k = lane; k < B; k += 32)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = t0 + warp; t < t1; t += 8)
+      for (int k = lane; k < n_bins; k += 32)
         D[(int64_t)t * P + k] = fmaxf(db_of(win[(int64_t)t * P + k], amin2, ref_db), floor_db);
   }
 }
@@ -284,6 +306,11 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(float) * (size_t)n_frames;
   if (smem > 160 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "subtract_db_exec: n_frames too large");
+  // the dB pass needs every window's final max: ref_out doubles as that buffer when the caller
+  // provides it, otherwise a stream-ordered scratch allocation is used
+  float* vmax = ref_out;
+  if (D_out && !vmax) SAGA_CUDA_OK(cudaMallocAsync(&vmax, sizeof(float) * n_windows, st));
+  a.vmax_scratch = (vmax != ref_out) ? vmax : nullptr;
   if (vec) {
     if (smem > 40 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(subtract_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -294,6 +321,19 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
     subtract_chain_kernel<false><<<n_windows, SUB_THREADS, smem, st>>>(a);
   }
   SAGA_LAUNCH_CHECK();
+  if (D_out) {
+    // ~8 CTAs of 256 threads per SM in flight, whole chunks of rows per CTA
+    int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames, (148 * 16 + n_windows - 1) / n_windows));
+    const int64_t blocks = (int64_t)n_windows * chunks;
+    if (vec)
+      window_db_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins,
+                                                              n_frames, frame_pitch, amin, top_db, chunks);
+    else
+      window_db_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins,
+                                                               n_frames, frame_pitch, amin, top_db, chunks);
+    SAGA_LAUNCH_CHECK();
+    if (vmax != ref_out) SAGA_CUDA_OK(cudaFreeAsync(vmax, st));
+  }
   return SAGA_OK;
 }
 
