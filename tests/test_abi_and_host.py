@@ -1,0 +1,89 @@
+"""No-GPU checks of the boundary: the C-ABI library loads, exports every symbol
+include/saga_b200.h declares, fails loudly without a device; host helpers of the
+audio_complete mirror agree with the oracle's restatement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import amt_saga_b200  # noqa: F401
+from amt_saga_b200 import _lib, util_audio
+from oracle import spectral as osp
+from oracle.audio_oracle import AudioOracle, band_edges
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "saga_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(saga_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libsaga_b200.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "ctypes binding missing for %s" % n
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.saga_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = lib.saga_stft_plan_create(C.byref(h), 2048, 512, 1, None)
+    assert rc == _lib.SAGA_ERR_CUDA and lib.saga_last_error_string()
+    with pytest.raises(RuntimeError):
+        util_audio.audio_complete(np.zeros(10, dtype=np.float32), 2048)
+
+
+def test_argument_errors_do_not_need_a_device(lib):
+    h = C.c_void_p()
+    assert lib.saga_stft_plan_create(C.byref(h), 1000, 512, 1, None) == _lib.SAGA_ERR_UNSUPPORTED
+    assert lib.saga_stft_plan_create(C.byref(h), 2048, 0, 1, None) == _lib.SAGA_ERR_INVALID
+    assert b"hop_length" in lib.saga_last_error_string()
+    assert lib.saga_subtract_db_exec(None, None, 0, None, None, 0, None, 0, None, None, None, None, None, 0, 0,
+                                     None, None, 1, 0, 4, 4, 4, 1e-5, 80.0, None) == _lib.SAGA_ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(_lib.SAGA_ERR_INVALID)
+    with pytest.raises(_lib.SagaUnsupported):
+        _lib.check(_lib.SAGA_ERR_UNSUPPORTED)
+
+
+def test_host_helpers_match_oracle():
+    for note in ("A0", "C1", "C8", "C#4", "Bb3", "D3"):
+        assert util_audio.note_to_midi(note) == osp.note_to_midi(note)
+        assert abs(util_audio.note_to_hz(note) - osp.note_to_hz(note)) < 1e-9
+    for m in (21, 50, 59, 60, 61, 108):
+        assert util_audio.midi_to_note(m) == osp.midi_to_note(m)
+    for n, b in ((2049, 20), (1025, 20), (1025, 80)):
+        assert np.array_equal(util_audio.band_edges(n, b), band_edges(n, b))
+    P = np.arange(3 * 11, dtype=float).reshape(3, 11)
+    for t in (0, 1, 2, 3, 5, 8, 11):
+        for target in (6, 8, 258):
+            assert np.array_equal(util_audio.audio_complete._resize(P[:, :t], target),
+                                  AudioOracle._resize(P[:, :t], target))
+    S = np.random.default_rng(0).random((2049, 7))
+    assert np.allclose(util_audio.audio_complete.compress_bands(S, bands=20), AudioOracle.compress_bands(S, bands=20))
+
+
+def test_frame_arithmetic_of_the_pipeline_without_gpu():
+    from amt_saga_b200.pipeline import seconds_to_frames
+    o = AudioOracle(np.zeros(263680, dtype=np.float32), 2048, 512)
+    o.mag = np.zeros((1025, 516), dtype=np.float32)
+    o._v["wf"] = np.zeros(263680, dtype=np.float32)
+    for t in (0.0, 0.5, 1.999, 3.0, 5.99):
+        assert seconds_to_frames(t, 516, 44100, 263680) == o._seconds_to_frames(t)

@@ -348,3 +348,97 @@ def test_window_pipeline_matches_oracle(saga):
         assert abs(float(pipe.ref[w]) - mag.max()) <= 2e-5 * mag.max()
         C = np.abs(ocqt.cqt(wav[w], sr=sr, hop_length=hop, fmin=osp.note_to_hz("C1"), n_bins=84, filter_scale=2))
         check_mag(pipe.C[w, :, :84].T.cpu().numpy(), C)
+
+
+# --------------------------------------------------------------------------- committed golden vectors
+GOLD = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+def test_golden_cfg1(saga, cfg1):
+    _, ua = saga
+    y, sr = cfg1
+    g = np.load(GOLD + "/cfg1.npz")
+    a = ua.audio_complete(y, 2048, hop_length=512, sample_rate=sr)
+    assert a.shape == tuple(g["mag_shape"]) and a.mag.stride() == (1, 1028)   # [bins, frames], frame-major
+    mag = a.mag.cpu().numpy()
+    assert np.abs(mag[:, g["cols"]] - g["mag_cols"]).max() <= MAG_TOL * float(g["ref_mag"])
+    assert np.abs(mag.sum(axis=0) - g["mag_colsum"]).max() <= 1e-5 * g["mag_colsum"].max()
+    assert abs(float(a.ref_mag) - float(g["ref_mag"])) <= 1e-6 * float(g["ref_mag"])
+    D = a.D.cpu().numpy()[:, g["cols"]]
+    above = g["D_cols"] > -79.9
+    assert np.abs(D[above] - g["D_cols"][above]).max() <= DB_TOL
+    C = a.slice_C(0, 10.0, 313, bins_per_tone=1, lowest_note="C1", nbins=84).cpu().numpy()
+    assert C.shape == tuple(g["cqt_shape"])
+    assert np.abs(C[:, g["cols"]] - g["cqt_cols"]).max() <= MAG_TOL * g["cqt_cols"].max()
+    assert np.abs(C.sum(axis=1) - g["cqt_rowsum"]).max() <= 1e-4 * g["cqt_rowsum"].max()
+
+
+def test_golden_subtract_istft_cqt87(saga):
+    ops, _ = saga
+    s = np.load(GOLD + "/subtract_chain.npz")
+    B, T = s["win"].shape
+    P = ops.frame_pitch(B)
+    st = torch.zeros((1, T, P), device="cuda")
+    st[0, :, :B] = dev(s["win"]).T
+    g = torch.zeros((1, 3, 9, P), device="cuda")
+    g[0, :, :, :B] = dev(s["guesses"]).transpose(1, 2)
+    D, ref = ops.subtract_db_batch(st, g, dev(s["offsets"]).reshape(1, 3), B)
+    assert np.array_equal(st[0, :, :B].T.cpu().numpy(), s["result"])          # bit exact
+    check_db(D[0, :, :B].T.cpu().numpy(), s["D"])
+    i = np.load(GOLD + "/istft.npz")
+    plan = ops.StftPlan(1024, 256, True)
+    r = ops.stft_batch(dev(i["wav"]), plan, want_complex=True)
+    w = ops.istft_batch(plan, F=r["F_storage"])[0].cpu().numpy()
+    assert w.shape == i["istft"].shape and np.abs(w - i["istft"]).max() <= 2e-5 * np.abs(i["istft"]).max()
+    c = np.load(GOLD + "/cqt87.npz")
+    cp = ops.CqtPlan(44100, 1024, osp.note_to_hz("A0"), 87, 12, filter_scale=2)
+    got = ops.cqt_batch(dev(c["wav"]), cp)["mag"][0].cpu().numpy()
+    check_mag(got, c["cqt"], tol=1e-5)
+
+
+# --------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_one_hour(saga):
+    """BASELINE cfg2/cfg3 size (1 h = 600 x 6 s windows): properties that do not
+    need the oracle at that size."""
+    ops, _ = saga
+    from amt_saga_b200 import synth
+    from amt_saga_b200.pipeline import WindowFeaturePipeline
+    W, ns, ng = 600, 264600, 65024
+    wav = synth.piano_batch(range(W), ns, seed_base=50000)
+    guess = synth.piano_batch(range(W), ng, n_notes=1, seed_base=90000)
+    plan = ops.get_stft_plan(2048, 512, True)
+    r = ops.stft_batch(wav, plan, want_complex=True)
+    assert tuple(r["mag"].shape) == (W, 1025, 517)
+    # (1) |F| == mag, per-frame / per-clip maxima consistent (a checksum of checksums)
+    assert float((r["F"].abs() - r["mag"]).abs().max()) <= 1e-5 * float(r["mag"].max())
+    assert torch.equal(r["frame_max"].amax(dim=1), r["clip_max"])
+    assert torch.allclose(r["mag"].amax(dim=1), r["frame_max"], rtol=0, atol=0)
+    # (2) linearity: STFT(2.5 x) == 2.5 STFT(x)
+    r2 = ops.stft_batch(wav * 2.5, plan)
+    assert float((r2["mag"] - 2.5 * r["mag"]).abs().max()) <= 2e-6 * float(r2["mag"].max())
+    # (3) analysis -> synthesis round trip reproduces the interior samples
+    back = ops.istft_batch(plan, F=r["F_storage"])
+    assert back.shape == (W, 512 * 516)
+    assert float((back[:, 2048:-2048] - wav[:, 2048:512 * 516 - 2048]).abs().max()) <= 2e-5
+    del r2, back
+    # (4) Parseval on the CQT side is not available (non-unitary bank); use shift invariance:
+    #     interior CQT frames of a clip delayed by 8 hops equal the original's frames 8 later.
+    cq = ops.get_cqt_plan(44100, 512, osp.note_to_hz("C1"), 84, 12, 2)
+    c0 = ops.cqt_batch(wav[:8], cq)["mag"]
+    c1 = ops.cqt_batch(torch.roll(wav[:8], 8 * 512, dims=1), cq)["mag"]
+    assert float((c1[:, :, 120:400] - c0[:, :, 112:392]).abs().max()) <= 2e-5 * float(c0.max())
+    # (5) the pipeline with a zero guess is the identity on the window and gives D = dB(mag)
+    pipe = WindowFeaturePipeline(W, ns, ng)
+    offs = torch.zeros((W, 1), device="cuda", dtype=torch.int32)
+    pipe.run(wav, torch.zeros_like(guess) + 1e-30, offs)
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.mag[:, :516, :1025], r["mag_storage"][:, :516, :1025])
+    assert float(pipe.D.max()) <= 0.0 and float(pipe.D[:, :516, :1025].min()) >= -80.0
+    assert torch.equal(pipe.ref, pipe.mag[:, :516, :1025].amax(dim=(1, 2)))
+    # (6) a real guess only lowers the window, never below zero, and only inside its column range
+    pipe.run(wav, guess, offs + 100)
+    torch.cuda.synchronize()
+    assert float(pipe.mag.min()) >= 0.0
+    d = r["mag_storage"][:, :516, :1025] - pipe.mag[:, :516, :1025]
+    assert float(d.min()) >= 0.0 and float(d[:, :100].abs().max()) == 0.0 and float(d[:, 228:].abs().max()) == 0.0
+    assert float(d[:, 100:228].max()) > 0.0
