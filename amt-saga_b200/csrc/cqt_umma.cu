@@ -51,6 +51,7 @@ constexpr int UM_STAGES = 4;
 constexpr int UM_PLANES_PER_STAGE = 4;      // 4 planes x 4 samples = 16 k-values per shift
 constexpr int UM_MAX_OCT = 12;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
+constexpr int UM_PREFETCH = 2;              // producer look-ahead in stages (must be < UM_STAGES)
 
 struct UmmaOct {
   const float* sig;
@@ -184,6 +185,35 @@ __device__ __forceinline__ ItemInfo decode_item(const UmmaArgs& a, int64_t item)
   return it;
 }
 
+// walks this CTA's (item, stage) jobs in the order every role processes them
+struct JobIter {
+  int64_t item, G;
+  int st;
+  bool started;
+  ItemInfo inf;
+  __device__ __forceinline__ void reset(int64_t first, int64_t stride) {
+    item = first - stride;
+    G = stride;
+    st = 0;
+    started = false;
+  }
+  __device__ __forceinline__ bool next(const UmmaArgs& a) {
+    if (started && st + 1 < a.oct[inf.o].n_stages) {
+      ++st;
+      return true;
+    }
+    for (;;) {
+      item += G;
+      if (item >= a.total_items) return false;
+      inf = decode_item(a, item);
+      if (inf.t0 < inf.T) break;
+    }
+    st = 0;
+    started = true;
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* b_s = smem_raw;
@@ -195,7 +225,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   uint64_t* tempty = bars + 2 * UM_STAGES + 2;  // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * UM_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast so the compiler knows the role index is warp-uniform (keeps MMA operands in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < UM_STAGES; ++s) {
@@ -341,73 +373,84 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
     }
   } else {
     // =========================== producers ===========================
+    // Software pipeline over this CTA's (item, stage) jobs: job k's raw fp32 rows are fetched with
+    // cp.async (16 B, L2 -> SMEM, no register staging) UM_PREFETCH jobs ahead of their conversion, so
+    // several stages of L2 requests are in flight per SM; each thread later converts exactly the
+    // elements it fetched (in place -> TF32 hi, plus lo), so cp.async.wait_group is the only sync.
     const int ptid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS);
     constexpr int PT = 32 * UM_PRODUCER_WARPS;
-    uint32_t it_stage = 0;
+    JobIter is, cv;
+    is.reset(blockIdx.x, G);
+    cv.reset(blockIdx.x, G);
+    bool have_issue = is.next(a);
     int cur_oct = -1;
-    for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
-      const ItemInfo inf = decode_item(a, item);
-      if (inf.t0 >= inf.T) continue;
-      const UmmaOct& oc = a.oct[inf.o];
-      if (inf.o != cur_oct) {
-        // new bank: every MMA that reads the old one must have retired
-        if (it_stage > 0) {
-          const uint32_t last = it_stage - 1;
-          mbar_wait(&empty[last % UM_STAGES], (last / UM_STAGES) & 1, a.error_flag);
+    const bool split = (a.n_split == 3);
+    for (uint32_t k = 0;; ++k) {
+      // ---- issue job k -------------------------------------------------------------------
+      if (have_issue) {
+        const UmmaOct& oc = a.oct[is.inf.o];
+        const uint32_t s = k % UM_STAGES;
+        mbar_wait(&empty[s], ((k / UM_STAGES) & 1) ^ 1, a.error_flag);
+        float4* raw = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
+        const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[is.inf.clip] : (int64_t)is.inf.clip * oc.sig_stride);
+        const bool base_al = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+        const int64_t origin = (int64_t)is.inf.t0 * oc.hop - (oc.n_fft >> 1);
+        const int g0 = is.st * UM_PLANES_PER_STAGE;
+        const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+        const int lg = (np == 4) ? 2 : (np == 2 ? 1 : 0);
+        const int total = np * oc.rows;
+        for (int e = ptid; e < total; e += PT) {
+          const int g = e & (np - 1), srow = e >> lg;
+          const int64_t idx = origin + (int64_t)srow * oc.hop + 4 * (g0 + g);
+          float4* dst = raw + (g * oc.rows_pad + srow);
+          if (base_al && idx >= 0 && idx + 3 < is.inf.len) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(y + idx) : "memory");
+          } else {
+            float4 x;
+            x.x = __ldg(y + reflect_index(idx, is.inf.len));
+            x.y = __ldg(y + reflect_index(idx + 1, is.inf.len));
+            x.z = __ldg(y + reflect_index(idx + 2, is.inf.len));
+            x.w = __ldg(y + reflect_index(idx + 3, is.inf.len));
+            *dst = x;
+          }
         }
+        have_issue = is.next(a);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");      // one group per k, possibly empty
+      if (k < UM_PREFETCH) continue;
+      // ---- convert job k - UM_PREFETCH ------------------------------------------------------
+      if (!cv.next(a)) break;
+      const uint32_t kc = k - UM_PREFETCH;
+      const UmmaOct& oc = a.oct[cv.inf.o];
+      if (cv.inf.o != cur_oct) {
+        // new bank: every MMA that reads the old one must have retired
+        if (kc > 0) mbar_wait(&empty[(kc - 1) % UM_STAGES], ((kc - 1) / UM_STAGES) & 1, a.error_flag);
         const int n16 = (oc.n_fft / 4) * 2 * oc.npad;      // 16-byte units of the packed bank
         const float4* gb = reinterpret_cast<const float4*>(oc.b_pack);
         float4* sb = reinterpret_cast<float4*>(b_s);
         for (int i = ptid; i < n16; i += PT) sb[i] = __ldg(gb + i);
-        cur_oct = inf.o;
+        cur_oct = cv.inf.o;
       }
-      const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[inf.clip] : (int64_t)inf.clip * oc.sig_stride);
-      const bool base_al = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
-      const int64_t origin = (int64_t)inf.t0 * oc.hop - (oc.n_fft >> 1);   // sample index of Y[0][0]
-      for (int st = 0; st < oc.n_stages; ++st, ++it_stage) {
-        const uint32_t s = it_stage % UM_STAGES;
-        mbar_wait(&empty[s], ((it_stage / UM_STAGES) & 1) ^ 1, a.error_flag);
+      asm volatile("cp.async.wait_group %0;" ::"n"(UM_PREFETCH) : "memory");
+      {
+        const uint32_t s = kc % UM_STAGES;
         float4* dh = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
         float4* dl = reinterpret_cast<float4*>(a_base + (2 * s + 1) * a.a_region_bytes);
-        const int g0 = st * UM_PLANES_PER_STAGE;
+        const int g0 = cv.st * UM_PLANES_PER_STAGE;
         const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+        const int lg = (np == 4) ? 2 : (np == 2 ? 1 : 0);
         const int total = np * oc.rows;
-        const int lg = oc.np_log2 < 2 ? oc.np_log2 : (np == 4 ? 2 : (np == 2 ? 1 : 0));
-        const bool split = (a.n_split == 3);
-        for (int e0 = ptid; e0 < total; e0 += 4 * PT) {
-          float4 x[4];
-          int dst[4];
-          // issue all loads of this batch before converting (keeps several L2 requests in flight)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = e0 + u * PT;
-            dst[u] = -1;
-            if (e < total) {
-              const int g = e & (np - 1), srow = e >> lg;
-              const int64_t idx = origin + (int64_t)srow * oc.hop + 4 * (g0 + g);
-              dst[u] = g * oc.rows_pad + srow;
-              if (base_al && idx >= 0 && idx + 3 < inf.len) {
-                x[u] = __ldg(reinterpret_cast<const float4*>(y + idx));
-              } else {
-                x[u].x = __ldg(y + reflect_index(idx, inf.len));
-                x[u].y = __ldg(y + reflect_index(idx + 1, inf.len));
-                x[u].z = __ldg(y + reflect_index(idx + 2, inf.len));
-                x[u].w = __ldg(y + reflect_index(idx + 3, inf.len));
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (dst[u] < 0) continue;
-            float4 h;
-            h.x = to_tf32(x[u].x); h.y = to_tf32(x[u].y); h.z = to_tf32(x[u].z); h.w = to_tf32(x[u].w);
-            dh[dst[u]] = h;
-            if (split) {
-              float4 l;
-              l.x = to_tf32(x[u].x - h.x); l.y = to_tf32(x[u].y - h.y);
-              l.z = to_tf32(x[u].z - h.z); l.w = to_tf32(x[u].w - h.w);
-              dl[dst[u]] = l;
-            }
+        for (int e = ptid; e < total; e += PT) {
+          const int g = e & (np - 1), srow = e >> lg;
+          const int d = g * oc.rows_pad + srow;
+          const float4 x = dh[d];
+          float4 h;
+          h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+          dh[d] = h;
+          if (split) {
+            float4 l;
+            l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+            dl[d] = l;
           }
         }
         fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -415,6 +458,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         if (lane == 0) mbar_arrive(&full[s]);
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();

@@ -62,6 +62,7 @@ class WindowFeaturePipeline:
         self._lib = lib
         # host side of the e2e path (pinned), allocated on demand
         self._host = None
+        self._streams = None
 
     # algorithmic work per window (DESIGN.md / SURVEY.md section 8d)
     def stft_bytes_per_window(self):
@@ -73,14 +74,17 @@ class WindowFeaturePipeline:
     def cqt_flops_per_window(self):
         return self.Tc * sum(8 * o["n_filters"] * (o["n_fft"] // 2 + 1) for o in self.cqt.octaves)
 
-    def run(self, wav, guess_wav, offset_frames, events=None):
+    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None):
         """wav [W, window_samples], guess_wav [W, guess_samples] CUDA float32 contiguous,
         offset_frames [W,1] int32 CUDA.  Results land in self.mag (subtracted,
         in place), self.D, self.C, self.ref.  `events`: optional list that
-        receives (stage, start_event, end_event) on the current stream."""
-        p = lambda t: C.c_void_p(t.data_ptr())
+        receives (stage, start_event, end_event) on the current stream.
+        `w0:w1` restricts the pass to that window range (chunked / overlapped use)."""
+        w1 = self.W if w1 is None else w1
+        p = lambda t: C.c_void_p(t[w0:].data_ptr())
+        q = lambda t: C.c_void_p(t.data_ptr())
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        lib, W = self._lib, self.W
+        lib, W = self._lib, w1 - w0
 
         def stage(name, fn):
             if events is None:
@@ -92,13 +96,13 @@ class WindowFeaturePipeline:
             events.append((name, a, b))
 
         stage("stft", lambda: _lib.check(lib.saga_stft_exec(
-            self.stft.handle, p(wav), p(self.offs_w), p(self.lens_w), W, self.ns, p(self.mag), None, None,
+            self.stft.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.mag), None, None,
             self.P, self.T_clip * self.P, p(self.frame_max), p(self.clip_max), st)))
         stage("cqt", lambda: _lib.check(lib.saga_cqt_exec(
-            self.cqt.handle, p(wav), p(self.offs_w), p(self.lens_w), W, self.ns, p(self.C), None,
-            self.Pc, self.Tc * self.Pc, p(self.ws), self.ws.numel(), self.cqt_impl, st)))
+            self.cqt.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.C), None,
+            self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl, st)))
         stage("stft_guess", lambda: _lib.check(lib.saga_stft_exec(
-            self.stft.handle, p(guess_wav), p(self.offs_g), p(self.lens_g), W, self.ng, p(self.gmag), None,
+            self.stft.handle, p(guess_wav), q(self.offs_g), q(self.lens_g), W, self.ng, p(self.gmag), None,
             None, self.P, self.Tg * self.P, None, p(self.gmax), st)))
         stage("subtract_db", lambda: _lib.check(lib.saga_subtract_db_exec(
             p(self.mag), None, self.T_clip * self.P, p(self.gmag), None, self.Tg * self.P, None, self.Tg,
@@ -121,17 +125,52 @@ class WindowFeaturePipeline:
                 d_offs=torch.empty((self.W, 1), device=self.dev, dtype=torch.int32))
         return self._host
 
-    def run_host(self):
+    def run_host(self, chunks=6):
         """Pinned host inputs -> device -> hot path -> features back on the host
         (CQT magnitudes + post-subtraction ref_mag; the subtracted window and its dB
-        image stay resident for the next loop iteration, as in training.py:449)."""
+        image stay resident for the next loop iteration, as in training.py:449).
+
+        The batch is cut into `chunks` window ranges; H2D copies, kernels and D2H
+        copies run on three streams so PCIe transfers overlap the compute (the
+        path is PCIe-bound: 1.3 MB of audio in per window)."""
         h = self.host_buffers()
-        h["d_wav"].copy_(h["wav"], non_blocking=True)
-        h["d_guess"].copy_(h["guess"], non_blocking=True)
-        h["d_offs"].copy_(h["offs"], non_blocking=True)
-        self.run(h["d_wav"], h["d_guess"], h["d_offs"])
-        h["C"].copy_(self.C, non_blocking=True)
-        h["ref"].copy_(self.ref, non_blocking=True)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+            self._last_compute = None
+        s_in, s_cmp, s_out = self._streams
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(cur)
+        s_in.wait_event(start)
+        s_cmp.wait_event(start)
+        s_out.wait_event(start)
+        n = max(1, min(chunks, self.W))
+        bounds = [(i * self.W // n, (i + 1) * self.W // n) for i in range(n)]
+        ev_in, ev_cmp = [], []
+        with torch.cuda.stream(s_in):
+            for a, b in bounds:
+                h["d_wav"][a:b].copy_(h["wav"][a:b], non_blocking=True)
+                h["d_guess"][a:b].copy_(h["guess"][a:b], non_blocking=True)
+                h["d_offs"][a:b].copy_(h["offs"][a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+        with torch.cuda.stream(s_cmp):
+            for (a, b), e in zip(bounds, ev_in):
+                s_cmp.wait_event(e)
+                self.run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
+                e2 = torch.cuda.Event()
+                e2.record(s_cmp)
+                ev_cmp.append(e2)
+        with torch.cuda.stream(s_out):
+            for (a, b), e in zip(bounds, ev_cmp):
+                s_out.wait_event(e)
+                h["C"][a:b].copy_(self.C[a:b], non_blocking=True)
+                h["ref"][a:b].copy_(self.ref[a:b], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(s_out)
+        cur.wait_event(done)
+        cur.wait_event(ev_in[-1])
 
     def h2d_bytes(self):
         return 4 * self.W * (self.ns + self.ng + 1)

@@ -230,12 +230,12 @@ def run_saga(args):
     torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     for _ in range(2):
-        pipe.run_host()
+        pipe.run_host(args.e2e_chunks)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
-        pipe.run_host()
+        pipe.run_host(args.e2e_chunks)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -301,7 +301,8 @@ def run_saga(args):
         "e2e": {"value": e2e_value, "unit": "window-features/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                 "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps,
-                "returns": "CQT magnitudes + post-subtraction ref_mag per window"},
+                "returns": "CQT magnitudes + post-subtraction ref_mag per window",
+                "overlap": "%d window chunks on 3 streams (H2D | kernels | D2H)" % args.e2e_chunks},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -323,6 +324,7 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=12, help="windows in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cqt-impl", type=int, default=0)
+    ap.add_argument("--e2e-chunks", type=int, default=12, help="window chunks for H2D/compute/D2H overlap")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -427,10 +427,11 @@ def test_full_size_properties_one_hour(saga):
     c0 = ops.cqt_batch(wav[:8], cq)["mag"]
     c1 = ops.cqt_batch(torch.roll(wav[:8], 8 * 512, dims=1), cq)["mag"]
     assert float((c1[:, :, 120:400] - c0[:, :, 112:392]).abs().max()) <= 2e-5 * float(c0.max())
-    # (5) the pipeline with a zero guess is the identity on the window and gives D = dB(mag)
+    # (5) a guess placed at the window's end is clipped away (util_audio.py:250-251): the pipeline is
+    #     then the identity on the window and D = dB(mag)
     pipe = WindowFeaturePipeline(W, ns, ng)
     offs = torch.zeros((W, 1), device="cuda", dtype=torch.int32)
-    pipe.run(wav, torch.zeros_like(guess) + 1e-30, offs)
+    pipe.run(wav, guess, offs + 516)
     torch.cuda.synchronize()
     assert torch.equal(pipe.mag[:, :516, :1025], r["mag_storage"][:, :516, :1025])
     assert float(pipe.D.max()) <= 0.0 and float(pipe.D[:, :516, :1025].min()) >= -80.0
@@ -442,3 +443,25 @@ def test_full_size_properties_one_hour(saga):
     d = r["mag_storage"][:, :516, :1025] - pipe.mag[:, :516, :1025]
     assert float(d.min()) >= 0.0 and float(d[:, :100].abs().max()) == 0.0 and float(d[:, 228:].abs().max()) == 0.0
     assert float(d[:, 100:228].max()) > 0.0
+
+
+def test_run_host_chunked_equals_resident_run(saga):
+    """The overlapped host path (chunks on three streams) returns exactly what the
+    resident single-shot pass computes."""
+    from amt_saga_b200.pipeline import WindowFeaturePipeline
+    W, ns, ng = 7, 44100, 16384
+    pipe = WindowFeaturePipeline(W, ns, ng)
+    wav = np.stack([piano_clip(700 + i, ns, n_notes=5) for i in range(W)])
+    gue = np.stack([piano_clip(800 + i, ng, n_notes=1) for i in range(W)])
+    offs = (np.arange(W, dtype=np.int32) * 9 % 70).reshape(-1, 1)
+    pipe.run(dev(wav), dev(gue), dev(offs))
+    torch.cuda.synchronize()
+    C0, ref0, mag0 = pipe.C.clone(), pipe.ref.clone(), pipe.mag.clone()
+    h = pipe.host_buffers()
+    h["wav"].copy_(torch.from_numpy(wav)); h["guess"].copy_(torch.from_numpy(gue)); h["offs"].copy_(torch.from_numpy(offs))
+    for chunks in (1, 3, 7):
+        h["C"].zero_(); h["ref"].zero_()
+        pipe.run_host(chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(h["C"], C0.cpu()) and torch.equal(h["ref"], ref0.cpu())
+        assert torch.equal(pipe.mag, mag0)
