@@ -28,6 +28,7 @@ struct saga_stft_plan {
   int n_pass;
   int radix[3];
   float* d_window;   // n_fft floats
+  float* d_window_half;  // 0.5 * window (forward kernel)
   float2* d_tw[3];   // per pass: [R][L/R] inter-pass twiddles (last pass: unused)
   float2* d_twN;     // M/2 + 1 entries exp(-2*pi*i*k/n_fft)
   int warps;         // warps per CTA
@@ -111,7 +112,25 @@ __device__ __forceinline__ int zpos(int k) {
   return (k % R0) * L1 + ((k / R0) % R1) * L2 + (k / (R0 * R1));
 }
 
-template <int M, int R0, int R1, int R2, int WARPS>
+__device__ __forceinline__ float fast_sqrt(float x) {   // sqrt.approx: ~1 ulp, exact 0 -> 0
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One pair of bins (k, M-k) of the real-FFT split.  The window table carries the factor 1/2 of
+//   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W^k (Z[k] - conj Z[M-k]) ]
+// so with s = Zk + Zm (componentwise), d = Zk - Zm:  T = W^k * (s.y, -d.x),
+//   X[k] = (s.x + T.x, d.y + T.y),   X[M-k] = conj(s.x - T.x, d.y - T.y).
+__device__ __forceinline__ void split_pair(float2 zk, float2 zm, float2 w, float2& Xk, float2& Xm) {
+  const float sx = zk.x + zm.x, dx = zk.x - zm.x, sy = zk.y + zm.y, dy = zk.y - zm.y;
+  const float tx = fmaf(w.x, sy, w.y * dx);      // Re(w * (sy - i dx))
+  const float ty = fmaf(w.y, sy, -(w.x * dx));   // Im
+  Xk = make_float2(sx + tx, dy + ty);
+  Xm = make_float2(sx - tx, ty - dy);
+}
+
+template <int M, int R0, int R1, int R2, int WARPS, bool EXTRA>
 __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(const StftArgs a) {
   constexpr int N = 2 * M;
   constexpr int BUF = M + M / 32;
@@ -153,6 +172,14 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* buf = bufs + warp * BUF;
   const float2* win2 = reinterpret_cast<const float2*>(a.window);
+  // smem positions of Z[lane + 32 i] and of its partner Z[M - lane - 32 i] (digit-reversed order):
+  //   zpos is affine in i for a fixed lane, so both are base + i * step
+  const int zk0 = pidx(zpos<M, R0, R1, R2>(lane));
+  const int zk1 = pidx(zpos<M, R0, R1, R2>(lane + 32));
+  const int zm0 = pidx(zpos<M, R0, R1, R2>((M - lane) & (M - 1)));
+  const int zm1 = pidx(zpos<M, R0, R1, R2>(M - lane - 32));
+  const int zm2 = pidx(zpos<M, R0, R1, R2>(M - lane - 64));
+  const int zk_step = zk1 - zk0, zm_step = zm2 - zm1;
 
   for (int f = warp; f < nF; f += WARPS) {
     const float* xs = span + f * a.hop;
@@ -164,39 +191,64 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
     // ---- real-FFT split, |X|, outputs -----------------------------------
     const int64_t t = t0 + f;
     const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
-    float* mag = a.mag_out + row;
+    float* mag_up = a.mag_out + row + lane;           // bins lane + 32 i
+    float* mag_dn = a.mag_out + row + (M - lane);     // bins M - lane - 32 i
+    const float2* twp = a.twN + lane;
     float vmax = 0.f;
-#pragma unroll 1
-    for (int k = lane; k <= M / 2; k += 32) {
-      const float2 zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
-      const float2 zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
-      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-      const float2 Tw = cmul(__ldg(a.twN + k), O);
-      const float2 Xk = make_float2(E.x + Tw.x, E.y + Tw.y);
-      const float2 Xm = make_float2(E.x - Tw.x, -(E.y - Tw.y));
-      const float mk = sqrtf(Xk.x * Xk.x + Xk.y * Xk.y);
-      const float mm = sqrtf(Xm.x * Xm.x + Xm.y * Xm.y);
-      vmax = fmaxf(vmax, fmaxf(mk, mm));
-      mag[k] = mk;
-      if (k != M / 2) mag[M - k] = mm;
-      if (a.cplx_out) {
-        float2* c = a.cplx_out + row;
-        c[k] = Xk;
-        if (k != M / 2) c[M - k] = Xm;
+    constexpr int ITERS = M / 64;                     // k = lane + 32 i < M/2
+#pragma unroll 8
+    for (int i = 0; i < ITERS; ++i) {
+      float2 zk, zm;
+      if constexpr (R2 == 1) {      // two-pass shapes: both positions are affine in i
+        zk = buf[zk0 + i * zk_step];
+        zm = buf[i == 0 ? zm0 : zm1 + (i - 1) * zm_step];
+      } else {
+        const int k = lane + 32 * i;
+        zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
+        zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
       }
-      if (a.phase_out) {
-        float2* p = a.phase_out + row;
-        p[k] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
-        if (k != M / 2)
+      float2 Xk, Xm;
+      split_pair(zk, zm, __ldg(twp + 32 * i), Xk, Xm);
+      const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
+      const float mm = fast_sqrt(fmaf(Xm.x, Xm.x, Xm.y * Xm.y));
+      vmax = fmaxf(vmax, fmaxf(mk, mm));
+      mag_up[32 * i] = mk;
+      mag_dn[-32 * i] = mm;
+      if (EXTRA) {
+        const int k = lane + 32 * i;
+        if (a.cplx_out) {
+          float2* c = a.cplx_out + row;
+          c[k] = Xk;
+          c[M - k] = Xm;
+        }
+        if (a.phase_out) {
+          float2* p = a.phase_out + row;
+          p[k] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
           p[M - k] = mm > 0.f ? make_float2(Xm.x / mm, Xm.y / mm) : make_float2(1.f, 0.f);
+        }
+      }
+    }
+    if (lane == 0) {
+      // k = M/2 pairs with itself
+      const float2 z = buf[pidx(zpos<M, R0, R1, R2>(M / 2))];
+      float2 Xk, Xm;
+      split_pair(z, z, __ldg(a.twN + M / 2), Xk, Xm);
+      const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
+      vmax = fmaxf(vmax, mk);
+      a.mag_out[row + M / 2] = mk;
+      if (EXTRA) {
+        if (a.cplx_out) a.cplx_out[row + M / 2] = Xk;
+        if (a.phase_out)
+          a.phase_out[row + M / 2] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
       }
     }
     // padding columns [M+1, frame_pitch) are defined as zero
     for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += 32) {
-      mag[k] = 0.f;
-      if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
-      if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
+      a.mag_out[row + k] = 0.f;
+      if (EXTRA) {
+        if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+        if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
+      }
     }
     vmax = warp_max(vmax);
     if (lane == 0) {
@@ -209,12 +261,9 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
 
 template <int M, int R0, int R1, int R2, int WARPS>
 static int launch_stft(const saga_stft_plan* p, const StftArgs& a, int n_clips, cudaStream_t st) {
-  auto kern = stft_kernel<M, R0, R1, R2, WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SAGA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  const bool extra = a.phase_out || a.cplx_out;
+  auto kern = extra ? stft_kernel<M, R0, R1, R2, WARPS, true> : stft_kernel<M, R0, R1, R2, WARPS, false>;
+  SAGA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t blocks = (int64_t)n_clips * a.tiles_per_clip;
   if (blocks <= 0) return SAGA_OK;
   if (blocks > 0x7fffffffLL) return set_error(SAGA_ERR_INVALID, "stft: grid too large");
@@ -395,6 +444,11 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
     win[n] = window_host ? window_host[n] : (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / n_fft));
   SAGA_CUDA_OK(cudaMalloc(&p->d_window, sizeof(float) * n_fft));
   SAGA_CUDA_OK(cudaMemcpy(p->d_window, win.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+  // forward transform: the 1/2 of the real-FFT split is folded into the analysis window (exact: power of two)
+  std::vector<float> half_win(n_fft);
+  for (int n = 0; n < n_fft; ++n) half_win[n] = 0.5f * win[n];
+  SAGA_CUDA_OK(cudaMalloc(&p->d_window_half, sizeof(float) * n_fft));
+  SAGA_CUDA_OK(cudaMemcpy(p->d_window_half, half_win.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
 
   // inter-pass twiddles: pass with block length L and radix R multiplies output r' of
   // the small FFT at in-block offset j by exp(-2*pi*i*j*r'/L); table layout [r'][j].
@@ -443,6 +497,7 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
 extern "C" int saga_stft_plan_destroy(saga_stft_plan* p) {
   if (!p) return SAGA_OK;
   cudaFree(p->d_window);
+  cudaFree(p->d_window_half);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_tw[i]);
   cudaFree(p->d_twN);
   delete p;
@@ -479,7 +534,7 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
   a.cplx_out = (float2*)cplx_out;
   a.frame_max_out = frame_max_out;
   a.clip_max_out = clip_max_out;
-  a.window = p->d_window;
+  a.window = p->d_window_half;
   a.tw0 = p->d_tw[0];
   a.tw1 = p->d_tw[1];
   a.twN = p->d_twN;
