@@ -31,7 +31,7 @@ constexpr int DEC_PER_THREAD = 4;
 
 __global__ void __launch_bounds__(DEC_THREADS)
 decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets,
-                int64_t in_stride, const int64_t* __restrict__ clip_lens, int in_shift,
+                int64_t in_stride, const int64_t* __restrict__ clip_lens, int64_t max_len, int in_shift,
                 int in_factor_total, float* __restrict__ out, int64_t out_stride,
                 const float* __restrict__ taps, int n_taps, int factor) {
   extern __shared__ float sm[];
@@ -40,7 +40,7 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   float* xs = sm + ((n_taps + 3) & ~3);  // tile of input
   const int clip = blockIdx.y;
   // length of this clip at the INPUT level of this stage
-  int64_t len = clip_lens[clip];
+  int64_t len = clip_lens ? clip_lens[clip] : max_len;   // NULL = equal-length batch
   if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;  // early stage
   for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;                        // halvings
   const int64_t n_full = len / factor;
@@ -83,16 +83,17 @@ constexpr int DEC2_OUT = 4;                         // outputs per thread
 constexpr int DEC2_S = 31;
 constexpr int DEC2_TILE = DEC2_THREADS * DEC2_OUT;  // outputs per CTA
 constexpr int DEC2_HALF = DEC2_TILE + 32;           // even (or odd) samples staged per CTA
+struct Dec2Taps { float t[DEC2_S + 1]; };           // by value: lives in the constant bank, feeds FFMA directly
 
 __global__ void __launch_bounds__(DEC2_THREADS)
 decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
-                 const int64_t* __restrict__ clip_lens, int in_shift, int in_factor_total,
-                 float* __restrict__ out, int64_t out_stride, const float* __restrict__ taps) {
+                 const int64_t* __restrict__ clip_lens, int64_t max_len, int in_shift, int in_factor_total,
+                 float* __restrict__ out, int64_t out_stride, const Dec2Taps taps) {
   // tile covers input samples [2*o0 - 32, 2*o0 + 2*TILE + 32)
   __shared__ __align__(16) float xe[DEC2_HALF + 4];
   __shared__ __align__(16) float xo[DEC2_HALF + 4];
   const int clip = blockIdx.y;
-  int64_t len = clip_lens[clip];
+  int64_t len = clip_lens ? clip_lens[clip] : max_len;   // NULL = equal-length batch
   if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;
   for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;
   const int64_t n_full = len >> 1, n_out = (len + 1) >> 1;
@@ -115,9 +116,7 @@ decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_of
       if (i & 1) xo[i >> 1] = v; else xe[i >> 1] = v;
     }
   }
-  float tp[DEC2_S + 1];
-#pragma unroll
-  for (int m = 0; m <= DEC2_S; ++m) tp[m] = __ldg(taps + m);
+  const float* tp = taps.t;
   __syncthreads();
   // output lo = 4*tid + u has its centre at even index c = lo + 16
   float we[36], wo[36];
@@ -162,7 +161,8 @@ struct ContractArgs {
   const float* sig;             // level signal base
   const int64_t* sig_offsets;   // optional per-clip offsets (level 0 without early stage = raw wav)
   int64_t sig_stride;
-  const int64_t* clip_lens;     // input-rate lengths
+  const int64_t* clip_lens;     // input-rate lengths (NULL: every clip has max_len samples)
+  int64_t max_len;
   int early_factor, level;
   const float* bank;            // [n_fft][ncol]
   int n_fft, ncol, hop, first_bin, n_bins;
@@ -182,7 +182,7 @@ cqt_contract_kernel(const ContractArgs a) {
   const int c0 = blockIdx.y * CT_FC;
   const int T = a.clip_frames[clip];
   if (t0 >= T) return;
-  int64_t len = a.clip_lens[clip];
+  int64_t len = a.clip_lens ? a.clip_lens[clip] : a.max_len;
   if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
   for (int s = 0; s < a.level; ++s) len = (len + 1) >> 1;
   const float* y = a.sig + (a.sig_offsets ? a.sig_offsets[clip] : (int64_t)clip * a.sig_stride);
@@ -244,11 +244,11 @@ cqt_contract_kernel(const ContractArgs a) {
 }
 
 // per-clip output frame count = min over octaves of 1 + len_o // hop_o (librosa __trim_stack)
-__global__ void cqt_frames_kernel(const int64_t* clip_lens, int n_clips, int early_factor,
+__global__ void cqt_frames_kernel(const int64_t* clip_lens, int64_t max_len, int n_clips, int early_factor,
                                   const int* levels, const int* hops, int n_oct, int32_t* out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_clips) return;
-  int64_t len0 = clip_lens[c];
+  int64_t len0 = clip_lens ? clip_lens[c] : max_len;
   if (len0 <= 0) { out[c] = 0; return; }
   if (early_factor > 1) len0 = (len0 + early_factor - 1) / early_factor;
   int64_t best = INT32_MAX;
@@ -297,6 +297,7 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
     if (cudaMalloc(&p->d_early_taps, sizeof(float) * d->n_early_taps) != cudaSuccess)
       return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
     cudaMemcpy(p->d_early_taps, d->early_taps_host, sizeof(float) * d->n_early_taps, cudaMemcpyHostToDevice);
+    for (int i = 0; i < 32 && i < d->n_early_taps; ++i) p->early_taps2[i] = d->early_taps_host[i];
   }
   std::vector<int> levels, hops;
   for (int o = 0; o < d->n_octaves; ++o) {
@@ -322,6 +323,7 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
     if (cudaMalloc(&p->d_half_taps, sizeof(float) * d->n_half_taps) != cudaSuccess)
       return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
     cudaMemcpy(p->d_half_taps, d->half_taps_host, sizeof(float) * d->n_half_taps, cudaMemcpyHostToDevice);
+    for (int i = 0; i < 32 && i < d->n_half_taps; ++i) p->half_taps2[i] = d->half_taps_host[i];
   }
   cudaMalloc(&p->d_levels, sizeof(int) * levels.size());
   cudaMalloc(&p->d_hops, sizeof(int) * hops.size());
@@ -369,7 +371,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
                              const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
                              void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
                              void* workspace, int64_t workspace_bytes, int impl, void* stream) {
-  if (!p || !wav || !clip_offsets || !clip_lens || !C_mag_out || !workspace)
+  if (!p || !wav || !clip_offsets || !C_mag_out || !workspace)
     return set_error(SAGA_ERR_INVALID, "cqt_exec: null argument");
   if (frame_pitch < p->n_bins) return set_error(SAGA_ERR_INVALID, "cqt_exec: frame_pitch < n_bins");
   if (n_clips <= 0 || max_len <= 0) return SAGA_OK;
@@ -379,6 +381,8 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t T_max = saga_cqt_num_frames(p, max_len);
+  const bool do_cascade = !(impl & SAGA_CQT_SKIP_CASCADE), do_contract = !(impl & SAGA_CQT_SKIP_CONTRACT);
+  impl &= 0xFF;
 
   // ---- carve the workspace -------------------------------------------------------
   char* ws = (char*)workspace;
@@ -393,14 +397,14 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     ws += (int64_t)n_clips * pitch[l] * 4;
   }
 
-  cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, n_clips, p->early_factor,
+  cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, max_len, n_clips, p->early_factor,
                                                            p->d_levels, p->d_hops, (int)p->oct.size(),
                                                            clip_frames);
   SAGA_LAUNCH_CHECK();
 
   // ---- decimation cascade ----------------------------------------------------------
   const int tile_out = DEC_THREADS * DEC_PER_THREAD;
-  if (p->early_factor > 1) {
+  if (do_cascade && p->early_factor > 1) {
     const int64_t n_out = level_len(max_len, p->early_factor, 0);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
     const size_t smem = sizeof(float) * (((p->n_early_taps + 3) & ~3) + tile_out * p->early_factor + 2 * (p->n_early_taps - 1));
@@ -409,15 +413,15 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p->early_factor == 2 && p->n_early_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
-      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
-                                                    p->d_early_taps);
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0], pitch[0],
+                                                    *reinterpret_cast<const Dec2Taps*>(p->early_taps2));
     } else {
-      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, 0, 1, lvl[0], pitch[0],
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0], pitch[0],
                                                        p->d_early_taps, p->n_early_taps, p->early_factor);
     }
     SAGA_LAUNCH_CHECK();
   }
-  for (int l = 1; l <= p->max_level; ++l) {
+  for (int l = 1; do_cascade && l <= p->max_level; ++l) {
     const int64_t n_out = level_len(max_len, p->early_factor, l);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
     const size_t smem = sizeof(float) * (((p->n_half_taps + 3) & ~3) + tile_out * 2 + 2 * (p->n_half_taps - 1));
@@ -425,20 +429,21 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     if (p->n_half_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
       decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
-                                                    from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
-                                                    p->early_factor, lvl[l], pitch[l], p->d_half_taps);
+                                                    from_wav ? 0 : pitch[l - 1], clip_lens, max_len, l - 1,
+                                                    p->early_factor, lvl[l], pitch[l], *reinterpret_cast<const Dec2Taps*>(p->half_taps2));
     } else {
       decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
-                                                       from_wav ? 0 : pitch[l - 1], clip_lens, l - 1,
+                                                       from_wav ? 0 : pitch[l - 1], clip_lens, max_len, l - 1,
                                                        p->early_factor, lvl[l], pitch[l], p->d_half_taps,
                                                        p->n_half_taps, 2);
     }
     SAGA_LAUNCH_CHECK();
   }
 
+  if (!do_contract) return SAGA_OK;
   // ---- contraction -------------------------------------------------------------------
   CqtLevels lv;
-  lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens;
+  lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
   lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.clip_frames = clip_frames;
   if (impl != 1) {
     int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
@@ -454,6 +459,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     a.sig_offsets = raw ? clip_offsets : nullptr;
     a.sig_stride = raw ? 0 : pitch[o.level];
     a.clip_lens = clip_lens;
+    a.max_len = max_len;
     a.early_factor = p->early_factor;
     a.level = o.level;
     a.bank = o.bank;

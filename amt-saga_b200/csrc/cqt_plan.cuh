@@ -19,6 +19,8 @@ struct saga_cqt_plan {
   int n_early_taps, n_half_taps;
   float* d_early_taps;
   float* d_half_taps;
+  float early_taps2[32] = {0};   // host copies of the 32-tap (63-point symmetric) 2:1 decimators,
+  float half_taps2[32] = {0};    // passed to the kernel by value
   int* d_levels;
   int* d_hops;
   int max_level;
@@ -32,7 +34,8 @@ namespace saga {
 struct CqtLevels {
   const float* wav;
   const int64_t* clip_offsets;
-  const int64_t* clip_lens;
+  const int64_t* clip_lens;  // NULL: every clip has max_len samples
+  int64_t max_len;
   float* const* lvl;        // [max_level+1] device buffers (lvl[0]==nullptr when early_factor==1)
   const int64_t* pitch;     // per-clip pitch of each level buffer
   const int32_t* clip_frames;

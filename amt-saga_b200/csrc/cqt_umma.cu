@@ -24,8 +24,7 @@
 // bound by how fast ONE thread can issue MMAs: descriptors are built once per
 // stage and advanced by adding to their low word.
 //
-// Warp roles per persistent CTA (one per SM): 8 producer warps (global -> split
-// -> planes), 4 MMA issuer warps (one elected thread each; K-slices dealt round
+// Warp roles per persistent CTA (one per SM): 16 producer warps (L2 -> cp.async -> planes; lo = x - trunc13(x)), 4 MMA issuer warps (one elected thread each; K-slices dealt round
 // robin, each warp accumulating into its own TMEM column group, because with
 // N <= 64 an MMA retires in 16-32 cycles and a single issuing thread cannot keep
 // up -- profiles/microbench/umma_latency.cu), 4 epilogue warps (tcgen05.ld, sum of
@@ -34,6 +33,7 @@
 // B descriptor on the host) stays resident in SMEM while the CTA works through
 // items of one octave (items are ordered octave-major).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -43,15 +43,15 @@
 namespace saga {
 
 constexpr int UM_TILE_M = 128;
-constexpr int UM_PRODUCER_WARPS = 8;
+constexpr int UM_PRODUCER_WARPS = 16;
 constexpr int UM_EPI_WARPS = 4;
 constexpr int UM_MMA_WARPS = 4;             // issuer warps: K-slices round-robin, one TMEM column group each
 constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_PRODUCER_WARPS);   // 0-3 MMA, 4-7 epilogue, 8-15 producers
-constexpr int UM_STAGES = 4;
-constexpr int UM_PLANES_PER_STAGE = 4;      // 4 planes x 4 samples = 16 k-values per shift
+constexpr int UM_STAGES = 2;
+constexpr int UM_PLANES_PER_STAGE = 8;      // 8 planes x 4 samples = 32 k-values per shift
 constexpr int UM_MAX_OCT = 12;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
-constexpr int UM_PREFETCH = 2;              // producer look-ahead in stages (must be < UM_STAGES)
+constexpr int UM_PREFETCH = 1;              // producer look-ahead in stages (must be < UM_STAGES)
 
 struct UmmaOct {
   const float* sig;
@@ -78,6 +78,9 @@ struct UmmaArgs {
   uint32_t acc_stride;       // columns between the two accumulator buffers
   uint32_t grp_stride;       // columns between issuer-warp column groups (2*npad_max)
   int* error_flag;
+  int uniform_T;             // > 0: every clip has this many frames and `uniform_len` samples (no per-item loads)
+  int64_t uniform_len;
+  int debug;                 // profiling bisect (SAGA_UMMA_DEBUG): 1 = no MMAs, 2 = no producer data, 4 = no epilogue work
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -141,6 +144,75 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- multi-slice issue blocks -------------------------------------------------------------
+// STEPS consecutive K-slices of one issuer warp in ONE asm block: per slice the main MMA
+// (A_hi x [B_hi|B_lo], N = 2*npad) and the correction MMA (A_lo x B_hi, N = npad); then both A
+// descriptors advance by `da` and the B descriptor by `db` (16-byte units, added to the low word).
+// Keeping the descriptor arithmetic inside the block lets ptxas carry it in uniform registers
+// instead of re-broadcasting seven vector registers in front of every MMA.
+#define UM_ASM_HEAD                                   \
+  "{\n\t"                                             \
+  ".reg .pred e, p, t;\n\t"                           \
+  ".reg .b64 ah, al, bb, dda, ddb;\n\t"               \
+  "elect.sync _|e, 0xFFFFFFFF;\n\t"                   \
+  "setp.ne.b32 p, %6, 0;\n\t"                         \
+  "setp.eq.b32 t, 0, 0;\n\t"                          \
+  "mov.b64 ah, %1;\n\t"                               \
+  "mov.b64 al, %2;\n\t"                               \
+  "mov.b64 bb, %3;\n\t"                               \
+  "cvt.u64.u32 dda, %7;\n\t"                          \
+  "cvt.u64.u32 ddb, %8;\n\t"                          \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %4, p;\n\t" \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bb, %5, t;\n\t"
+#define UM_ASM_NEXT                                   \
+  "add.u64 ah, ah, dda;\n\t"                          \
+  "add.u64 al, al, dda;\n\t"                          \
+  "add.u64 bb, bb, ddb;\n\t"                          \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %4, t;\n\t" \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bb, %5, t;\n\t"
+#define UM_ASM_TAIL "}\n"
+#define UM_ASM_ARGS                                                                                        \
+  ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b), "r"(idesc_main), "r"(idesc_lo), "r"(accumulate), "r"(da), \
+      "r"(db)                                                                                             \
+      : "memory"
+
+__device__ __forceinline__ void tc_mma_split_x1(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                                uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate,
+                                                uint32_t da, uint32_t db) {
+  asm volatile(UM_ASM_HEAD UM_ASM_TAIL UM_ASM_ARGS);
+}
+__device__ __forceinline__ void tc_mma_split_x2(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                                uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate,
+                                                uint32_t da, uint32_t db) {
+  asm volatile(UM_ASM_HEAD UM_ASM_NEXT UM_ASM_TAIL UM_ASM_ARGS);
+}
+__device__ __forceinline__ void tc_mma_split_x4(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                                uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate,
+                                                uint32_t da, uint32_t db) {
+  asm volatile(UM_ASM_HEAD UM_ASM_NEXT UM_ASM_NEXT UM_ASM_NEXT UM_ASM_TAIL UM_ASM_ARGS);
+}
+// `steps` consecutive slices starting at (a_hi, a_lo, b)
+__device__ __forceinline__ void tc_mma_split_run(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                                 uint32_t idesc_main, uint32_t idesc_lo, uint32_t& accumulate,
+                                                 uint32_t da, uint32_t db, int steps) {
+  while (steps >= 4) {
+    tc_mma_split_x4(d_tmem, a_hi, a_lo, b, idesc_main, idesc_lo, accumulate, da, db);
+    accumulate = 1;
+    a_hi += 4ull * da; a_lo += 4ull * da; b += 4ull * db;
+    steps -= 4;
+  }
+  if (steps >= 2) {
+    tc_mma_split_x2(d_tmem, a_hi, a_lo, b, idesc_main, idesc_lo, accumulate, da, db);
+    accumulate = 1;
+    a_hi += 2ull * da; a_lo += 2ull * da; b += 2ull * db;
+    steps -= 2;
+  }
+  if (steps >= 1) {
+    tc_mma_split_x1(d_tmem, a_hi, a_lo, b, idesc_main, idesc_lo, accumulate, da, db);
+    accumulate = 1;
+  }
+}
+
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -173,12 +245,18 @@ __device__ __forceinline__ ItemInfo decode_item(const UmmaArgs& a, int64_t item)
   ItemInfo it;
   int o = 0;
   while (o + 1 < a.n_oct && item >= a.oct[o + 1].item_begin) ++o;
-  const int64_t local = item - a.oct[o].item_begin;
+  const uint32_t local = (uint32_t)(item - a.oct[o].item_begin);      // < n_clips * tiles_per_clip < 2^31
   it.o = o;
-  it.clip = (int)(local / a.tiles_per_clip);
-  it.t0 = (int)(local % a.tiles_per_clip) * UM_TILE_M;
-  it.T = a.clip_frames[it.clip];
-  int64_t len = a.clip_lens[it.clip];
+  it.clip = (int)(local / (uint32_t)a.tiles_per_clip);
+  it.t0 = (int)(local % (uint32_t)a.tiles_per_clip) * UM_TILE_M;
+  int64_t len;
+  if (a.uniform_T > 0) {          // equal-length batch: nothing to fetch
+    it.T = a.uniform_T;
+    len = a.uniform_len;
+  } else {
+    it.T = a.clip_frames[it.clip];
+    len = a.clip_lens[it.clip];
+  }
   if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
   for (int s = 0; s < a.oct[o].level; ++s) len = (len + 1) >> 1;
   it.len = len;
@@ -279,7 +357,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const uint32_t s = it_stage % UM_STAGES;
         mbar_wait_warp(&full[s], (it_stage / UM_STAGES) & 1, a.error_flag);
         tc_fence_after();
-        {
+        if (!(a.debug & 1)) {
           const uint32_t ah = smem_u32(a_base + (2 * s) * a.a_region_bytes);
           const uint32_t al = smem_u32(a_base + (2 * s + 1) * a.a_region_bytes);
           if (oc.planes >= 2) {
@@ -287,38 +365,56 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             const uint64_t dal0 = smem_desc(al, plane16 * 16u, 128);
             const int g0 = st * UM_PLANES_PER_STAGE;
             const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
-            const int np2_log = (np == 4) ? 1 : 0;                  // plane pairs per shift: 2 or 1
+            const int np2_log = 30 - __clz(np);                     // log2(plane pairs per shift): np = 2, 4, 8 -> 0, 1, 2
             const int n_slices = oc.Q << np2_log;
             const uint32_t bq = (uint32_t)oc.planes * bchunk16;
-            // this warp's K-slices: sl = warp, warp + 4, ...;  sl -> (shift q, plane pair p)
-            int sl = rr;
-            for (; sl < n_slices; sl += UM_MMA_WARPS) {
-              const uint32_t q = (uint32_t)(sl >> np2_log);
-              const uint32_t pp = (uint32_t)(sl & ((1 << np2_log) - 1)) * 2u;
-              const uint32_t a_off = pp * plane16 + q;
-              const uint64_t db = db0 + (uint64_t)(q * bq + ((uint32_t)g0 + pp) * bchunk16);
-              tc_mma_tf32(d_tmem, dah0 + a_off, db, idesc_main, accum);
-              accum = 1;
-              if (split) tc_mma_tf32(d_tmem, dal0 + a_off, db, idesc_n1, 1u);
+            if (split && rr == warp && (n_slices % UM_MMA_WARPS) == 0) {
+              // this warp's slices sl = warp + 4 i: shift q advances by 4 >> np2_log per step, the plane
+              // pair is fixed  ->  both descriptors are arithmetic progressions
+              const uint32_t q0 = (uint32_t)(warp >> np2_log);
+              const uint32_t pp = (uint32_t)(warp & ((1 << np2_log) - 1)) * 2u;
+              const uint32_t dq = (uint32_t)(UM_MMA_WARPS >> np2_log);   // needs pairs-per-shift <= UM_MMA_WARPS
+              const uint32_t a_off = pp * plane16 + q0;
+              const uint64_t db = db0 + (uint64_t)(q0 * bq + ((uint32_t)g0 + pp) * bchunk16);
+              tc_mma_split_run(d_tmem, dah0 + a_off, dal0 + a_off, db, idesc_main, idesc_n1, accum, dq, dq * bq,
+                               n_slices / UM_MMA_WARPS);
+            } else {
+              int sl = rr;
+              for (; sl < n_slices; sl += UM_MMA_WARPS) {
+                const uint32_t q = (uint32_t)(sl >> np2_log);
+                const uint32_t pp = (uint32_t)(sl & ((1 << np2_log) - 1)) * 2u;
+                const uint32_t a_off = pp * plane16 + q;
+                const uint64_t db = db0 + (uint64_t)(q * bq + ((uint32_t)g0 + pp) * bchunk16);
+                tc_mma_tf32(d_tmem, dah0 + a_off, db, idesc_main, accum);
+                accum = 1;
+                if (split) tc_mma_tf32(d_tmem, dal0 + a_off, db, idesc_n1, 1u);
+              }
+              rr = sl - n_slices;
             }
-            rr = sl - n_slices;
           } else {
             // hop == 4: one plane; the two K-chunks of an MMA are shifts q and q+1 (LBO = 16 B)
             const uint64_t dah0 = smem_desc(ah, 16, 128);
             const uint64_t dal0 = smem_desc(al, 16, 128);
-            int sl = rr;
-            for (; sl < (oc.Q >> 1); sl += UM_MMA_WARPS) {
-              const uint32_t q = 2u * (uint32_t)sl;
-              const uint64_t db = db0 + (uint64_t)(q * bchunk16);
-              tc_mma_tf32(d_tmem, dah0 + q, db, idesc_main, accum);
-              accum = 1;
-              if (split) tc_mma_tf32(d_tmem, dal0 + q, db, idesc_n1, 1u);
+            const int n_slices = oc.Q >> 1;
+            if (split && rr == warp && (n_slices % UM_MMA_WARPS) == 0) {
+              const uint32_t q0 = 2u * (uint32_t)warp;
+              tc_mma_split_run(d_tmem, dah0 + q0, dal0 + q0, db0 + (uint64_t)(q0 * bchunk16), idesc_main, idesc_n1,
+                               accum, 2u * UM_MMA_WARPS, 2u * UM_MMA_WARPS * bchunk16, n_slices / UM_MMA_WARPS);
+            } else {
+              int sl = rr;
+              for (; sl < n_slices; sl += UM_MMA_WARPS) {
+                const uint32_t q = 2u * (uint32_t)sl;
+                const uint64_t db = db0 + (uint64_t)(q * bchunk16);
+                tc_mma_tf32(d_tmem, dah0 + q, db, idesc_main, accum);
+                accum = 1;
+                if (split) tc_mma_tf32(d_tmem, dal0 + q, db, idesc_n1, 1u);
+              }
+              rr = sl - n_slices;
             }
-            rr = sl - (oc.Q >> 1);
           }
-          tc_commit(&empty[s]);                                 // smem stage reusable once these MMAs retire
-          if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);    // accumulator complete
         }
+        tc_commit(&empty[s]);                                   // smem stage reusable once these MMAs retire
+        if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);      // accumulator complete
         __syncwarp();
       }
       ++it_acc;
@@ -337,7 +433,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       const int t = inf.t0 + ew * 32 + lane;
       const int64_t row = (int64_t)inf.clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
       const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
-      for (int c0 = 0; c0 < oc.npad; c0 += 16) {
+      for (int c0 = 0; c0 < oc.npad && !(a.debug & 4); c0 += 16) {
         float sum[16];
 #pragma unroll
         for (int f = 0; f < 16; ++f) sum[f] = 0.f;
@@ -397,21 +493,36 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const int64_t origin = (int64_t)is.inf.t0 * oc.hop - (oc.n_fft >> 1);
         const int g0 = is.st * UM_PLANES_PER_STAGE;
         const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
-        const int lg = (np == 4) ? 2 : (np == 2 ? 1 : 0);
+        const int lg = 31 - __clz(np);
         const int total = np * oc.rows;
-        for (int e = ptid; e < total; e += PT) {
-          const int g = e & (np - 1), srow = e >> lg;
-          const int64_t idx = origin + (int64_t)srow * oc.hop + 4 * (g0 + g);
-          float4* dst = raw + (g * oc.rows_pad + srow);
-          if (base_al && idx >= 0 && idx + 3 < is.inf.len) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(y + idx) : "memory");
-          } else {
-            float4 x;
-            x.x = __ldg(y + reflect_index(idx, is.inf.len));
-            x.y = __ldg(y + reflect_index(idx + 1, is.inf.len));
-            x.z = __ldg(y + reflect_index(idx + 2, is.inf.len));
-            x.w = __ldg(y + reflect_index(idx + 3, is.inf.len));
-            *dst = x;
+        const int64_t first = origin + 4 * g0;                                  // sample index of element (row 0, plane g0)
+        const int64_t last = first + (int64_t)(oc.rows - 1) * oc.hop + 4 * np;  // one past the last sample touched
+        const uint32_t raw_s = smem_u32(raw);
+        if (a.debug & 2) {
+        } else if (base_al && first >= 0 && last <= is.inf.len) {
+          // interior tile: no bounds / reflection tests, 32-bit offsets
+          const float* src0 = y + first;
+          for (int e = ptid; e < total; e += PT) {
+            const int g = e & (np - 1), srow = e >> lg;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + 16u * (uint32_t)(g * oc.rows_pad + srow)),
+                         "l"(src0 + (srow * oc.hop + 4 * g))
+                         : "memory");
+          }
+        } else {
+          for (int e = ptid; e < total; e += PT) {
+            const int g = e & (np - 1), srow = e >> lg;
+            const int64_t idx = first + (int64_t)srow * oc.hop + 4 * g;
+            float4* dst = raw + (g * oc.rows_pad + srow);
+            if (base_al && idx >= 0 && idx + 3 < is.inf.len) {
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(y + idx) : "memory");
+            } else {
+              float4 x;
+              x.x = __ldg(y + reflect_index(idx, is.inf.len));
+              x.y = __ldg(y + reflect_index(idx + 1, is.inf.len));
+              x.z = __ldg(y + reflect_index(idx + 2, is.inf.len));
+              x.w = __ldg(y + reflect_index(idx + 3, is.inf.len));
+              *dst = x;
+            }
           }
         }
         have_issue = is.next(a);
@@ -438,19 +549,27 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         float4* dl = reinterpret_cast<float4*>(a_base + (2 * s + 1) * a.a_region_bytes);
         const int g0 = cv.st * UM_PLANES_PER_STAGE;
         const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
-        const int lg = (np == 4) ? 2 : (np == 2 ? 1 : 0);
+        const int lg = 31 - __clz(np);
         const int total = np * oc.rows;
-        for (int e = ptid; e < total; e += PT) {
+        for (int e = ptid; e < total && !(a.debug & 2); e += PT) {
           const int g = e & (np - 1), srow = e >> lg;
           const int d = g * oc.rows_pad + srow;
           const float4 x = dh[d];
-          float4 h;
-          h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-          dh[d] = h;
           if (split) {
+            // kind::tf32 reads only the top 19 bits of each operand (the low 13 mantissa bits are
+            // ignored), so the raw fp32 samples already ARE the hi operand: hi = trunc13(x), and
+            // lo = tf32(x - hi) is exact up to 2^-21 |x|.  Only the lo plane has to be written.
             float4 l;
-            l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+            l.x = to_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+            l.y = to_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+            l.z = to_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+            l.w = to_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
             dl[d] = l;
+          } else {
+            // single pass: round to nearest instead of the hardware's truncation
+            float4 h;
+            h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+            dh[d] = h;
           }
         }
         fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -612,6 +731,12 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.acc_stride = st->acc_stride;
   a.grp_stride = st->grp_stride;
   a.error_flag = st->d_error;
+  a.uniform_T = lv.clip_lens ? 0 : (int)T_max;
+  a.uniform_len = lv.max_len;
+  {
+    const char* dbg = getenv("SAGA_UMMA_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   const int64_t per_oct = (int64_t)n_clips * a.tiles_per_clip;
   for (int i = 0; i < a.n_oct; ++i) {
     const CqtOctaveDev& o = p->oct[i];

@@ -220,7 +220,8 @@ def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0):
     cx = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_complex else None
     nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
     ws = _workspace(nbytes, dev)
-    _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev), n_clips, max_len,
+    _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev) if lens is not None else None,
+                                 n_clips, max_len,
                                  _ptr(mag), _ptr(cx), P, T * P, _ptr(ws), ws.numel(), impl, _stream()),
                ParameterError)
     out = {"mag": bins_frames_view(mag, plan.n_bins), "mag_storage": mag}

@@ -98,9 +98,15 @@ class WindowFeaturePipeline:
         stage("stft", lambda: _lib.check(lib.saga_stft_exec(
             self.stft.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.mag), None, None,
             self.P, self.T_clip * self.P, p(self.frame_max), p(self.clip_max), st)))
-        stage("cqt", lambda: _lib.check(lib.saga_cqt_exec(
-            self.cqt.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.C), None,
-            self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl, st)))
+        def cqt(flags):
+            _lib.check(lib.saga_cqt_exec(
+                self.cqt.handle, p(wav), q(self.offs_w), None, W, self.ns, p(self.C), None,
+                self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl | flags, st))
+        if events is None:
+            cqt(0)
+        else:       # timed separately: decimation cascade, then the kernel-bank contraction
+            stage("cqt_cascade", lambda: cqt(0x100))
+            stage("cqt_contract", lambda: cqt(0x200))
         stage("stft_guess", lambda: _lib.check(lib.saga_stft_exec(
             self.stft.handle, p(guess_wav), q(self.offs_g), q(self.lens_g), W, self.ng, p(self.gmag), None,
             None, self.P, self.Tg * self.P, None, p(self.gmax), st)))

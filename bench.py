@@ -260,28 +260,42 @@ def run_saga(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # per-stage algorithmic work
+    # per-stage algorithmic work (DESIGN.md section 4)
     stft_bytes = W * 4 * (pipe.ns + pipe.T_clip * pipe.nb)
     gst_bytes = W * 4 * (pipe.ng + pipe.Tg * pipe.nb)
     sub_bytes = W * pipe.subtract_bytes_per_window()
     cqt_flops = W * pipe.cqt_flops_per_window()
+    casc_bytes = W * 4 * pipe.ns * 2          # each level read once, written once at half the length: <= 2x the input
+    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     stages = {
-        "stft": {"ms": stage_ms.get("stft"), "GBps": stft_bytes / stage_ms["stft"] / 1e6},
-        "stft_guess": {"ms": stage_ms.get("stft_guess"), "GBps": gst_bytes / stage_ms["stft_guess"] / 1e6},
-        "subtract_db": {"ms": stage_ms.get("subtract_db"), "GBps": sub_bytes / stage_ms["subtract_db"] / 1e6},
-        "cqt": {"ms": stage_ms.get("cqt"), "TFLOPs_algorithmic": cqt_flops / stage_ms["cqt"] / 1e9},
+        "stft": {"ms": stage_ms.get("stft"), "bound": "hbm", "GBps": stft_bytes / stage_ms["stft"] / 1e6},
+        "stft_guess": {"ms": stage_ms.get("stft_guess"), "bound": "hbm", "GBps": gst_bytes / stage_ms["stft_guess"] / 1e6},
+        "subtract_db": {"ms": stage_ms.get("subtract_db"), "bound": "hbm", "GBps": sub_bytes / stage_ms["subtract_db"] / 1e6},
+        "cqt_cascade": {"ms": stage_ms.get("cqt_cascade"), "bound": "hbm", "GBps": casc_bytes / stage_ms["cqt_cascade"] / 1e6},
+        "cqt_contract": {"ms": stage_ms.get("cqt_contract"), "bound": "tensor",
+                         "TFLOPs_algorithmic": cqt_flops / stage_ms["cqt_contract"] / 1e9,
+                         "TFLOPs_issued_tf32": cqt_flops * (96.0 / 24.0) / stage_ms["cqt_contract"] / 1e9},
     }
+    for k, v in stages.items():
+        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs_algorithmic"] / tpeak)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     dom = max(stage_ms, key=stage_ms.get)
-    if dom == "cqt":
-        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        roof = {"kernel": "cqt (decimation cascade + contraction)", "bound": "tensor",
-                "achieved": stages["cqt"]["TFLOPs_algorithmic"], "peak": tpeak, "unit": "TFLOP/s",
-                "frac": stages["cqt"]["TFLOPs_algorithmic"] / tpeak, "traffic": None,
-                "peak_source": "bf16 sustained, " + peak_src}
+    tr = traffic.get(dom, {}).get("bytes")
+    if stages[dom]["bound"] == "tensor":
+        roof = {"kernel": "cqt_umma_kernel (tcgen05 kernel-bank contraction)", "bound": "tensor",
+                "achieved": stages[dom]["TFLOPs_algorithmic"], "peak": tpeak, "unit": "TFLOP/s",
+                "frac": stages[dom]["frac"], "traffic": tr,
+                "peak_source": "cuBLAS bf16 sustained, " + peak_src,
+                "note": "algorithmic flops = 172704/frame (SURVEY 8d); the 3xTF32 split issues 4x that (N=64 main + N=32 correction MMA per 24 useful columns); "
+                        "tcgen05 dispatch floor for N<=64 is 44-48 cycles/MMA (profiles/microbench)"}
     else:
         ach = stages[dom]["GBps"]
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src}
+                "frac": ach / hbm_peak, "traffic": tr, "peak_source": peak_src}
 
     cpu = None
     if world == 1 and args.cpu_windows > 0:
@@ -317,12 +331,12 @@ def run_saga(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="saga", choices=["saga", "reference"])
     ap.add_argument("--windows", type=int, default=600, help="6 s windows per GPU per step (600 = 1 h)")
     ap.add_argument("--cpu-windows", type=int, default=12, help="windows in the cpu_baseline sample (0 = skip)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cqt-impl", type=int, default=0)
     ap.add_argument("--e2e-chunks", type=int, default=12, help="window chunks for H2D/compute/D2H overlap")
     args = ap.parse_args()

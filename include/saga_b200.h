@@ -142,6 +142,8 @@ int saga_amplitude_to_db_exec(const float* mag, float* D_out, const float* ref, 
  * (amt-saga_b200/cqt_plan.py) produces this descriptor.
  * ---------------------------------------------------------------------- */
 typedef struct saga_cqt_plan saga_cqt_plan;
+#define SAGA_CQT_SKIP_CONTRACT 0x100
+#define SAGA_CQT_SKIP_CASCADE 0x200
 
 typedef struct saga_cqt_octave {
   int level;            /* number of 2:1 decimations after the early downsample */
@@ -171,12 +173,17 @@ int64_t saga_cqt_num_frames(const saga_cqt_plan* plan, int64_t len);
 /* bytes of device scratch saga_cqt_exec needs for this batch shape */
 int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* plan, int n_clips, int64_t max_len);
 
-/* C_mag_out: |C| frame-major: (clip c, frame t, bin k) at c*out_clip_stride + t*frame_pitch + k
+/* clip_lens may be NULL: every clip then has exactly max_len samples (equal-length batches skip
+ * the per-item length look-ups).
+ * C_mag_out: |C| frame-major: (clip c, frame t, bin k) at c*out_clip_stride + t*frame_pitch + k
  * C_cplx_out: optional float2 complex CQT, same indexing in float2 units
  * impl: 0 = default (tcgen05 tensor-core path, 3xTF32 split = fp32-grade accuracy, when the
  *       plan fits it, else the fp32 CUDA-core path), 1 = force the fp32 CUDA-core path
  *       (validation), 2 = force the tensor path (SAGA_ERR_UNSUPPORTED if it does not fit),
- *       3 = tensor path with a single TF32 pass (~3e-5 of peak) */
+ *       3 = tensor path with a single TF32 pass (measured 1.1e-4 of peak: NOT parity-grade)
+ *       | SAGA_CQT_SKIP_CONTRACT: run only the decimation cascade (fills the workspace)
+ *       | SAGA_CQT_SKIP_CASCADE:  run only the contraction on a workspace filled by an earlier call
+ *       (the two flags let a caller time / overlap the phases separately) */
 int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
                   const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
                   void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
