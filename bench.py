@@ -24,6 +24,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's banner / debug output on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 SR, N_FFT, HOP = 44100, 2048, 512
 WIN_SAMPLES = 6 * SR            # 264600 -> 517 STFT columns, window = first 516
