@@ -306,3 +306,84 @@ def amplitude_to_db_batch(mag_storage, n_bins, ref=None, amin=1e-5, top_db=80.0)
 
 def launch_count():
     return int(_lib.lib().saga_launch_count())
+
+
+# ---------------------------------------------------------------------------
+# K5: classifier feature gather
+# ---------------------------------------------------------------------------
+def compress_bands_batch(mag_storage, n_bins, edges, inv_scale=None):
+    """util_audio.compress_bands on frame-major storage [clips, T, P]: returns
+    frame-major [clips, T, Pb] whose [..., :n_bands].transpose is [bands, frames]."""
+    _require_cuda(mag_storage, "mag")
+    m = mag_storage if mag_storage.dim() == 3 else mag_storage.unsqueeze(0)
+    if m.stride(2) != 1 or m.dtype != torch.float32:
+        raise ValueError("mag must be frame-major float32 storage")
+    edges = np.ascontiguousarray(np.asarray(edges, dtype=np.int32))
+    n_bands = len(edges) - 1
+    if edges[-1] > n_bins:
+        raise ValueError("band edge beyond the spectrum")
+    n_clips, T, _ = m.shape
+    P = m.stride(1) if T > 1 else m.shape[2]
+    Pb = frame_pitch(n_bands)
+    out = torch.empty((n_clips, T, Pb), device=m.device, dtype=torch.float32)
+    if inv_scale is not None:
+        inv_scale = inv_scale.to(device=m.device, dtype=torch.float32).contiguous()
+    _lib.check(_lib.lib().saga_compress_bands_exec(
+        _ptr(m), _ptr(out), edges.ctypes.data_as(C.c_void_p), n_bands, n_clips, T, P,
+        m.stride(0) if n_clips > 1 else T * P, Pb, T * Pb, _ptr(inv_scale), _stream()))
+    return out
+
+
+def resize_indices(t, target):
+    """Source column of every output column of util_audio._resize (util_audio.py:384-409);
+    -1 marks the all-zero result of an empty slice."""
+    if t == 0:
+        return np.full(target, -1, dtype=np.int32)
+    if t == target:
+        return np.arange(target, dtype=np.int32)
+    if t < 3:
+        return np.array([0] + [t - 1] * (target - 1), dtype=np.int32)
+    if t < target:
+        lim = min(1, int(np.round(t / 3)))
+        reps = int(np.floor((target - 2 * lim) / (t - 2 * lim)))
+        mid = list(range(lim, t - lim)) * reps
+        tail = target - len(mid) - lim
+        return np.array(list(range(lim)) + mid + list(range(t - tail, t)), dtype=np.int32)
+    return np.arange(target, dtype=np.int32)
+
+
+def short_window_features(mag_st, phase_st, src_frames, band_min, n_rows, n_bins, inv_ref=1.0,
+                          want_lin=True, want_log=True, want_phase=False):
+    """One launch for resize + section_power + normalisations (training.py:337-363).
+    mag_st / phase_st: frame-major [T, P] storage of ONE window; src_frames: int32
+    window-frame index per output column (-1 = zeros).  Returns a dict of
+    [n_rows, n_cols] views (lin, log, phase)."""
+    _require_cuda(mag_st, "mag")
+    src = torch.as_tensor(np.asarray(src_frames, dtype=np.int32), device=mag_st.device)
+    n_cols = int(src.numel())
+    P = mag_st.stride(0) if mag_st.shape[0] > 1 else mag_st.shape[1]
+    Po = frame_pitch(n_rows)
+    mk = lambda on: torch.zeros((n_cols, Po), device=mag_st.device, dtype=torch.float32) if on else None
+    lin, log, pha = mk(want_lin), mk(want_log), mk(want_phase)
+    ph_ptr = None
+    if want_phase:
+        if phase_st is None or phase_st.stride(0) != mag_st.stride(0):
+            raise ValueError("phase storage must match the magnitude storage")
+        ph_ptr = _ptr(torch.view_as_real(phase_st))
+    _lib.check(_lib.lib().saga_short_window_exec(
+        _ptr(mag_st), ph_ptr, _ptr(src), n_cols, int(band_min), int(n_rows), int(n_bins), P, float(inv_ref),
+        _ptr(lin), _ptr(log), _ptr(pha), Po, _stream()))
+    view = lambda x: None if x is None else x[:, :n_rows].transpose(0, 1)
+    return {"lin": view(lin), "log": view(log), "phase": view(pha)}
+
+
+def spectral_flatness_batch(mag_storage, n_bins, amin=1e-10):
+    """librosa.feature.spectral_flatness(power=2) per frame: [clips, T]."""
+    m = mag_storage if mag_storage.dim() == 3 else mag_storage.unsqueeze(0)
+    _require_cuda(m, "mag")
+    n_clips, T, _ = m.shape
+    P = m.stride(1) if T > 1 else m.shape[2]
+    out = torch.empty((n_clips, T), device=m.device, dtype=torch.float32)
+    _lib.check(_lib.lib().saga_spectral_flatness_exec(
+        _ptr(m), _ptr(out), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P, float(amin), _stream()))
+    return out

@@ -440,11 +440,28 @@ class audio_complete:
 
     def spectral_flatness(self):
         """util_audio.py:330-332 (librosa.feature.spectral_flatness, power 2, amin 1e-10)."""
-        r = ops.stft_batch(self._wave(), ops.get_stft_plan(int(self.N), int(self.hl), True),
-                           want_max=False)
-        S = torch.clamp(r["mag"][0].double() ** 2, min=1e-10)
-        flat = torch.exp(torch.mean(torch.log(S), dim=0)) / torch.mean(S, dim=0)
-        return float(flat.mean().item())
+        plan = ops.get_stft_plan(int(self.N), int(self.hl), True)
+        r = ops.stft_batch(self._wave(), plan, want_max=False)
+        flat = ops.spectral_flatness_batch(r["mag_storage"], plan.n_bins)
+        return float(flat.double().mean().item())
+
+    def short_window_features(self, start, duration, target_frame_count, band_min, n_rows,
+                              ref=None, want_phase=True):
+        """Fused form of the producer loop's short-window block (training.py:337-363):
+        resize(start, duration, target, ['mag','ph']) -> section_power(band_min, band_min+n_rows)
+        -> x/ref, log10(1000x+1)/max, (angle(ph)+3.15)/6.3 in ONE kernel launch.  Returns a dict of
+        [n_rows, target] arrays: lin, log, phase."""
+        t = self._seconds_to_frames(start + duration)
+        s = self._seconds_to_frames(start)
+        m = self._spec_mag()
+        s_c, t_c = min(max(s, 0), m.T), min(max(t, 0), m.T)
+        idx = ops.resize_indices(max(t_c - s_c, 0), target_frame_count)
+        src = np.where(idx >= 0, idx + s_c, -1).astype(np.int32)
+        ph = self._spec_ph() if want_phase else None
+        inv = 1.0 / float(ref if ref is not None else self.ref_mag)
+        r = ops.short_window_features(m.st, None if ph is None else ph.st, src, band_min, n_rows, m.nb,
+                                      inv_ref=inv, want_phase=want_phase)
+        return {k: self._out(v) for k, v in r.items()}
 
     def section_power(self, name, band_min, band_max):
         """util_audio.py:334-349."""
@@ -493,7 +510,8 @@ class audio_complete:
 
     @staticmethod
     def compress_bands(spectrum, bands=80, log=True):
-        """util_audio.py:436-466: mean over (log-spaced) groups of rows."""
+        """util_audio.py:436-466: mean over (log-spaced) groups of rows; CUDA tensors go through
+        saga_compress_bands_exec, host arrays are averaged on the host like the reference."""
         n_rows = spectrum.shape[0]
         edges = band_edges(n_rows, bands) if log else np.arange(bands + 1) * (n_rows // bands)
         if isinstance(spectrum, np.ndarray):
@@ -501,10 +519,11 @@ class audio_complete:
             for i in range(bands):
                 out[i] = np.mean(spectrum[int(edges[i]):int(edges[i + 1]), :], axis=0)
             return out
-        csum = torch.cat((torch.zeros((1, spectrum.shape[1]), device=spectrum.device, dtype=torch.float64),
-                          torch.cumsum(spectrum.double(), dim=0)), dim=0)
-        e = torch.as_tensor(np.asarray(edges, dtype=np.int64), device=spectrum.device)
-        return (csum[e[1:]] - csum[e[:-1]]) / (e[1:] - e[:-1]).unsqueeze(1).double()
+        st = spectrum.transpose(0, 1)
+        if st.stride(1) != 1 or st.dtype != torch.float32 or (st.shape[0] > 1 and st.stride(0) < n_rows):
+            st = _Spec.from_view(spectrum, torch.float32, spectrum.device).st
+        out = ops.compress_bands_batch(st.unsqueeze(0), n_rows, edges)
+        return out[0, :, :bands].transpose(0, 1)
 
     def resize(self, start, duration, target_frame_count, attribs=("F",)):
         """util_audio.py:469-507."""

@@ -189,6 +189,29 @@ int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* cl
                   void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
                   void* workspace, int64_t workspace_bytes, int impl, void* stream);
 
+/* ------------------------------------------------------------------------
+ * K5  feature gather for the classifiers (training.py:333-388)
+ * ---------------------------------------------------------------------- */
+/* util_audio.py:436-466 compress_bands: out[t][b] = mean(mag[t][e[b] : e[b+1]]) * inv_scale[clip]
+ * (inv_scale optional, e.g. 1/song ref_mag of training.py:335-336); band_edges_host has n_bands+1 ints. */
+int saga_compress_bands_exec(const float* mag, float* out, const int32_t* band_edges_host, int n_bands,
+                             int n_clips, int n_frames, int64_t frame_pitch, int64_t clip_stride,
+                             int64_t out_pitch, int64_t out_clip_stride, const float* inv_scale,
+                             void* stream);
+
+/* util_audio.py:469-507 resize + :334-349 section_power + training.py:347-363 normalisations in one
+ * launch.  Output column j (of n_cols) copies window frame src_frames[j] (device int32; -1 = zeros), rows
+ * are bins [band_min, band_min+n_rows) zero-padded past n_bins; outputs are frame-major [n_cols][out_pitch]:
+ *   out_lin = mag * inv_ref,  out_log = log10(1000 mag + 1) / max(.),  out_phase = (angle(ph)+3.15)/6.3
+ * (each optional; phase = float2 unit phasors, may be NULL when out_phase is NULL). */
+int saga_short_window_exec(const float* mag, const void* phase, const int32_t* src_frames, int n_cols,
+                           int band_min, int n_rows, int n_bins, int64_t frame_pitch, float inv_ref,
+                           float* out_lin, float* out_log, float* out_phase, int64_t out_pitch, void* stream);
+
+/* util_audio.py:330-332 librosa.feature.spectral_flatness(power=2): flatness_out[clip*n_frames + t] */
+int saga_spectral_flatness_exec(const float* mag, float* flatness_out, int n_clips, int n_bins, int n_frames,
+                                int64_t frame_pitch, int64_t clip_stride, float amin, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

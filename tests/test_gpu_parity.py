@@ -465,3 +465,40 @@ def test_run_host_chunked_equals_resident_run(saga):
         torch.cuda.synchronize()
         assert torch.equal(h["C"], C0.cpu()) and torch.equal(h["ref"], ref0.cpu())
         assert torch.equal(pipe.mag, mag0)
+
+
+# --------------------------------------------------------------------------- K5 feature gather
+def test_feature_gather_matches_oracle_sequence(saga):
+    """compress_bands, the fused short-window block and spectral flatness vs the
+    oracle doing the reference's call sequence (training.py:333-363)."""
+    ops, ua = saga
+    sr, N = 44100, 4096
+    song = piano_clip(91, sr * 7)
+    a, o = ua.audio_complete(song, N), AudioOracle(song, N)
+    a.mag, o.mag
+    aw, ow = a.section(0, None, 258), o.section(0, None, 258)
+    # C_timing (training.py:333-336)
+    ct = ua.audio_complete._resize(ua.audio_complete.compress_bands(aw.mag, bands=20), 258) / float(a.ref_mag)
+    cto = AudioOracle._resize(AudioOracle.compress_bands(ow.mag, bands=20), 258) / o.ref_mag
+    check_mag(ct.cpu().numpy(), cto, tol=1e-5)
+    assert abs(a.spectral_flatness() - o.spectral_flatness()) <= 1e-5
+    for onset, dur, pitch in ((0.7, 0.9, 60), (2.0, 0.02, 40), (4.1, 3.0, 88), (5.9, 0.5, 100)):
+        b0 = aw.midi_tone_to_FFT(pitch)
+        f = aw.short_window_features(onset, dur, 8, b0, 348, ref=a.ref_mag)
+        so = ow.resize(onset, dur, 8, attribs=["mag", "ph"])
+        lin = so.section_power("mag", b0, b0 + 348)
+        log = np.log10(lin * 1000 + 1)
+        log /= np.max(log)
+        pha = (np.angle(so.section_power("ph", b0, b0 + 348)) + 3.15) / 6.3
+        assert tuple(f["lin"].shape) == lin.shape == (348, 8)
+        check_mag(f["lin"].cpu().numpy(), lin / o.ref_mag, tol=2e-5)
+        assert np.abs(f["log"].cpu().numpy() - log).max() <= 2e-4
+        big = lin > 1e-3 * lin.max()            # phase is noise where the magnitude is
+        assert np.abs(f["phase"].cpu().numpy() - pha)[big].max() <= 2e-3
+    for t in (0, 1, 2, 3, 5, 8, 11, 300):
+        for target in (8, 258):
+            idx = ops.resize_indices(t, target)
+            P = np.arange(t, dtype=float)[None, :]
+            exp = AudioOracle._resize(P, target)[0]
+            got = np.where(idx >= 0, P[0][np.clip(idx, 0, max(t - 1, 0))] if t else 0.0, 0.0)
+            assert np.array_equal(got, exp)
