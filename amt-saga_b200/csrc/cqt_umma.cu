@@ -33,6 +33,7 @@
 // B descriptor on the host) stays resident in SMEM while the CTA works through
 // items of one octave (items are ordered octave-major).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -47,11 +48,9 @@ constexpr int UM_PRODUCER_WARPS = 16;
 constexpr int UM_EPI_WARPS = 4;
 constexpr int UM_MMA_WARPS = 4;             // issuer warps: K-slices round-robin, one TMEM column group each
 constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_PRODUCER_WARPS);   // 0-3 MMA, 4-7 epilogue, 8-15 producers
-constexpr int UM_STAGES = 2;
-constexpr int UM_PLANES_PER_STAGE = 8;      // 8 planes x 4 samples = 32 k-values per shift
+constexpr int UM_MAX_STAGES = 6;            // barrier array capacity; the actual count is a plan parameter
 constexpr int UM_MAX_OCT = 12;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
-constexpr int UM_PREFETCH = 1;              // producer look-ahead in stages (must be < UM_STAGES)
 
 struct UmmaOct {
   const float* sig;
@@ -78,6 +77,7 @@ struct UmmaArgs {
   uint32_t acc_stride;       // columns between the two accumulator buffers
   uint32_t grp_stride;       // columns between issuer-warp column groups (2*npad_max)
   int* error_flag;
+  int stages, pps, prefetch; // pipeline shape: SMEM stages, planes per stage (4 or 8), producer look-ahead (< stages)
   int uniform_T;             // > 0: every clip has this many frames and `uniform_len` samples (no per-item loads)
   int64_t uniform_len;
   int debug;                 // profiling bisect (SAGA_UMMA_DEBUG): 1 = no MMAs, 2 = no producer data, 4 = no epilogue work
@@ -296,19 +296,20 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* b_s = smem_raw;
   uint8_t* a_base = b_s + a.b_region_bytes;                     // stages: [hi | lo] x UM_STAGES
+  const uint32_t UM_STAGES = (uint32_t)a.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + 2 * UM_STAGES * a.a_region_bytes);
-  uint64_t* full = bars;                    // [UM_STAGES]
-  uint64_t* empty = bars + UM_STAGES;       // [UM_STAGES]
-  uint64_t* tfull = bars + 2 * UM_STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * UM_STAGES + 2;  // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * UM_STAGES + 4);
+  uint64_t* full = bars;                        // [stages]
+  uint64_t* empty = bars + UM_MAX_STAGES;       // [stages]
+  uint64_t* tfull = bars + 2 * UM_MAX_STAGES;   // [2]
+  uint64_t* tempty = bars + 2 * UM_MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * UM_MAX_STAGES + 4);
 
   // broadcast so the compiler knows the role index is warp-uniform (keeps MMA operands in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < UM_STAGES; ++s) {
+    for (uint32_t s = 0; s < UM_STAGES; ++s) {
       mbar_init(&full[s], UM_PRODUCER_WARPS);
       mbar_init(&empty[s], UM_MMA_WARPS);
     }
@@ -363,8 +364,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
           if (oc.planes >= 2) {
             const uint64_t dah0 = smem_desc(ah, plane16 * 16u, 128);
             const uint64_t dal0 = smem_desc(al, plane16 * 16u, 128);
-            const int g0 = st * UM_PLANES_PER_STAGE;
-            const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+            const int g0 = st * a.pps;
+            const int np = min(a.pps, oc.planes - g0);
             const int np2_log = 30 - __clz(np);                     // log2(plane pairs per shift): np = 2, 4, 8 -> 0, 1, 2
             const int n_slices = oc.Q << np2_log;
             const uint32_t bq = (uint32_t)oc.planes * bchunk16;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   } else {
     // =========================== producers ===========================
     // Software pipeline over this CTA's (item, stage) jobs: job k's raw fp32 rows are fetched with
-    // cp.async (16 B, L2 -> SMEM, no register staging) UM_PREFETCH jobs ahead of their conversion, so
+    // cp.async (16 B, L2 -> SMEM, no register staging) a.prefetch jobs ahead of their conversion, so
     // several stages of L2 requests are in flight per SM; each thread later converts exactly the
     // elements it fetched (in place -> TF32 hi, plus lo), so cp.async.wait_group is the only sync.
     const int ptid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS);
@@ -491,8 +492,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[is.inf.clip] : (int64_t)is.inf.clip * oc.sig_stride);
         const bool base_al = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
         const int64_t origin = (int64_t)is.inf.t0 * oc.hop - (oc.n_fft >> 1);
-        const int g0 = is.st * UM_PLANES_PER_STAGE;
-        const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+        const int g0 = is.st * a.pps;
+        const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
         const int total = np * oc.rows;
         const int64_t first = origin + 4 * g0;                                  // sample index of element (row 0, plane g0)
@@ -528,10 +529,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         have_issue = is.next(a);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");      // one group per k, possibly empty
-      if (k < UM_PREFETCH) continue;
-      // ---- convert job k - UM_PREFETCH ------------------------------------------------------
+      if (k < a.prefetch) continue;
+      // ---- convert job k - a.prefetch ------------------------------------------------------
       if (!cv.next(a)) break;
-      const uint32_t kc = k - UM_PREFETCH;
+      const uint32_t kc = k - a.prefetch;
       const UmmaOct& oc = a.oct[cv.inf.o];
       if (cv.inf.o != cur_oct) {
         // new bank: every MMA that reads the old one must have retired
@@ -542,13 +543,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         for (int i = ptid; i < n16; i += PT) sb[i] = __ldg(gb + i);
         cur_oct = cv.inf.o;
       }
-      asm volatile("cp.async.wait_group %0;" ::"n"(UM_PREFETCH) : "memory");
+      if (a.prefetch == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else if (a.prefetch == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else asm volatile("cp.async.wait_group 3;" ::: "memory");
       {
         const uint32_t s = kc % UM_STAGES;
         float4* dh = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
         float4* dl = reinterpret_cast<float4*>(a_base + (2 * s + 1) * a.a_region_bytes);
-        const int g0 = cv.st * UM_PLANES_PER_STAGE;
-        const int np = min(UM_PLANES_PER_STAGE, oc.planes - g0);
+        const int g0 = cv.st * a.pps;
+        const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
         const int total = np * oc.rows;
         for (int e = ptid; e < total && !(a.debug & 2); e += PT) {
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             dh[d] = h;
           }
         }
-        fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (!(a.debug & 8)) fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
       }
@@ -614,6 +617,7 @@ struct CqtUmmaState {
   int* d_error = nullptr;
   int num_sms = 0;
   int n_split = 3;
+  int stages = 2, pps = 8, prefetch = 1;   // pipeline shape (SAGA_UMMA_CFG="stages,planes,prefetch" overrides)
 };
 
 namespace saga {
@@ -633,6 +637,13 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   CqtUmmaState* st = new CqtUmmaState();
   p->umma = st;
   if ((int)p->oct.size() > UM_MAX_OCT) return;
+  if (const char* cfg = getenv("SAGA_UMMA_CFG")) {
+    int a_ = 0, b_ = 0, c_ = 0;
+    if (sscanf(cfg, "%d,%d,%d", &a_, &b_, &c_) == 3 && a_ >= 2 && a_ <= UM_MAX_STAGES && (b_ == 4 || b_ == 8) && c_ >= 1 &&
+        c_ <= 3 && c_ < a_) {
+      st->stages = a_; st->pps = b_; st->prefetch = c_;
+    }
+  }
   uint32_t bmax = 0, amax = 0;
   int npad_max = 0;
   for (auto& o : p->oct) {
@@ -641,22 +652,22 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
     if (npad > 128) return;   // [hi|lo] operand: N = 2*npad <= 256
     if (o.hop < 4 || (o.hop % 4) != 0 || (o.n_fft % o.hop) != 0 || (o.n_fft % 8) != 0) return;
     const int planes = o.hop / 4;
-    if (planes >= 2 && (std::min(planes, UM_PLANES_PER_STAGE) % 2) != 0) return;
+    if (planes >= 2 && (std::min(planes, st->pps) % 2) != 0) return;
     const int Q = o.n_fft / o.hop;
     if (planes == 1 && (Q % 2) != 0) return;
-    const int np0 = std::min(planes, UM_PLANES_PER_STAGE);
+    const int np0 = std::min(planes, st->pps);
     const int slices = planes >= 2 ? Q * (np0 / 2) : Q / 2;      // K-slices per stage
-    const int n_st = (planes + UM_PLANES_PER_STAGE - 1) / UM_PLANES_PER_STAGE;
+    const int n_st = (planes + st->pps - 1) / st->pps;
     if (slices * n_st < UM_MMA_WARPS) return;                     // every issuer warp must get work in an item
     const int rows = UM_TILE_M + Q - 1;
     const int rows_pad = rows | 1;
     bmax = std::max<uint32_t>(bmax, (uint32_t)o.n_fft * 2u * npad * 4u);
-    amax = std::max<uint32_t>(amax, (uint32_t)std::min(planes, UM_PLANES_PER_STAGE) * rows_pad * 16u);
+    amax = std::max<uint32_t>(amax, (uint32_t)std::min(planes, st->pps) * rows_pad * 16u);
     npad_max = std::max(npad_max, npad);
   }
   amax = (amax + 127u) & ~127u;
   bmax = (bmax + 127u) & ~127u;
-  const size_t smem = (size_t)bmax + 2ull * UM_STAGES * amax + 256;
+  const size_t smem = (size_t)bmax + 2ull * st->stages * amax + 256;
   if (smem > 225 * 1024) return;
   uint32_t cols = 32;
   while (cols < 2u * UM_MMA_WARPS * 2u * npad_max) cols <<= 1;   // 2 buffers x issuer groups x (hi|lo)
@@ -731,6 +742,9 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.acc_stride = st->acc_stride;
   a.grp_stride = st->grp_stride;
   a.error_flag = st->d_error;
+  a.stages = st->stages;
+  a.pps = st->pps;
+  a.prefetch = st->prefetch;
   a.uniform_T = lv.clip_lens ? 0 : (int)T_max;
   a.uniform_len = lv.max_len;
   {
@@ -754,7 +768,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     u.first_bin = o.first_bin;
     u.planes = o.hop / 4;
     u.np_log2 = u.planes >= 4 ? 2 : (u.planes == 2 ? 1 : 0);
-    u.n_stages = (u.planes + UM_PLANES_PER_STAGE - 1) / UM_PLANES_PER_STAGE;
+    u.n_stages = (u.planes + st->pps - 1) / st->pps;
     u.Q = o.n_fft / o.hop;
     u.rows = UM_TILE_M + u.Q - 1;
     u.rows_pad = u.rows | 1;
