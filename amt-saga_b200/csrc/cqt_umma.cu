@@ -51,6 +51,7 @@ constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_PRODUCER_WARPS
 constexpr int UM_MAX_STAGES = 6;            // barrier array capacity; the actual count is a plan parameter
 constexpr int UM_MAX_OCT = 12;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
+constexpr int UM_PROF_SLOTS = 16;
 
 struct UmmaOct {
   const float* sig;
@@ -60,6 +61,7 @@ struct UmmaOct {
   int level, hop, n_fft, ncol, npad, first_bin;
   int planes, np_log2, n_stages, Q, rows, rows_pad;
   int64_t item_begin;
+  int64_t uniform_len;    // length of every clip at this octave's level (equal-length batches)
 };
 
 struct UmmaArgs {
@@ -80,7 +82,9 @@ struct UmmaArgs {
   int stages, pps, prefetch; // pipeline shape: SMEM stages, planes per stage (4 or 8), producer look-ahead (< stages)
   int uniform_T;             // > 0: every clip has this many frames and `uniform_len` samples (no per-item loads)
   int64_t uniform_len;
-  int debug;                 // profiling bisect (SAGA_UMMA_DEBUG): 1 = no MMAs, 2 = no producer data, 4 = no epilogue work
+  int debug;                 // profiling bisect (SAGA_UMMA_DEBUG): 1 = no MMAs, 2 = no producer data, 4 = no epilogue work,
+                             // 8 = no proxy fence, 16 = per-role cycle breakdown into `prof`
+  long long* prof;           // [grid][UM_PROF_SLOTS] cycle counters (debug & 16)
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -119,6 +123,9 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   mbar_wait(bar, parity, error_flag);
   __syncwarp();
 }
+// cycle breakdown (debug & 16): PROF_T(slot) adds the cycles since the previous mark to pr[slot]
+#define PROF_DECL const bool prof_on = (a.debug & 16) != 0; long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = prof_on ? clock64() : 0; const long long pt0 = pt
+#define PROF_T(slot) do { if (prof_on) { const long long n_ = clock64(); pr[slot] += n_ - pt; pt = n_; } } while (0)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -249,14 +256,13 @@ __device__ __forceinline__ ItemInfo decode_item(const UmmaArgs& a, int64_t item)
   it.o = o;
   it.clip = (int)(local / (uint32_t)a.tiles_per_clip);
   it.t0 = (int)(local % (uint32_t)a.tiles_per_clip) * UM_TILE_M;
-  int64_t len;
-  if (a.uniform_T > 0) {          // equal-length batch: nothing to fetch
+  if (a.uniform_T > 0) {          // equal-length batch: nothing to fetch or derive
     it.T = a.uniform_T;
-    len = a.uniform_len;
-  } else {
-    it.T = a.clip_frames[it.clip];
-    len = a.clip_lens[it.clip];
+    it.len = a.oct[o].uniform_len;
+    return it;
   }
+  it.T = a.clip_frames[it.clip];
+  int64_t len = a.clip_lens[it.clip];
   if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
   for (int s = 0; s < a.oct[o].level; ++s) len = (len + 1) >> 1;
   it.len = len;
@@ -335,10 +341,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   if (warp < UM_MMA_WARPS) {
     // =========================== MMA issuers ===========================
     uint32_t it_stage = 0, it_acc = 0;
+    PROF_DECL;
     for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
       const ItemInfo inf = decode_item(a, item);
       if (inf.t0 >= inf.T) continue;
       const UmmaOct& oc = a.oct[inf.o];
+      PROF_T(0);
       // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128; N = 2*npad (hi|lo) and N = npad
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UM_TILE_M >> 4) << 24);
       const uint32_t idesc_n1 = idesc_base | ((uint32_t)(oc.npad >> 3) << 17);
@@ -346,6 +354,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       const uint32_t acc = it_acc & 1;
       mbar_wait_warp(&tempty[acc], ((it_acc >> 1) & 1) ^ 1, a.error_flag);
       tc_fence_after();
+      PROF_T(1);
       const uint32_t d_tmem = tmem_base + acc * a.acc_stride + (uint32_t)warp * a.grp_stride;
       const uint32_t plane16 = (uint32_t)oc.rows_pad;          // plane pitch in 16-byte units
       const uint32_t bchunk16 = 2u * (uint32_t)oc.npad;        // K-chunk pitch of the bank in 16-byte units
@@ -358,6 +367,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const uint32_t s = it_stage % UM_STAGES;
         mbar_wait_warp(&full[s], (it_stage / UM_STAGES) & 1, a.error_flag);
         tc_fence_after();
+        PROF_T(2);
         if (!(a.debug & 1)) {
           const uint32_t ah = smem_u32(a_base + (2 * s) * a.a_region_bytes);
           const uint32_t al = smem_u32(a_base + (2 * s + 1) * a.a_region_bytes);
@@ -414,16 +424,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             }
           }
         }
+        PROF_T(3);
         tc_commit(&empty[s]);                                   // smem stage reusable once these MMAs retire
         if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);      // accumulator complete
         __syncwarp();
+        PROF_T(4);
       }
       ++it_acc;
     }
+    if (prof_on && warp == 0 && lane == 0)
+      for (int i = 0; i < 5; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + i] = pr[i];
   } else if (warp < UM_MMA_WARPS + UM_EPI_WARPS) {
     // =========================== epilogue ===========================
     const int ew = warp & 3;                 // a warp may only touch TMEM lanes [32*(warp%4), +32)
     uint32_t it_acc = 0;
+    PROF_DECL;
     for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
       const ItemInfo inf = decode_item(a, item);
       if (inf.t0 >= inf.T) continue;
@@ -431,6 +446,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       const uint32_t acc = it_acc & 1;
       mbar_wait(&tfull[acc], (it_acc >> 1) & 1, a.error_flag);
       tc_fence_after();
+      PROF_T(0);
       const int t = inf.t0 + ew * 32 + lane;
       const int64_t row = (int64_t)inf.clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
       const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
@@ -467,7 +483,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       ++it_acc;
+      PROF_T(1);
     }
+    if (prof_on && ew == 0 && lane == 0)
+      for (int i = 0; i < 2; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + 5 + i] = pr[i];
   } else {
     // =========================== producers ===========================
     // Software pipeline over this CTA's (item, stage) jobs: job k's raw fp32 rows are fetched with
@@ -482,12 +501,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
     bool have_issue = is.next(a);
     int cur_oct = -1;
     const bool split = (a.n_split == 3);
+    PROF_DECL;
     for (uint32_t k = 0;; ++k) {
       // ---- issue job k -------------------------------------------------------------------
       if (have_issue) {
         const UmmaOct& oc = a.oct[is.inf.o];
         const uint32_t s = k % UM_STAGES;
+        PROF_T(0);
         mbar_wait(&empty[s], ((k / UM_STAGES) & 1) ^ 1, a.error_flag);
+        PROF_T(1);
         float4* raw = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
         const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[is.inf.clip] : (int64_t)is.inf.clip * oc.sig_stride);
         const bool base_al = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
@@ -495,9 +517,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const int g0 = is.st * a.pps;
         const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
-        const int total = np * oc.rows;
+        // rows that valid frames read: frame r uses rows r .. r+Q-1; the rest of a partial tile stays stale
+        // (MMA rows are independent and frames >= T are never stored)
+        const int rows_used = min(oc.rows, is.inf.T - is.inf.t0 + oc.Q - 1);
+        const int total = np * rows_used;
         const int64_t first = origin + 4 * g0;                                  // sample index of element (row 0, plane g0)
-        const int64_t last = first + (int64_t)(oc.rows - 1) * oc.hop + 4 * np;  // one past the last sample touched
+        const int64_t last = first + (int64_t)(rows_used - 1) * oc.hop + 4 * np;  // one past the last sample touched
         const uint32_t raw_s = smem_u32(raw);
         if (a.debug & 2) {
         } else if (base_al && first >= 0 && last <= is.inf.len) {
@@ -529,6 +554,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         have_issue = is.next(a);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");      // one group per k, possibly empty
+      PROF_T(2);
       if (k < a.prefetch) continue;
       // ---- convert job k - a.prefetch ------------------------------------------------------
       if (!cv.next(a)) break;
@@ -542,10 +568,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         float4* sb = reinterpret_cast<float4*>(b_s);
         for (int i = ptid; i < n16; i += PT) sb[i] = __ldg(gb + i);
         cur_oct = cv.inf.o;
+        PROF_T(3);
       }
+      PROF_T(0);
       if (a.prefetch == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else if (a.prefetch == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
       else asm volatile("cp.async.wait_group 3;" ::: "memory");
+      PROF_T(4);
       {
         const uint32_t s = kc % UM_STAGES;
         float4* dh = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
@@ -553,7 +582,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
         const int g0 = cv.st * a.pps;
         const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
-        const int total = np * oc.rows;
+        const int total = np * min(oc.rows, cv.inf.T - cv.inf.t0 + oc.Q - 1);
         for (int e = ptid; e < total && !(a.debug & 2); e += PT) {
           const int g = e & (np - 1), srow = e >> lg;
           const int d = g * oc.rows_pad + srow;
@@ -575,12 +604,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             dh[d] = h;
           }
         }
+        PROF_T(5);
         if (!(a.debug & 8)) fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+        PROF_T(6);
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (prof_on && ptid == 0)
+      for (int i = 0; i < 7; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + 7 + i] = pr[i];
   }
 
   tc_fence_before();
@@ -615,6 +648,7 @@ struct CqtUmmaState {
   uint32_t b_region_bytes = 0, a_region_bytes = 0, tmem_cols = 0, acc_stride = 0, grp_stride = 0;
   size_t smem_bytes = 0;
   int* d_error = nullptr;
+  long long* d_prof = nullptr;
   int num_sms = 0;
   int n_split = 3;
   int stages = 2, pps = 8, prefetch = 1;   // pipeline shape (SAGA_UMMA_CFG="stages,planes,prefetch" overrides)
@@ -699,6 +733,7 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   }
   if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) return;
   cudaMemset(st->d_error, 0, sizeof(int));
+  if (cudaMalloc(&st->d_prof, sizeof(long long) * 256 * UM_PROF_SLOTS) != cudaSuccess) return;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -713,6 +748,7 @@ void cqt_umma_plan_free(saga_cqt_plan* p) {
   if (!p->umma) return;
   for (auto& pk : p->umma->packs) cudaFree(pk.d_pack);
   cudaFree(p->umma->d_error);
+  cudaFree(p->umma->d_prof);
   delete p->umma;
   p->umma = nullptr;
 }
@@ -742,6 +778,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.acc_stride = st->acc_stride;
   a.grp_stride = st->grp_stride;
   a.error_flag = st->d_error;
+  a.prof = st->d_prof;
   a.stages = st->stages;
   a.pps = st->pps;
   a.prefetch = st->prefetch;
@@ -773,6 +810,12 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     u.rows = UM_TILE_M + u.Q - 1;
     u.rows_pad = u.rows | 1;
     u.item_begin = per_oct * i;
+    {
+      int64_t len = lv.max_len;
+      if (p->early_factor > 1) len = (len + p->early_factor - 1) / p->early_factor;
+      for (int s = 0; s < o.level; ++s) len = (len + 1) >> 1;
+      u.uniform_len = len;
+    }
   }
   a.total_items = per_oct * a.n_oct;
   if (a.total_items <= 0) return SAGA_OK;
@@ -785,6 +828,20 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   const int grid = (int)std::min<int64_t>(a.total_items, st->num_sms > 0 ? st->num_sms : 148);
   cqt_umma_kernel<<<grid, UM_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
+  if (a.debug & 16) {
+    // profiling aid only: synchronous read-back of the per-role cycle counters, mean over CTAs
+    std::vector<long long> h((size_t)grid * UM_PROF_SLOTS);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), st->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    static const char* names[14] = {"mma.decode", "mma.wait_tempty", "mma.wait_full", "mma.issue", "mma.commit",
+                                    "epi.wait_tfull", "epi.work", "prod.loop", "prod.wait_empty", "prod.issue",
+                                    "prod.bank", "prod.wait_group", "prod.convert", "prod.fence_arrive"};
+    for (int s = 0; s < 14; ++s) {
+      double sum = 0;
+      for (int c = 0; c < grid; ++c) sum += (double)h[(size_t)c * UM_PROF_SLOTS + s];
+      fprintf(stderr, "umma_prof %-18s %10.0f cycles/CTA\n", names[s], sum / grid);
+    }
+  }
   return SAGA_OK;
 }
 

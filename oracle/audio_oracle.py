@@ -6,7 +6,8 @@ The reference class cannot be imported here (matplotlib, magenta, librosa,
 soundfile missing; `np.int` gone from numpy 2.x), so this module re-expresses
 its behaviour: lazy fields with the reference's invalidation rules, the
 generative-subtractive `subtract`, the float64 time<->frame maps, the window
-slide helpers and the CQT slice.  PARITY UNPINNED (see oracle/__init__.py).
+slide helpers and the CQT slice.  Pinned on the reference's own FLAC outputs for the
+STFT/subtract/iSTFT chain; CQT and dB unpinned (see oracle/__init__.py).
 
 Each method cites the reference lines it follows.
 """
