@@ -267,8 +267,149 @@ static int64_t level_len(int64_t len, int early_factor, int level) {
   return len;
 }
 
+// reflect margin kept on both sides of every clip of a level buffer: n_fft/2 of the octave analysed there
+int cqt_level_pad(const saga_cqt_plan* p, int level) {
+  int pad = 0;
+  for (auto& o : p->oct)
+    if (o.level == level) pad = std::max(pad, ((o.n_fft / 2) + 3) & ~3);
+  return pad;
+}
+
 int64_t cqt_level_pitch(const saga_cqt_plan* p, int level, int64_t max_len) {
-  return (level_len(max_len, p->early_factor, level) + 3 + 4) & ~int64_t(3);
+  return (level_len(max_len, p->early_factor, level) + 2 * cqt_level_pad(p, level) + 3 + 4) & ~int64_t(3);
+}
+
+// ---------------------------------------------------------------------------
+// reflect margins of the level buffers (np.pad(mode='reflect') of librosa's centred framing), written
+// once per level so that the contraction kernels read plain strided tiles.  Level 0 without an early
+// stage is the caller's wav: that level is copied into its padded buffer as well.
+// ---------------------------------------------------------------------------
+constexpr int PAD_MAX_LEVELS = 16;
+struct PadArgs {
+  float* lvl[PAD_MAX_LEVELS];
+  int64_t pitch[PAD_MAX_LEVELS];
+  int pad[PAD_MAX_LEVELS];
+  const float* wav;              // raw level 0 source (early_factor == 1), else NULL
+  const int64_t* clip_offsets;
+  const int64_t* clip_lens;
+  int64_t max_len;
+  int early_factor;
+};
+
+__global__ void __launch_bounds__(256) cqt_pad_kernel(const PadArgs a) {
+  const int l = blockIdx.x, clip = blockIdx.y;
+  const int pad = a.pad[l];
+  if (pad == 0 || !a.lvl[l]) return;
+  int64_t len = a.clip_lens ? a.clip_lens[clip] : a.max_len;
+  if (len <= 0) return;
+  if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
+  for (int s = 0; s < l; ++s) len = (len + 1) >> 1;
+  float* dst = a.lvl[l] + (int64_t)clip * a.pitch[l] + pad;
+  const bool raw = (l == 0 && a.wav != nullptr);
+  const float* src = raw ? a.wav + a.clip_offsets[clip] : dst;
+  const int tid = blockIdx.z * blockDim.x + threadIdx.x, nth = gridDim.z * blockDim.x;
+  if (raw)
+    for (int64_t i = tid; i < len; i += nth) dst[i] = __ldg(src + i);
+  for (int i = tid; i < 2 * pad; i += nth) {
+    const int64_t s = i < pad ? (int64_t)i - pad : len + (i - pad);
+    dst[s] = src[reflect_index(s, len)];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Partial last tiles with few valid frames (<= TAIL_MAX): the tensor-core kernel would pay a full
+// 128-row MMA sequence for them, so they are contracted here on the CUDA cores instead.  CTA =
+// (octave, clip); lane = output column, the 8 warps split n_fft; the signal value is a warp-uniform
+// (broadcast) load from the padded level buffer.
+// ---------------------------------------------------------------------------
+constexpr int TAIL_MAX = 16;
+constexpr int TAIL_TILE = 128;
+struct TailOct {
+  const float* sig;       // padded level signal, element 0 of a clip = sample -n_fft/2
+  int64_t sig_stride;
+  const float* bank;      // [n_fft][ncol]
+  int hop, n_fft, ncol, first_bin;
+};
+struct TailArgs {
+  TailOct oct[12];
+  const int32_t* clip_frames;
+  int uniform_T, n_bins;
+  float* mag_out;
+  float2* cplx_out;
+  int64_t frame_pitch, out_clip_stride;
+};
+
+constexpr int TAIL_KC = 256;   // kernel samples staged per pass
+
+__global__ void __launch_bounds__(256) cqt_tail_kernel(const TailArgs a) {
+  __shared__ __align__(16) float ysm[TAIL_MAX][TAIL_KC];   // signal rows of the tail frames
+  __shared__ float red[8][TAIL_MAX][32];
+  const TailOct& oc = a.oct[blockIdx.x];
+  const int clip = blockIdx.y;
+  const int T = a.uniform_T > 0 ? a.uniform_T : a.clip_frames[clip];
+  const int rem = T % TAIL_TILE;
+  if (rem == 0 || rem > TAIL_MAX) return;
+  const int t0 = T - rem;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* y = oc.sig + (int64_t)clip * oc.sig_stride + (int64_t)t0 * oc.hop;
+  for (int c0 = 0; c0 < oc.ncol; c0 += 32) {
+    const int col = c0 + lane;
+    float acc[TAIL_MAX];
+#pragma unroll
+    for (int f = 0; f < TAIL_MAX; ++f) acc[f] = 0.f;
+    for (int n0 = 0; n0 < oc.n_fft; n0 += TAIL_KC) {
+      __syncthreads();
+#pragma unroll
+      for (int f = 0; f < TAIL_MAX; ++f) {
+        const int n = n0 + (int)threadIdx.x;
+        if (f < rem) ysm[f][threadIdx.x] = n < oc.n_fft ? __ldg(y + f * oc.hop + n) : 0.f;
+      }
+      __syncthreads();
+      // warp w contracts samples [n0 + 32 w, n0 + 32 w + 32): coalesced bank rows; the signal is a broadcast
+      // 16-byte shared load per (frame, 4 samples); frames beyond `rem` are skipped (warp-uniform test)
+      const int nb = n0 + 32 * w;
+      float g[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        g[i] = (col < oc.ncol && nb + i < oc.n_fft) ? __ldg(oc.bank + (int64_t)(nb + i) * oc.ncol + col) : 0.f;
+#pragma unroll
+      for (int f = 0; f < TAIL_MAX; ++f) {
+        if (f < rem) {
+          const float4* yr = reinterpret_cast<const float4*>(&ysm[f][32 * w]);
+          float r = acc[f];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 v = yr[i4];
+            r = fmaf(g[4 * i4 + 0], v.x, r);
+            r = fmaf(g[4 * i4 + 1], v.y, r);
+            r = fmaf(g[4 * i4 + 2], v.z, r);
+            r = fmaf(g[4 * i4 + 3], v.w, r);
+          }
+          acc[f] = r;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < TAIL_MAX; ++f) red[w][f][lane] = acc[f];
+    __syncthreads();
+    // thread -> (frame f, filter j of this column chunk)
+    const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
+    if (f < rem && c0 + 2 * j < oc.ncol) {
+      float re = 0.f, im = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) {
+        re += red[ww][f][2 * j];
+        im += red[ww][f][2 * j + 1];
+      }
+      const int bin = oc.first_bin + (c0 >> 1) + j;
+      if (bin >= 0 && bin < a.n_bins) {
+        const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)(t0 + f) * a.frame_pitch;
+        a.mag_out[row + bin] = sqrtf(re * re + im * im);
+        if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
+      }
+    }
+  }
 }
 
 }  // namespace saga
@@ -362,7 +503,7 @@ static int64_t ws_header_bytes(int n_clips) { return (((int64_t)n_clips * 4) + 2
 extern "C" int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* p, int n_clips, int64_t max_len) {
   if (!p || n_clips <= 0 || max_len <= 0) return 256;
   int64_t b = ws_header_bytes(n_clips);
-  for (int l = (p->early_factor > 1 ? 0 : 1); l <= p->max_level; ++l)
+  for (int l = 0; l <= p->max_level; ++l)
     b += (int64_t)n_clips * cqt_level_pitch(p, l, max_len) * 4;
   return b + 256;
 }
@@ -388,14 +529,17 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   char* ws = (char*)workspace;
   int32_t* clip_frames = (int32_t*)ws;
   ws += ws_header_bytes(n_clips);
-  std::vector<float*> lvl(p->max_level + 1, nullptr);
+  if (p->max_level + 1 > PAD_MAX_LEVELS) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: too many levels");
+  std::vector<float*> lvl(p->max_level + 1, nullptr);   // padded buffers; sample 0 of a clip at + pad[l]
   std::vector<int64_t> pitch(p->max_level + 1, 0);
+  std::vector<int> pad(p->max_level + 1, 0);
   for (int l = 0; l <= p->max_level; ++l) {
     pitch[l] = cqt_level_pitch(p, l, max_len);
-    if (l == 0 && p->early_factor == 1) continue;  // level 0 is the caller's wav
+    pad[l] = cqt_level_pad(p, l);
     lvl[l] = (float*)ws;
     ws += (int64_t)n_clips * pitch[l] * 4;
   }
+  const bool raw0 = (p->early_factor == 1);   // level 0 = the caller's wav (copied into lvl[0] by the pad pass)
 
   cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, max_len, n_clips, p->early_factor,
                                                            p->d_levels, p->d_hops, (int)p->oct.size(),
@@ -413,11 +557,11 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p->early_factor == 2 && p->n_early_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
-      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0], pitch[0],
-                                                    *reinterpret_cast<const Dec2Taps*>(p->early_taps2));
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
+                                                    pitch[0], *reinterpret_cast<const Dec2Taps*>(p->early_taps2));
     } else {
-      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0], pitch[0],
-                                                       p->d_early_taps, p->n_early_taps, p->early_factor);
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
+                                                       pitch[0], p->d_early_taps, p->n_early_taps, p->early_factor);
     }
     SAGA_LAUNCH_CHECK();
   }
@@ -428,15 +572,36 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     const bool from_wav = (l == 1 && p->early_factor == 1);
     if (p->n_half_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
-      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
-                                                    from_wav ? 0 : pitch[l - 1], clip_lens, max_len, l - 1,
-                                                    p->early_factor, lvl[l], pitch[l], *reinterpret_cast<const Dec2Taps*>(p->half_taps2));
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
+                                                    from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
+                                                    clip_lens, max_len, l - 1, p->early_factor, lvl[l] + pad[l], pitch[l],
+                                                    *reinterpret_cast<const Dec2Taps*>(p->half_taps2));
     } else {
-      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1], from_wav ? clip_offsets : nullptr,
-                                                       from_wav ? 0 : pitch[l - 1], clip_lens, max_len, l - 1,
-                                                       p->early_factor, lvl[l], pitch[l], p->d_half_taps,
-                                                       p->n_half_taps, 2);
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
+                                                       from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
+                                                       clip_lens, max_len, l - 1, p->early_factor, lvl[l] + pad[l],
+                                                       pitch[l], p->d_half_taps, p->n_half_taps, 2);
     }
+    SAGA_LAUNCH_CHECK();
+  }
+
+  const bool tensor_path = (impl != 1) && cqt_umma_supported(p);
+  if (do_cascade && tensor_path) {
+    // reflect margins (and the padded copy of a raw level 0): part of the cascade phase
+    PadArgs pa;
+    for (int l = 0; l < PAD_MAX_LEVELS; ++l) {
+      const bool on = l <= p->max_level;
+      pa.lvl[l] = on ? lvl[l] : nullptr;
+      pa.pitch[l] = on ? pitch[l] : 0;
+      pa.pad[l] = on ? pad[l] : 0;
+    }
+    pa.wav = raw0 ? wav : nullptr;
+    pa.clip_offsets = clip_offsets;
+    pa.clip_lens = clip_lens;
+    pa.max_len = max_len;
+    pa.early_factor = p->early_factor;
+    dim3 grid(p->max_level + 1, n_clips, raw0 ? 16 : 1);
+    cqt_pad_kernel<<<grid, 256, 0, st>>>(pa);
     SAGA_LAUNCH_CHECK();
   }
 
@@ -444,18 +609,45 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   // ---- contraction -------------------------------------------------------------------
   CqtLevels lv;
   lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
-  lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.clip_frames = clip_frames;
+  lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.pad = pad.data(); lv.clip_frames = clip_frames;
   if (impl != 1) {
     int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
-                           out_clip_stride, impl == 3 ? 1 : 3, st);
-    if (rc == SAGA_OK) return SAGA_OK;
+                           out_clip_stride, impl == 3 ? 1 : 3, TAIL_MAX, st);
+    if (rc == SAGA_OK) {
+      const int rem = (int)(T_max % TAIL_TILE);
+      if (clip_lens || (rem > 0 && rem <= TAIL_MAX)) {   // some clip may end in a short partial tile
+        TailArgs ta;
+        if (p->oct.size() > 12) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: too many octaves");
+        for (size_t i = 0; i < p->oct.size(); ++i) {
+          const CqtOctaveDev& o = p->oct[i];
+          ta.oct[i].sig = lvl[o.level] + (pad[o.level] - o.n_fft / 2);
+          ta.oct[i].sig_stride = pitch[o.level];
+          ta.oct[i].bank = o.bank;
+          ta.oct[i].hop = o.hop;
+          ta.oct[i].n_fft = o.n_fft;
+          ta.oct[i].ncol = 2 * o.n_filters;
+          ta.oct[i].first_bin = o.first_bin;
+        }
+        ta.clip_frames = clip_frames;
+        ta.uniform_T = clip_lens ? 0 : (int)T_max;
+        ta.n_bins = p->n_bins;
+        ta.mag_out = C_mag_out;
+        ta.cplx_out = (float2*)C_cplx_out;
+        ta.frame_pitch = frame_pitch;
+        ta.out_clip_stride = out_clip_stride;
+        dim3 grid((unsigned)p->oct.size(), n_clips);
+        cqt_tail_kernel<<<grid, 256, 0, st>>>(ta);
+        SAGA_LAUNCH_CHECK();
+      }
+      return SAGA_OK;
+    }
     if (rc != SAGA_ERR_UNSUPPORTED || impl >= 2) return rc;
   }
   bool first = true;
   for (auto& o : p->oct) {
     ContractArgs a;
     const bool raw = (o.level == 0 && p->early_factor == 1);
-    a.sig = raw ? wav : lvl[o.level];
+    a.sig = raw ? wav : lvl[o.level] + pad[o.level];
     a.sig_offsets = raw ? clip_offsets : nullptr;
     a.sig_stride = raw ? 0 : pitch[o.level];
     a.clip_lens = clip_lens;

@@ -36,16 +36,21 @@ struct CqtLevels {
   const int64_t* clip_offsets;
   const int64_t* clip_lens;  // NULL: every clip has max_len samples
   int64_t max_len;
-  float* const* lvl;        // [max_level+1] device buffers (lvl[0]==nullptr when early_factor==1)
+  // level buffers are REFLECT-PADDED: sample s of clip c at lvl[l] + c*pitch[l] + pad[l] + s, valid for
+  // s in [-pad, len_l + pad) (cqt_pad_kernel); pad[l] = n_fft/2 of the octave(s) analysed at that level
+  float* const* lvl;        // [max_level+1] device buffers
   const int64_t* pitch;     // per-clip pitch of each level buffer
+  const int* pad;           // per-level margin in samples (multiple of 4)
   const int32_t* clip_frames;
 };
 
 void cqt_umma_plan_init(saga_cqt_plan* p);
 void cqt_umma_plan_free(saga_cqt_plan* p);
 // returns SAGA_ERR_UNSUPPORTED when the plan does not fit the tensor path
+// tiles with <= tail_max valid frames are skipped (the caller runs cqt_tail_kernel for them)
 int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t max_len,
                   int64_t T_max, float* mag_out, float2* cplx_out, int64_t frame_pitch,
-                  int64_t out_clip_stride, int n_split, cudaStream_t st);
+                  int64_t out_clip_stride, int n_split, int tail_max, cudaStream_t st);
+bool cqt_umma_supported(const saga_cqt_plan* p);
 
 }  // namespace saga

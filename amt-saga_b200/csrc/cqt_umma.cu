@@ -15,24 +15,35 @@
 // 16-byte K-chunks of an MMA are consecutive shifts: LBO = 16 B.
 // Every sample is fetched from L2 once per tile instead of n_fft/hop times.
 //
-// fp32 accuracy on TF32 tensor cores: operands are split x = hi + lo (both
-// TF32, round-to-nearest) and hi*hi + hi*lo + lo*hi is accumulated in fp32
-// TMEM (n_split = 3).  The bank is packed [B_hi | B_lo] along N, so per K-slice
-// ONE N=2*npad MMA (A_hi x [B_hi|B_lo]) plus one N=npad MMA (A_lo x B_hi) do the
-// work of three; the epilogue adds the two column groups.  n_split = 1 keeps
-// only hi*hi.  N is tiny here (24 real columns per octave), so the kernel is
-// bound by how fast ONE thread can issue MMAs: descriptors are built once per
-// stage and advanced by adding to their low word.
+// The level signals arrive REFLECT-PADDED (cqt.cu: cqt_pad_kernel), so every tile of
+// every clip is a plain strided copy: no bounds tests, no index mirroring, always
+// 16-byte aligned.
 //
-// Warp roles per persistent CTA (one per SM): 16 producer warps (L2 -> cp.async -> planes; lo = x - trunc13(x)), 4 MMA issuer warps (one elected thread each; K-slices dealt round
-// robin, each warp accumulating into its own TMEM column group, because with
-// N <= 64 an MMA retires in 16-32 cycles and a single issuing thread cannot keep
-// up -- profiles/microbench/umma_latency.cu), 4 epilogue warps (tcgen05.ld, sum of
-// the column groups, |re + i im| -> global).  mbarrier pipelines: smem full/empty per
-// A stage, TMEM full/empty per accumulator buffer.  The bank G_o (packed for the
-// B descriptor on the host) stays resident in SMEM while the CTA works through
-// items of one octave (items are ordered octave-major).
+// fp32 accuracy on TF32 tensor cores: operands are split x = hi + lo and
+// hi*hi + hi*lo + lo*hi is accumulated in fp32 TMEM (n_split = 3).  The bank is
+// packed [B_hi | B_lo] along N (2*ncol columns), so per K-slice ONE MMA with
+// N = n_main (A_hi x [B_hi|B_lo]) plus one with N = n_lo (A_lo x B_hi..., into the
+// SAME accumulator columns) do the work of three; the epilogue adds column c and
+// column ncol + c.  kind::tf32 ignores the low 13 mantissa bits of an operand, so
+// the raw fp32 samples ARE A_hi; only lo = tf32(x - trunc13(x)) is computed.
+//
+// Measured (profiles/microbench): an SS-mode tcgen05.mma is paced by the shared-memory
+// bytes it reads (A 4 KB + B 32*N bytes at 128 B/clk: 44 cycles for N<=32, 48 @ N=64),
+// so the contraction is bound by one thread-issued MMA pair (~88 cycles) per 8 k-values.
+//
+// Warp roles per persistent CTA (one per SM):
+//   4 MMA issuer warps  K-slices dealt round robin, one TMEM column group each
+//   4 epilogue warps    tcgen05.ld, sum of the column groups, |re + i im| -> global
+//   8 loader warps      cp.async 16 B (L2 -> plane layout), completion signalled to an
+//                       mbarrier by cp.async.mbarrier.arrive -- loaders never wait for data
+//   8 converter warps   lo plane from the landed hi plane, proxy fence, arrive `full`
+// mbarrier pipelines: raw / full / empty per A stage, full / empty per TMEM buffer, one
+// for the bank.  The bank G_o stays resident in SMEM while the CTA works through tiles of
+// one octave (tiles are ordered octave-major) and is replaced by ONE bulk async copy.
+// Partial tiles with <= tail_max valid frames are left to cqt_tail_kernel (cqt.cu):
+// an MMA costs the same for 5 valid rows as for 128.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,47 +55,51 @@
 namespace saga {
 
 constexpr int UM_TILE_M = 128;
-constexpr int UM_PRODUCER_WARPS = 16;
-constexpr int UM_EPI_WARPS = 4;
 constexpr int UM_MMA_WARPS = 4;             // issuer warps: K-slices round-robin, one TMEM column group each
-constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_PRODUCER_WARPS);   // 0-3 MMA, 4-7 epilogue, 8-15 producers
-constexpr int UM_MAX_STAGES = 6;            // barrier array capacity; the actual count is a plan parameter
+constexpr int UM_EPI_WARPS = 4;
+constexpr int UM_LOAD_WARPS = 8;
+constexpr int UM_CONV_WARPS = 8;
+constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_LOAD_WARPS + UM_CONV_WARPS);
+constexpr int UM_MAX_STAGES = 8;            // barrier array capacity; the actual count is a plan parameter
 constexpr int UM_MAX_OCT = 12;
+constexpr int UM_MAX_COLS = 128;
 constexpr uint32_t UM_SPIN_LIMIT = 1u << 27;
-constexpr int UM_PROF_SLOTS = 16;
+constexpr int UM_PROF_SLOTS = 24;
+constexpr uint32_t UM_SMEM_LIMIT = 232448 - 1024;   // 227 KB opt-in maximum, minus slack
 
 struct UmmaOct {
-  const float* sig;
-  const int64_t* sig_offsets;
-  int64_t sig_stride;
-  const float* b_pack;    // packed [n_fft/4][2*npad][4]: rows [0,npad) = TF32 hi, [npad,2npad) = lo
-  int level, hop, n_fft, ncol, npad, first_bin;
-  int planes, np_log2, n_stages, Q, rows, rows_pad;
-  int64_t item_begin;
-  int64_t uniform_len;    // length of every clip at this octave's level (equal-length batches)
+  const float* sig;       // padded level signal, element 0 of a clip = sample -n_fft/2
+  int64_t sig_stride;     // floats per clip
+  const float* b_pack;    // packed [n_fft/4][n_main][4]: rows [0,ncol) = TF32 hi, [ncol,2ncol) = lo, rest 0
+  uint32_t bank_bytes;
+  int hop, n_fft, ncol, first_bin;
+  int planes, n_stages, Q, rows, rows_pad;
+  int n_main, n_lo;       // MMA N of the main and of the correction MMA
 };
 
 struct UmmaArgs {
   UmmaOct oct[UM_MAX_OCT];
-  int n_oct, n_clips, tiles_per_clip, early_factor, n_bins, n_split;
-  int64_t total_items;
-  const int64_t* clip_lens;
+  int n_oct, n_clips, n_bins, n_split;
+  uint32_t tiles_per_clip, per_oct, total_items;
   const int32_t* clip_frames;
+  int uniform_T;             // > 0: every clip has this many frames (no per-item loads)
+  int tail_max;              // tiles with <= tail_max valid frames are skipped (cqt_tail_kernel does them)
   float* mag_out;
   float2* cplx_out;
   int64_t frame_pitch, out_clip_stride;
-  uint32_t b_region_bytes;   // resident bank (hi and lo rows interleaved per K-chunk)
+  uint32_t b_region_bytes;   // resident bank
   uint32_t a_region_bytes;   // one of hi / lo, per stage
-  uint32_t tmem_cols;        // allocation (power of two >= 2*npad_max)
+  uint32_t tmem_cols;        // allocation (power of two)
   uint32_t acc_stride;       // columns between the two accumulator buffers
-  uint32_t grp_stride;       // columns between issuer-warp column groups (2*npad_max)
+  uint32_t grp_stride;       // columns between issuer-warp column groups
   int* error_flag;
-  int stages, pps, prefetch; // pipeline shape: SMEM stages, planes per stage (4 or 8), producer look-ahead (< stages)
-  int uniform_T;             // > 0: every clip has this many frames and `uniform_len` samples (no per-item loads)
-  int64_t uniform_len;
-  int debug;                 // profiling bisect (SAGA_UMMA_DEBUG): 1 = no MMAs, 2 = no producer data, 4 = no epilogue work,
-                             // 8 = no proxy fence, 16 = per-role cycle breakdown into `prof`
-  long long* prof;           // [grid][UM_PROF_SLOTS] cycle counters (debug & 16)
+  int stages, pps;           // pipeline shape: SMEM stages, planes per stage (2, 4 or 8)
+  int shared_bank;           // every octave's bank is a per-column multiple of octave 0's (librosa re-uses one
+                             // basis): ONE resident bank, tiles interleave octaves, the epilogue applies col_scale
+  const float* col_scale;    // [n_oct][UM_MAX_COLS]
+  int debug;                 // SAGA_UMMA_DEBUG: 1 = no MMAs, 2 = no loads / conversion, 4 = no epilogue work,
+                             // 16 = per-role cycle breakdown into `prof`
+  long long* prof;           // [grid][UM_PROF_SLOTS]
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -96,6 +111,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -124,8 +151,23 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   __syncwarp();
 }
 // cycle breakdown (debug & 16): PROF_T(slot) adds the cycles since the previous mark to pr[slot]
-#define PROF_DECL const bool prof_on = (a.debug & 16) != 0; long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = prof_on ? clock64() : 0; const long long pt0 = pt
-#define PROF_T(slot) do { if (prof_on) { const long long n_ = clock64(); pr[slot] += n_ - pt; pt = n_; } } while (0)
+#define PROF_DECL                            \
+  const bool prof_on = (a.debug & 16) != 0;  \
+  long long pr[6] = {0, 0, 0, 0, 0, 0};      \
+  long long pt = prof_on ? clock64() : 0
+#define PROF_T(slot)                \
+  do {                              \
+    if (prof_on) {                  \
+      const long long n_ = clock64(); \
+      pr[slot] += n_ - pt;          \
+      pt = n_;                      \
+    }                               \
+  } while (0)
+#define PROF_OUT(base, n)                                                                               \
+  do {                                                                                                  \
+    if (prof_on)                                                                                        \
+      for (int i_ = 0; i_ < (n); ++i_) a.prof[blockIdx.x * UM_PROF_SLOTS + (base) + i_] = pr[i_];       \
+  } while (0)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -140,7 +182,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {   // whole warp calls
 }
 // Issued by ONE elected lane, but called by the whole (converged) MMA warp with warp-uniform
 // operands: that keeps descriptors in uniform registers (UIADD3 + UTCHMMA per MMA) instead of a
-// per-instruction R2UR waterfall -- with N = 32..64 the tensor pipe needs a new MMA every 16-32 cycles.
+// per-instruction R2UR waterfall.
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -153,10 +195,8 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
 }
 // ---- multi-slice issue blocks -------------------------------------------------------------
 // STEPS consecutive K-slices of one issuer warp in ONE asm block: per slice the main MMA
-// (A_hi x [B_hi|B_lo], N = 2*npad) and the correction MMA (A_lo x B_hi, N = npad); then both A
+// (A_hi x [B_hi|B_lo], N = n_main) and the correction MMA (A_lo x B_hi, N = n_lo); then both A
 // descriptors advance by `da` and the B descriptor by `db` (16-byte units, added to the low word).
-// Keeping the descriptor arithmetic inside the block lets ptxas carry it in uniform registers
-// instead of re-broadcasting seven vector registers in front of every MMA.
 #define UM_ASM_HEAD                                   \
   "{\n\t"                                             \
   ".reg .pred e, p, t;\n\t"                           \
@@ -234,95 +274,108 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-struct ItemInfo {
-  int o, clip, t0, T;
-  int64_t len;
+// One (octave, clip, 128-frame tile) work item.  A CTA walks items blockIdx.x, +G, +2G, ...; the walk is
+// kept incremental (two divisions at the start, a handful of adds per step) because every role of the CTA
+// decodes every item and a division chain on one warp is ~500 cycles of exposed latency.
+//   shared bank : item = local * n_oct + o   (octave-minor: consecutive tiles mix load-heavy and light octaves)
+//   else        : item = o * per_oct + local (octave-major: the resident bank changes n_oct times per CTA)
+// local = clip * tiles_per_clip + tile
+struct Tile {
+  int o, clip, t0, valid;
 };
-
-__device__ __forceinline__ ItemInfo decode_item(const UmmaArgs& a, int64_t item) {
-  ItemInfo it;
-  int o = 0;
-  while (o + 1 < a.n_oct && item >= a.oct[o + 1].item_begin) ++o;
-  const uint32_t local = (uint32_t)(item - a.oct[o].item_begin);      // < n_clips * tiles_per_clip < 2^31
-  it.o = o;
-  it.clip = (int)(local / (uint32_t)a.tiles_per_clip);
-  it.t0 = (int)(local % (uint32_t)a.tiles_per_clip) * UM_TILE_M;
-  if (a.uniform_T > 0) {          // equal-length batch: nothing to fetch or derive
-    it.T = a.uniform_T;
-    it.len = a.oct[o].uniform_len;
-    return it;
-  }
-  it.T = a.clip_frames[it.clip];
-  int64_t len = a.clip_lens[it.clip];
-  if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
-  for (int s = 0; s < a.oct[o].level; ++s) len = (len + 1) >> 1;
-  it.len = len;
-  return it;
-}
-
-// walks this CTA's (item, stage) jobs in the order every role processes them
-struct JobIter {
-  int64_t item, G;
-  int st;
-  bool started;
-  ItemInfo inf;
-  __device__ __forceinline__ void reset(int64_t first, int64_t stride) {
-    item = first - stride;
-    G = stride;
-    st = 0;
-    started = false;
-  }
-  __device__ __forceinline__ bool next(const UmmaArgs& a) {
-    if (started && st + 1 < a.oct[inf.o].n_stages) {
-      ++st;
-      return true;
+struct TileIter {
+  uint32_t item, o, local, clip, tile;
+  uint32_t dO, dL, dC, dT;
+  __device__ __forceinline__ void init(const UmmaArgs& a, uint32_t first, uint32_t G) {
+    item = first;
+    if (a.shared_bank) {
+      local = first / (uint32_t)a.n_oct;
+      o = first - local * (uint32_t)a.n_oct;
+      dL = G / (uint32_t)a.n_oct;
+      dO = G - dL * (uint32_t)a.n_oct;
+    } else {
+      o = first / a.per_oct;
+      local = first - o * a.per_oct;
+      dL = G;
+      dO = 0;
     }
-    for (;;) {
-      item += G;
-      if (item >= a.total_items) return false;
-      inf = decode_item(a, item);
-      if (inf.t0 < inf.T) break;
+    clip = local / a.tiles_per_clip;
+    tile = local - clip * a.tiles_per_clip;
+    dC = dL / a.tiles_per_clip;
+    dT = dL - dC * a.tiles_per_clip;
+  }
+  __device__ __forceinline__ bool done(const UmmaArgs& a) const { return item >= a.total_items; }
+  __device__ __forceinline__ void step(const UmmaArgs& a, uint32_t G) {
+    item += G;
+    local += dL;
+    clip += dC;
+    tile += dT;
+    if (a.shared_bank) {
+      o += dO;
+      if (o >= (uint32_t)a.n_oct) {
+        o -= (uint32_t)a.n_oct;
+        ++local;
+        ++tile;
+      }
     }
-    st = 0;
-    started = true;
-    return true;
+    if (tile >= a.tiles_per_clip) {
+      tile -= a.tiles_per_clip;
+      ++clip;
+    }
+    if (!a.shared_bank && local >= a.per_oct && item < a.total_items) {   // crossed into the next octave(s)
+      o = item / a.per_oct;
+      local = item - o * a.per_oct;
+      clip = local / a.tiles_per_clip;
+      tile = local - clip * a.tiles_per_clip;
+    }
+  }
+  // false: nothing to do for this item (beyond the clip's frames, or a short tail left to cqt_tail_kernel)
+  __device__ __forceinline__ bool get(const UmmaArgs& a, Tile& t) const {
+    t.o = (int)o;
+    t.clip = (int)clip;
+    t.t0 = (int)tile * UM_TILE_M;
+    const int T = a.uniform_T > 0 ? a.uniform_T : a.clip_frames[clip];
+    t.valid = min(T - t.t0, UM_TILE_M);
+    return t.valid > a.tail_max;
   }
 };
 
 __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* b_s = smem_raw;
-  uint8_t* a_base = b_s + a.b_region_bytes;                     // stages: [hi | lo] x UM_STAGES
-  const uint32_t UM_STAGES = (uint32_t)a.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + 2 * UM_STAGES * a.a_region_bytes);
-  uint64_t* full = bars;                        // [stages]
-  uint64_t* empty = bars + UM_MAX_STAGES;       // [stages]
-  uint64_t* tfull = bars + 2 * UM_MAX_STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * UM_MAX_STAGES + 2;  // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * UM_MAX_STAGES + 4);
+  uint8_t* a_base = b_s + a.b_region_bytes;                     // stages: [hi | lo] x S
+  const uint32_t S = (uint32_t)a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + 2 * S * a.a_region_bytes);
+  uint64_t* raw = bars;                             // [S] hi plane landed (cp.async completion)
+  uint64_t* full = bars + UM_MAX_STAGES;            // [S] lo plane written, stage ready for the tensor core
+  uint64_t* empty = bars + 2 * UM_MAX_STAGES;       // [S] MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * UM_MAX_STAGES;       // [2]
+  uint64_t* tempty = bars + 3 * UM_MAX_STAGES + 2;  // [2]
+  uint64_t* bankbar = bars + 3 * UM_MAX_STAGES + 4; // [1]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 3 * UM_MAX_STAGES + 5);
 
   // broadcast so the compiler knows the role index is warp-uniform (keeps MMA operands in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < UM_STAGES; ++s) {
-      mbar_init(&full[s], UM_PRODUCER_WARPS);
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(&raw[s], 32 * UM_LOAD_WARPS);
+      mbar_init(&full[s], UM_CONV_WARPS);
       mbar_init(&empty[s], UM_MMA_WARPS);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], UM_MMA_WARPS);
       mbar_init(&tempty[s], UM_EPI_WARPS);
     }
+    mbar_init(bankbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -336,38 +389,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
-  const int64_t G = gridDim.x;
+  const uint32_t G = gridDim.x;
+  const bool split = (a.n_split == 3);
 
   if (warp < UM_MMA_WARPS) {
     // =========================== MMA issuers ===========================
-    uint32_t it_stage = 0, it_acc = 0;
+    uint32_t k = 0, it_acc = 0, n_bank = 0;
+    int cur_oct = -1;
     PROF_DECL;
-    for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
-      const ItemInfo inf = decode_item(a, item);
-      if (inf.t0 >= inf.T) continue;
-      const UmmaOct& oc = a.oct[inf.o];
+    TileIter ti;
+    for (ti.init(a, blockIdx.x, G); !ti.done(a); ti.step(a, G)) {
+      Tile tl;
+      if (!ti.get(a, tl)) continue;
+      const UmmaOct& oc = a.oct[tl.o];
       PROF_T(0);
-      // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128; N = 2*npad (hi|lo) and N = npad
+      const int bank_id = a.shared_bank ? 0 : tl.o;
+      if (bank_id != cur_oct) {       // the loaders replace the resident bank at an octave switch
+        mbar_wait_warp(bankbar, n_bank & 1, a.error_flag);
+        ++n_bank;
+        cur_oct = bank_id;
+        PROF_T(1);
+      }
+      // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UM_TILE_M >> 4) << 24);
-      const uint32_t idesc_n1 = idesc_base | ((uint32_t)(oc.npad >> 3) << 17);
-      const uint32_t idesc_n2 = idesc_base | ((uint32_t)((2 * oc.npad) >> 3) << 17);
+      const uint32_t idesc_lo = idesc_base | ((uint32_t)(oc.n_lo >> 3) << 17);
+      const uint32_t idesc_main = split ? (idesc_base | ((uint32_t)(oc.n_main >> 3) << 17)) : idesc_lo;
       const uint32_t acc = it_acc & 1;
       mbar_wait_warp(&tempty[acc], ((it_acc >> 1) & 1) ^ 1, a.error_flag);
       tc_fence_after();
-      PROF_T(1);
+      PROF_T(2);
       const uint32_t d_tmem = tmem_base + acc * a.acc_stride + (uint32_t)warp * a.grp_stride;
       const uint32_t plane16 = (uint32_t)oc.rows_pad;          // plane pitch in 16-byte units
-      const uint32_t bchunk16 = 2u * (uint32_t)oc.npad;        // K-chunk pitch of the bank in 16-byte units
-      const bool split = (a.n_split == 3);
-      const uint32_t idesc_main = split ? idesc_n2 : idesc_n1;
+      const uint32_t bchunk16 = (uint32_t)oc.n_main;           // K-chunk pitch of the bank in 16-byte units
       const uint64_t db0 = smem_desc(smem_u32(b_s), bchunk16 * 16u, 128);
       uint32_t accum = 0;
       int rr = warp;      // next K-slice (within the current stage) owned by this warp
-      for (int st = 0; st < oc.n_stages; ++st, ++it_stage) {
-        const uint32_t s = it_stage % UM_STAGES;
-        mbar_wait_warp(&full[s], (it_stage / UM_STAGES) & 1, a.error_flag);
+      for (int st = 0; st < oc.n_stages; ++st, ++k) {
+        const uint32_t s = k % S;
+        // the converters observed the cp.async data (mbarrier), wrote the lo plane and executed the
+        // generic->async proxy fence before their release-arrive on `full`
+        mbar_wait_warp(&full[s], (k / S) & 1, a.error_flag);
         tc_fence_after();
-        PROF_T(2);
+        PROF_T(3);
         if (!(a.debug & 1)) {
           const uint32_t ah = smem_u32(a_base + (2 * s) * a.a_region_bytes);
           const uint32_t al = smem_u32(a_base + (2 * s + 1) * a.a_region_bytes);
@@ -387,7 +450,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
               const uint32_t dq = (uint32_t)(UM_MMA_WARPS >> np2_log);   // needs pairs-per-shift <= UM_MMA_WARPS
               const uint32_t a_off = pp * plane16 + q0;
               const uint64_t db = db0 + (uint64_t)(q0 * bq + ((uint32_t)g0 + pp) * bchunk16);
-              tc_mma_split_run(d_tmem, dah0 + a_off, dal0 + a_off, db, idesc_main, idesc_n1, accum, dq, dq * bq,
+              tc_mma_split_run(d_tmem, dah0 + a_off, dal0 + a_off, db, idesc_main, idesc_lo, accum, dq, dq * bq,
                                n_slices / UM_MMA_WARPS);
             } else {
               int sl = rr;
@@ -398,7 +461,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
                 const uint64_t db = db0 + (uint64_t)(q * bq + ((uint32_t)g0 + pp) * bchunk16);
                 tc_mma_tf32(d_tmem, dah0 + a_off, db, idesc_main, accum);
                 accum = 1;
-                if (split) tc_mma_tf32(d_tmem, dal0 + a_off, db, idesc_n1, 1u);
+                if (split) tc_mma_tf32(d_tmem, dal0 + a_off, db, idesc_lo, 1u);
               }
               rr = sl - n_slices;
             }
@@ -409,7 +472,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             const int n_slices = oc.Q >> 1;
             if (split && rr == warp && (n_slices % UM_MMA_WARPS) == 0) {
               const uint32_t q0 = 2u * (uint32_t)warp;
-              tc_mma_split_run(d_tmem, dah0 + q0, dal0 + q0, db0 + (uint64_t)(q0 * bchunk16), idesc_main, idesc_n1,
+              tc_mma_split_run(d_tmem, dah0 + q0, dal0 + q0, db0 + (uint64_t)(q0 * bchunk16), idesc_main, idesc_lo,
                                accum, 2u * UM_MMA_WARPS, 2u * UM_MMA_WARPS * bchunk16, n_slices / UM_MMA_WARPS);
             } else {
               int sl = rr;
@@ -418,63 +481,80 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
                 const uint64_t db = db0 + (uint64_t)(q * bchunk16);
                 tc_mma_tf32(d_tmem, dah0 + q, db, idesc_main, accum);
                 accum = 1;
-                if (split) tc_mma_tf32(d_tmem, dal0 + q, db, idesc_n1, 1u);
+                if (split) tc_mma_tf32(d_tmem, dal0 + q, db, idesc_lo, 1u);
               }
               rr = sl - n_slices;
             }
           }
         }
-        PROF_T(3);
+        PROF_T(4);
         tc_commit(&empty[s]);                                   // smem stage reusable once these MMAs retire
         if (st == oc.n_stages - 1) tc_commit(&tfull[acc]);      // accumulator complete
         __syncwarp();
-        PROF_T(4);
+        PROF_T(5);
       }
       ++it_acc;
     }
-    if (prof_on && warp == 0 && lane == 0)
-      for (int i = 0; i < 5; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + i] = pr[i];
+    if (warp == 0 && lane == 0) PROF_OUT(0, 6);
   } else if (warp < UM_MMA_WARPS + UM_EPI_WARPS) {
     // =========================== epilogue ===========================
     const int ew = warp & 3;                 // a warp may only touch TMEM lanes [32*(warp%4), +32)
     uint32_t it_acc = 0;
     PROF_DECL;
-    for (int64_t item = blockIdx.x; item < a.total_items; item += G) {
-      const ItemInfo inf = decode_item(a, item);
-      if (inf.t0 >= inf.T) continue;
-      const UmmaOct& oc = a.oct[inf.o];
+    TileIter ti;
+    for (ti.init(a, blockIdx.x, G); !ti.done(a); ti.step(a, G)) {
+      Tile tl;
+      if (!ti.get(a, tl)) continue;
+      const UmmaOct& oc = a.oct[tl.o];
       const uint32_t acc = it_acc & 1;
       mbar_wait(&tfull[acc], (it_acc >> 1) & 1, a.error_flag);
       tc_fence_after();
       PROF_T(0);
-      const int t = inf.t0 + ew * 32 + lane;
-      const int64_t row = (int64_t)inf.clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
+      const int f = ew * 32 + lane;                                        // frame within the tile
+      const int64_t row = (int64_t)tl.clip * a.out_clip_stride + (int64_t)(tl.t0 + f) * a.frame_pitch;
       const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
-      for (int c0 = 0; c0 < oc.npad && !(a.debug & 4); c0 += 16) {
-        float sum[16];
-#pragma unroll
-        for (int f = 0; f < 16; ++f) sum[f] = 0.f;
+      const bool vec_ok = ((a.frame_pitch | a.out_clip_stride | (int64_t)oc.first_bin) & 3) == 0 && !a.cplx_out &&
+                          (reinterpret_cast<uintptr_t>(a.mag_out) & 15) == 0;
+      for (int c0 = 0; c0 < oc.ncol && !(a.debug & 4); c0 += 8) {
+        float sum[8];
+        uint32_t v[UM_MMA_WARPS][8], u[UM_MMA_WARPS][8];
 #pragma unroll
         for (int g = 0; g < UM_MMA_WARPS; ++g) {
-          uint32_t v[16], u[16];
-          tmem_ld16(tbase + (uint32_t)g * a.grp_stride + (uint32_t)c0, v);
-          if (a.n_split == 3) tmem_ld16(tbase + (uint32_t)g * a.grp_stride + (uint32_t)(oc.npad + c0), u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int f = 0; f < 16; ++f) {
-            sum[f] += __uint_as_float(v[f]);
-            if (a.n_split == 3) sum[f] += __uint_as_float(u[f]);
-          }
+          tmem_ld8(tbase + (uint32_t)g * a.grp_stride + (uint32_t)c0, v[g]);
+          if (split) tmem_ld8(tbase + (uint32_t)g * a.grp_stride + (uint32_t)(oc.ncol + c0), u[g]);
         }
-        if (t < inf.T) {
+        tmem_ld_wait();
 #pragma unroll
-          for (int f = 0; f < 16; f += 2) {
-            const int col = c0 + f;
-            const int bin = oc.first_bin + (col >> 1);
-            if (col < oc.ncol && bin >= 0 && bin < a.n_bins) {
-              const float re = sum[f], im = sum[f + 1];
-              a.mag_out[row + bin] = sqrtf(re * re + im * im);
-              if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
+        for (int i = 0; i < 8; ++i) {
+          float h = 0.f, l = 0.f;
+#pragma unroll
+          for (int g = 0; g < UM_MMA_WARPS; ++g) {
+            h += __uint_as_float(v[g][i]);
+            if (split) l += __uint_as_float(u[g][i]);
+          }
+          sum[i] = h + l;      // the correction columns are ~2^-11 of the main ones: add them last
+        }
+        if (f < tl.valid) {
+          const int bin0 = oc.first_bin + (c0 >> 1);
+          if (a.shared_bank) {
+            const float4* sc = reinterpret_cast<const float4*>(a.col_scale + tl.o * UM_MAX_COLS + c0);
+            const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1);
+            sum[0] *= s0.x; sum[1] *= s0.y; sum[2] *= s0.z; sum[3] *= s0.w;
+            sum[4] *= s1.x; sum[5] *= s1.y; sum[6] *= s1.z; sum[7] *= s1.w;
+          }
+          float m[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = sqrtf(sum[2 * i] * sum[2 * i] + sum[2 * i + 1] * sum[2 * i + 1]);
+          if (vec_ok && bin0 >= 0 && bin0 + 4 <= a.n_bins) {
+            *reinterpret_cast<float4*>(a.mag_out + row + bin0) = make_float4(m[0], m[1], m[2], m[3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int bin = bin0 + i;
+              if (bin >= 0 && bin < a.n_bins) {
+                a.mag_out[row + bin] = m[i];
+                if (a.cplx_out) a.cplx_out[row + bin] = make_float2(sum[2 * i], sum[2 * i + 1]);
+              }
             }
           }
         }
@@ -485,112 +565,106 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
       ++it_acc;
       PROF_T(1);
     }
-    if (prof_on && ew == 0 && lane == 0)
-      for (int i = 0; i < 2; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + 5 + i] = pr[i];
-  } else {
-    // =========================== producers ===========================
-    // Software pipeline over this CTA's (item, stage) jobs: job k's raw fp32 rows are fetched with
-    // cp.async (16 B, L2 -> SMEM, no register staging) a.prefetch jobs ahead of their conversion, so
-    // several stages of L2 requests are in flight per SM; each thread later converts exactly the
-    // elements it fetched (in place -> TF32 hi, plus lo), so cp.async.wait_group is the only sync.
-    const int ptid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS);
-    constexpr int PT = 32 * UM_PRODUCER_WARPS;
-    JobIter is, cv;
-    is.reset(blockIdx.x, G);
-    cv.reset(blockIdx.x, G);
-    bool have_issue = is.next(a);
+    if (ew == 0 && lane == 0) PROF_OUT(6, 2);
+  } else if (warp < UM_MMA_WARPS + UM_EPI_WARPS + UM_LOAD_WARPS) {
+    // =========================== loaders ===========================
+    const int ltid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS);
+    constexpr int LT = 32 * UM_LOAD_WARPS;
+    uint32_t k = 0;
     int cur_oct = -1;
-    const bool split = (a.n_split == 3);
     PROF_DECL;
-    for (uint32_t k = 0;; ++k) {
-      // ---- issue job k -------------------------------------------------------------------
-      if (have_issue) {
-        const UmmaOct& oc = a.oct[is.inf.o];
-        const uint32_t s = k % UM_STAGES;
-        PROF_T(0);
-        mbar_wait(&empty[s], ((k / UM_STAGES) & 1) ^ 1, a.error_flag);
+    TileIter ti;
+    for (ti.init(a, blockIdx.x, G); !ti.done(a); ti.step(a, G)) {
+      Tile tl;
+      if (!ti.get(a, tl)) continue;
+      const UmmaOct& oc = a.oct[tl.o];
+      PROF_T(0);
+      const int bank_id = a.shared_bank ? 0 : tl.o;
+      if (bank_id != cur_oct) {
+        const UmmaOct& ob = a.oct[bank_id];
+        if (ltid == 0) {
+          // new bank: every MMA that reads the old one must have retired (= all stages in flight consumed)
+          const uint32_t back = min(k, S);
+          for (uint32_t j = 1; j <= back; ++j) mbar_wait(&empty[(k - j) % S], ((k - j) / S) & 1, a.error_flag);
+          mbar_arrive_expect_tx(bankbar, ob.bank_bytes);
+          const uint32_t dst = smem_u32(b_s);
+          for (uint32_t off = 0; off < ob.bank_bytes; off += 32768u)
+            bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(ob.b_pack) + off, min(32768u, ob.bank_bytes - off),
+                     bankbar);
+        }
+        cur_oct = bank_id;
         PROF_T(1);
-        float4* raw = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
-        const float* y = oc.sig + (oc.sig_offsets ? oc.sig_offsets[is.inf.clip] : (int64_t)is.inf.clip * oc.sig_stride);
-        const bool base_al = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
-        const int64_t origin = (int64_t)is.inf.t0 * oc.hop - (oc.n_fft >> 1);
-        const int g0 = is.st * a.pps;
+      }
+      // rows that valid frames read: frame r uses rows r .. r+Q-1; the rest of a partial tile stays stale
+      // (MMA rows are independent and frames >= T are never stored)
+      const int rows_used = min(oc.rows, tl.valid + oc.Q - 1);
+      const float* src_tile = oc.sig + (int64_t)tl.clip * oc.sig_stride + (int64_t)tl.t0 * oc.hop;
+      {
+        // pull the NEXT tile of this CTA from HBM into L2 now: its cp.asyncs are issued a few stages from
+        // now and then pay L2 latency instead of DRAM latency (the stage ring is too short to hide the latter)
+        TileIter nx = ti;
+        nx.step(a, G);
+        Tile tn;
+        if (!nx.done(a) && nx.get(a, tn)) {
+          const UmmaOct& on = a.oct[tn.o];
+          const char* p0 = reinterpret_cast<const char*>(on.sig + (int64_t)tn.clip * on.sig_stride + (int64_t)tn.t0 * on.hop);
+          const int nbytes = min(on.rows, tn.valid + on.Q - 1) * on.hop * 4;
+          for (int off = ltid * 128; off < nbytes; off += LT * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + off));
+        }
+      }
+      for (int st = 0; st < oc.n_stages; ++st, ++k) {
+        const uint32_t s = k % S;
+        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
+        PROF_T(2);
+        const int g0 = st * a.pps;
         const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
-        // rows that valid frames read: frame r uses rows r .. r+Q-1; the rest of a partial tile stays stale
-        // (MMA rows are independent and frames >= T are never stored)
-        const int rows_used = min(oc.rows, is.inf.T - is.inf.t0 + oc.Q - 1);
-        const int total = np * rows_used;
-        const int64_t first = origin + 4 * g0;                                  // sample index of element (row 0, plane g0)
-        const int64_t last = first + (int64_t)(rows_used - 1) * oc.hop + 4 * np;  // one past the last sample touched
-        const uint32_t raw_s = smem_u32(raw);
-        if (a.debug & 2) {
-        } else if (base_al && first >= 0 && last <= is.inf.len) {
-          // interior tile: no bounds / reflection tests, 32-bit offsets
-          const float* src0 = y + first;
-          for (int e = ptid; e < total; e += PT) {
-            const int g = e & (np - 1), srow = e >> lg;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + 16u * (uint32_t)(g * oc.rows_pad + srow)),
-                         "l"(src0 + (srow * oc.hop + 4 * g))
-                         : "memory");
-          }
-        } else {
-          for (int e = ptid; e < total; e += PT) {
-            const int g = e & (np - 1), srow = e >> lg;
-            const int64_t idx = first + (int64_t)srow * oc.hop + 4 * g;
-            float4* dst = raw + (g * oc.rows_pad + srow);
-            if (base_al && idx >= 0 && idx + 3 < is.inf.len) {
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(y + idx) : "memory");
-            } else {
-              float4 x;
-              x.x = __ldg(y + reflect_index(idx, is.inf.len));
-              x.y = __ldg(y + reflect_index(idx + 1, is.inf.len));
-              x.z = __ldg(y + reflect_index(idx + 2, is.inf.len));
-              x.w = __ldg(y + reflect_index(idx + 3, is.inf.len));
-              *dst = x;
-            }
-          }
+        const int total = (a.debug & 2) ? 0 : np * rows_used;
+        const uint32_t dst0 = smem_u32(a_base + (2 * s) * a.a_region_bytes);
+        const float* src0 = src_tile + 4 * g0;
+        for (int e = ltid; e < total; e += LT) {
+          const int g = e & (np - 1), srow = e >> lg;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * (uint32_t)(g * oc.rows_pad + srow)),
+                       "l"(src0 + (srow * oc.hop + 4 * g))
+                       : "memory");
         }
-        have_issue = is.next(a);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");      // one group per k, possibly empty
-      PROF_T(2);
-      if (k < a.prefetch) continue;
-      // ---- convert job k - a.prefetch ------------------------------------------------------
-      if (!cv.next(a)) break;
-      const uint32_t kc = k - a.prefetch;
-      const UmmaOct& oc = a.oct[cv.inf.o];
-      if (cv.inf.o != cur_oct) {
-        // new bank: every MMA that reads the old one must have retired
-        if (kc > 0) mbar_wait(&empty[(kc - 1) % UM_STAGES], ((kc - 1) / UM_STAGES) & 1, a.error_flag);
-        const int n16 = (oc.n_fft / 4) * 2 * oc.npad;      // 16-byte units of the packed bank
-        const float4* gb = reinterpret_cast<const float4*>(oc.b_pack);
-        float4* sb = reinterpret_cast<float4*>(b_s);
-        for (int i = ptid; i < n16; i += PT) sb[i] = __ldg(gb + i);
-        cur_oct = cv.inf.o;
+        cp_async_arrive_noinc(&raw[s]);
         PROF_T(3);
       }
+    }
+    if (ltid == 0) PROF_OUT(8, 4);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // =========================== converters ===========================
+    const int ctid = threadIdx.x - 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_LOAD_WARPS);
+    constexpr int CT = 32 * UM_CONV_WARPS;
+    uint32_t k = 0;
+    PROF_DECL;
+    TileIter ti;
+    for (ti.init(a, blockIdx.x, G); !ti.done(a); ti.step(a, G)) {
+      Tile tl;
+      if (!ti.get(a, tl)) continue;
+      const UmmaOct& oc = a.oct[tl.o];
+      const int rows_used = min(oc.rows, tl.valid + oc.Q - 1);
       PROF_T(0);
-      if (a.prefetch == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else if (a.prefetch == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-      else asm volatile("cp.async.wait_group 3;" ::: "memory");
-      PROF_T(4);
-      {
-        const uint32_t s = kc % UM_STAGES;
+      for (int st = 0; st < oc.n_stages; ++st, ++k) {
+        const uint32_t s = k % S;
+        mbar_wait(&raw[s], (k / S) & 1, a.error_flag);
+        PROF_T(1);
         float4* dh = reinterpret_cast<float4*>(a_base + (2 * s) * a.a_region_bytes);
         float4* dl = reinterpret_cast<float4*>(a_base + (2 * s + 1) * a.a_region_bytes);
-        const int g0 = cv.st * a.pps;
+        const int g0 = st * a.pps;
         const int np = min(a.pps, oc.planes - g0);
         const int lg = 31 - __clz(np);
-        const int total = np * min(oc.rows, cv.inf.T - cv.inf.t0 + oc.Q - 1);
-        for (int e = ptid; e < total && !(a.debug & 2); e += PT) {
+        const int total = (a.debug & 2) ? 0 : np * rows_used;
+        for (int e = ctid; e < total; e += CT) {
           const int g = e & (np - 1), srow = e >> lg;
           const int d = g * oc.rows_pad + srow;
           const float4 x = dh[d];
           if (split) {
-            // kind::tf32 reads only the top 19 bits of each operand (the low 13 mantissa bits are
-            // ignored), so the raw fp32 samples already ARE the hi operand: hi = trunc13(x), and
-            // lo = tf32(x - hi) is exact up to 2^-21 |x|.  Only the lo plane has to be written.
+            // kind::tf32 reads only the top 19 bits of each operand, so the raw fp32 samples already ARE
+            // the hi operand: hi = trunc13(x), and lo = tf32(x - hi) is exact up to 2^-21 |x|.
             float4 l;
             l.x = to_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
             l.y = to_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
@@ -604,16 +678,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
             dh[d] = h;
           }
         }
-        PROF_T(5);
-        if (!(a.debug & 8)) fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
+        fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
-        PROF_T(6);
+        PROF_T(2);
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (prof_on && ptid == 0)
-      for (int i = 0; i < 7; ++i) a.prof[blockIdx.x * UM_PROF_SLOTS + 7 + i] = pr[i];
+    if (ctid == 0) PROF_OUT(12, 3);
   }
 
   tc_fence_before();
@@ -637,7 +708,8 @@ __global__ void cqt_zero_pad_kernel(float* mag, float2* cplx, const int32_t* cli
 // ------------------------------------------------------------------ host side
 struct OctPack {
   float* d_pack = nullptr;
-  int npad = 0;
+  int n_main = 0, n_lo = 0;
+  uint32_t bytes = 0;
 };
 
 }  // namespace saga
@@ -649,9 +721,10 @@ struct CqtUmmaState {
   size_t smem_bytes = 0;
   int* d_error = nullptr;
   long long* d_prof = nullptr;
+  float* d_col_scale = nullptr;
+  bool shared_bank = false;
   int num_sms = 0;
-  int n_split = 3;
-  int stages = 2, pps = 8, prefetch = 1;   // pipeline shape (SAGA_UMMA_CFG="stages,planes,prefetch" overrides)
+  int stages = 0, pps = 4;   // pipeline shape (SAGA_UMMA_CFG="stages,planes" overrides; stages 0 = as many as fit)
 };
 
 namespace saga {
@@ -672,60 +745,100 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   p->umma = st;
   if ((int)p->oct.size() > UM_MAX_OCT) return;
   if (const char* cfg = getenv("SAGA_UMMA_CFG")) {
-    int a_ = 0, b_ = 0, c_ = 0;
-    if (sscanf(cfg, "%d,%d,%d", &a_, &b_, &c_) == 3 && a_ >= 2 && a_ <= UM_MAX_STAGES && (b_ == 4 || b_ == 8) && c_ >= 1 &&
-        c_ <= 3 && c_ < a_) {
-      st->stages = a_; st->pps = b_; st->prefetch = c_;
+    int a_ = 0, b_ = 0;
+    if (sscanf(cfg, "%d,%d", &a_, &b_) == 2 && a_ >= 0 && a_ <= UM_MAX_STAGES && a_ != 1 &&
+        (b_ == 2 || b_ == 4 || b_ == 8)) {
+      st->stages = a_; st->pps = b_;
     }
   }
   uint32_t bmax = 0, amax = 0;
-  int npad_max = 0;
+  int nmain_max = 0;
   for (auto& o : p->oct) {
     const int ncol = 2 * o.n_filters;
-    const int npad = (ncol + 15) & ~15;
-    if (npad > 128) return;   // [hi|lo] operand: N = 2*npad <= 256
+    if (ncol % 8) return;                           // the epilogue reads 8 columns (4 filters) at a time
+    const int n_main = (2 * ncol + 15) & ~15;       // [B_hi | B_lo]; M = 128 needs N % 16 == 0
+    if (n_main > 256 || ncol > UM_MAX_COLS) return;
     if (o.hop < 4 || (o.hop % 4) != 0 || (o.n_fft % o.hop) != 0 || (o.n_fft % 8) != 0) return;
     const int planes = o.hop / 4;
     if (planes >= 2 && (std::min(planes, st->pps) % 2) != 0) return;
     const int Q = o.n_fft / o.hop;
     if (planes == 1 && (Q % 2) != 0) return;
     const int np0 = std::min(planes, st->pps);
+    if ((np0 / 2) > UM_MMA_WARPS) return;                         // arithmetic-progression issue path
     const int slices = planes >= 2 ? Q * (np0 / 2) : Q / 2;      // K-slices per stage
     const int n_st = (planes + st->pps - 1) / st->pps;
     if (slices * n_st < UM_MMA_WARPS) return;                     // every issuer warp must get work in an item
     const int rows = UM_TILE_M + Q - 1;
     const int rows_pad = rows | 1;
-    bmax = std::max<uint32_t>(bmax, (uint32_t)o.n_fft * 2u * npad * 4u);
-    amax = std::max<uint32_t>(amax, (uint32_t)std::min(planes, st->pps) * rows_pad * 16u);
-    npad_max = std::max(npad_max, npad);
+    bmax = std::max<uint32_t>(bmax, (uint32_t)o.n_fft * n_main * 4u);
+    amax = std::max<uint32_t>(amax, (uint32_t)np0 * rows_pad * 16u);
+    nmain_max = std::max(nmain_max, n_main);
   }
   amax = (amax + 127u) & ~127u;
   bmax = (bmax + 127u) & ~127u;
-  const size_t smem = (size_t)bmax + 2ull * st->stages * amax + 256;
-  if (smem > 225 * 1024) return;
+  const uint32_t fixed = bmax + 512;              // bank + barriers
+  if (fixed + 2u * 2u * amax > UM_SMEM_LIMIT) return;
+  int fit = (int)((UM_SMEM_LIMIT - fixed) / (2u * amax));
+  fit = std::min(fit, UM_MAX_STAGES);
+  if (st->stages == 0 || st->stages > fit) st->stages = fit;
+  const size_t smem = (size_t)bmax + 2ull * st->stages * amax + 512;
+  const uint32_t grp = ((uint32_t)nmain_max + 31u) & ~31u;
   uint32_t cols = 32;
-  while (cols < 2u * UM_MMA_WARPS * 2u * npad_max) cols <<= 1;   // 2 buffers x issuer groups x (hi|lo)
+  while (cols < 2u * UM_MMA_WARPS * grp) cols <<= 1;   // 2 buffers x issuer groups
   if (cols > 512) return;
   st->b_region_bytes = bmax;
   st->a_region_bytes = amax;
   st->tmem_cols = cols;
   st->acc_stride = cols / 2;
-  st->grp_stride = 2u * npad_max;
+  st->grp_stride = grp;
   st->smem_bytes = smem;
-  // pack each bank for the B descriptor: [n_fft/4][npad][4], split into TF32 hi / lo
+  // librosa analyses every octave with the SAME sparsified basis (times sqrt(2)^level and the per-bin length
+  // normalisation), so each bank is normally a per-column multiple of the first one: detect that and keep
+  // one bank resident for the whole kernel
+  {
+    const CqtOctaveDev& o0 = p->oct[0];
+    const int ncol0 = 2 * o0.n_filters;
+    std::vector<float> scale((size_t)p->oct.size() * UM_MAX_COLS, 0.f);
+    bool shared = p->oct.size() > 1 && getenv("SAGA_UMMA_NO_SHARED_BANK") == nullptr;
+    for (size_t i = 0; shared && i < p->oct.size(); ++i) {
+      const CqtOctaveDev& o = p->oct[i];
+      if (o.n_fft != o0.n_fft || o.n_filters != o0.n_filters) { shared = false; break; }
+      for (int c = 0; c < ncol0 && shared; ++c) {
+        double num = 0, den = 0, peak = 0;
+        for (int k = 0; k < o.n_fft; ++k) {
+          const double b0 = o0.bank_host[(size_t)k * ncol0 + c], b = o.bank_host[(size_t)k * ncol0 + c];
+          num += b * b0; den += b0 * b0; peak = std::max(peak, std::fabs(b));
+        }
+        const double sc = den > 0 ? num / den : 0.0;
+        double dev = 0;
+        for (int k = 0; k < o.n_fft; ++k)
+          dev = std::max(dev, std::fabs(o.bank_host[(size_t)k * ncol0 + c] - sc * o0.bank_host[(size_t)k * ncol0 + c]));
+        if (dev > 4e-7 * peak) shared = false;     // fp32 rounding of the host-built banks is ~6e-8 relative
+        scale[i * UM_MAX_COLS + c] = (float)sc;
+      }
+    }
+    st->shared_bank = shared;
+    if (shared) {
+      if (cudaMalloc(&st->d_col_scale, scale.size() * 4) != cudaSuccess) return;
+      cudaMemcpy(st->d_col_scale, scale.data(), scale.size() * 4, cudaMemcpyHostToDevice);
+    }
+  }
+  // pack each bank for the B descriptor: [n_fft/4][n_main][4]; rows [0,ncol) TF32 hi, [ncol,2ncol) lo
   for (auto& o : p->oct) {
     OctPack pk;
     const int ncol = 2 * o.n_filters;
-    pk.npad = (ncol + 15) & ~15;
-    const size_t n = (size_t)o.n_fft * 2 * pk.npad;
+    pk.n_main = (2 * ncol + 15) & ~15;
+    pk.n_lo = (ncol + 15) & ~15;
+    const size_t n = (size_t)o.n_fft * pk.n_main;
+    pk.bytes = (uint32_t)(n * 4);
     std::vector<float> pack(n, 0.f);
     for (int k = 0; k < o.n_fft; ++k)
       for (int c = 0; c < ncol; ++c) {
         const float b = o.bank_host[(size_t)k * ncol + c];
         const float h = tf32_rna_host(b);
-        const size_t chunk = (size_t)(k / 4) * 2 * pk.npad;
+        const size_t chunk = (size_t)(k / 4) * pk.n_main;
         pack[(chunk + c) * 4 + (k % 4)] = h;
-        pack[(chunk + pk.npad + c) * 4 + (k % 4)] = tf32_rna_host(b - h);
+        pack[(chunk + ncol + c) * 4 + (k % 4)] = tf32_rna_host(b - h);
       }
     if (cudaMalloc(&pk.d_pack, n * 4) != cudaSuccess) return;
     cudaMemcpy(pk.d_pack, pack.data(), n * 4, cudaMemcpyHostToDevice);
@@ -734,6 +847,7 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) return;
   cudaMemset(st->d_error, 0, sizeof(int));
   if (cudaMalloc(&st->d_prof, sizeof(long long) * 256 * UM_PROF_SLOTS) != cudaSuccess) return;
+  cudaMemset(st->d_prof, 0, sizeof(long long) * 256 * UM_PROF_SLOTS);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -749,25 +863,33 @@ void cqt_umma_plan_free(saga_cqt_plan* p) {
   for (auto& pk : p->umma->packs) cudaFree(pk.d_pack);
   cudaFree(p->umma->d_error);
   cudaFree(p->umma->d_prof);
+  cudaFree(p->umma->d_col_scale);
   delete p->umma;
   p->umma = nullptr;
 }
 
+bool cqt_umma_supported(const saga_cqt_plan* p) { return p->umma && p->umma->supported; }
+
 int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t max_len, int64_t T_max,
                   float* mag_out, float2* cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
-                  int n_split, cudaStream_t stream) {
+                  int n_split, int tail_max, cudaStream_t stream) {
   const CqtUmmaState* st = p->umma;
   if (!st || !st->supported) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: plan does not fit the tcgen05 path");
   UmmaArgs a;
   std::memset(&a, 0, sizeof(a));
   a.n_oct = (int)p->oct.size();
   a.n_clips = n_clips;
-  a.tiles_per_clip = (int)((T_max + UM_TILE_M - 1) / UM_TILE_M);
-  a.early_factor = p->early_factor;
+  const int64_t tpc = (T_max + UM_TILE_M - 1) / UM_TILE_M;
+  const int64_t per_oct = (int64_t)n_clips * tpc;
+  if (per_oct * a.n_oct >= (int64_t)1 << 31) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: batch too large for one launch");
+  a.tiles_per_clip = (uint32_t)tpc;
+  a.per_oct = (uint32_t)per_oct;
+  a.total_items = (uint32_t)(per_oct * a.n_oct);
   a.n_bins = p->n_bins;
   a.n_split = (n_split == 1) ? 1 : 3;
-  a.clip_lens = lv.clip_lens;
   a.clip_frames = lv.clip_frames;
+  a.uniform_T = lv.clip_lens ? 0 : (int)T_max;
+  a.tail_max = tail_max;
   a.mag_out = mag_out;
   a.cplx_out = cplx_out;
   a.frame_pitch = frame_pitch;
@@ -781,44 +903,33 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.prof = st->d_prof;
   a.stages = st->stages;
   a.pps = st->pps;
-  a.prefetch = st->prefetch;
-  a.uniform_T = lv.clip_lens ? 0 : (int)T_max;
-  a.uniform_len = lv.max_len;
+  a.shared_bank = st->shared_bank ? 1 : 0;
+  a.col_scale = st->d_col_scale;
   {
     const char* dbg = getenv("SAGA_UMMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
   }
-  const int64_t per_oct = (int64_t)n_clips * a.tiles_per_clip;
   for (int i = 0; i < a.n_oct; ++i) {
     const CqtOctaveDev& o = p->oct[i];
     UmmaOct& u = a.oct[i];
-    const bool raw = (o.level == 0 && p->early_factor == 1);
-    u.sig = raw ? lv.wav : lv.lvl[o.level];
-    u.sig_offsets = raw ? lv.clip_offsets : nullptr;
-    u.sig_stride = raw ? 0 : lv.pitch[o.level];
+    // padded level buffer: sample s of clip c lives at lvl + c*pitch + pad + s
+    u.sig = lv.lvl[o.level] + (lv.pad[o.level] - o.n_fft / 2);
+    u.sig_stride = lv.pitch[o.level];
     u.b_pack = st->packs[i].d_pack;
-    u.level = o.level;
+    u.bank_bytes = st->packs[i].bytes;
     u.hop = o.hop;
     u.n_fft = o.n_fft;
     u.ncol = 2 * o.n_filters;
-    u.npad = st->packs[i].npad;
+    u.n_main = st->packs[i].n_main;
+    u.n_lo = st->packs[i].n_lo;
     u.first_bin = o.first_bin;
     u.planes = o.hop / 4;
-    u.np_log2 = u.planes >= 4 ? 2 : (u.planes == 2 ? 1 : 0);
     u.n_stages = (u.planes + st->pps - 1) / st->pps;
     u.Q = o.n_fft / o.hop;
     u.rows = UM_TILE_M + u.Q - 1;
     u.rows_pad = u.rows | 1;
-    u.item_begin = per_oct * i;
-    {
-      int64_t len = lv.max_len;
-      if (p->early_factor > 1) len = (len + p->early_factor - 1) / p->early_factor;
-      for (int s = 0; s < o.level; ++s) len = (len + 1) >> 1;
-      u.uniform_len = len;
-    }
   }
-  a.total_items = per_oct * a.n_oct;
-  if (a.total_items <= 0) return SAGA_OK;
+  if (a.total_items == 0) return SAGA_OK;
   if (frame_pitch > p->n_bins) {
     dim3 grid(8, n_clips), block(32, 8);
     cqt_zero_pad_kernel<<<grid, block, 0, stream>>>(mag_out, cplx_out, lv.clip_frames, p->n_bins, frame_pitch,
@@ -833,13 +944,28 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     std::vector<long long> h((size_t)grid * UM_PROF_SLOTS);
     cudaStreamSynchronize(stream);
     cudaMemcpy(h.data(), st->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    static const char* names[14] = {"mma.decode", "mma.wait_tempty", "mma.wait_full", "mma.issue", "mma.commit",
-                                    "epi.wait_tfull", "epi.work", "prod.loop", "prod.wait_empty", "prod.issue",
-                                    "prod.bank", "prod.wait_group", "prod.convert", "prod.fence_arrive"};
-    for (int s = 0; s < 14; ++s) {
-      double sum = 0;
-      for (int c = 0; c < grid; ++c) sum += (double)h[(size_t)c * UM_PROF_SLOTS + s];
-      fprintf(stderr, "umma_prof %-18s %10.0f cycles/CTA\n", names[s], sum / grid);
+    static const char* names[15] = {"mma.decode", "mma.wait_bank", "mma.wait_tempty", "mma.wait_full", "mma.issue",
+                                    "mma.commit", "epi.wait_tfull", "epi.work", "load.decode", "load.bank",
+                                    "load.wait_empty", "load.issue", "conv.decode", "conv.wait_raw", "conv.convert"};
+    fprintf(stderr, "umma_prof stages=%d planes/stage=%d smem=%zu shared_bank=%d\n", st->stages, st->pps, st->smem_bytes,
+            (int)st->shared_bank);
+    for (int s = 0; s < 15; ++s) {
+      double sum = 0, mx = 0;
+      for (int c = 0; c < grid; ++c) {
+        sum += (double)h[(size_t)c * UM_PROF_SLOTS + s];
+        mx = std::max(mx, (double)h[(size_t)c * UM_PROF_SLOTS + s]);
+      }
+      fprintf(stderr, "umma_prof %-18s %10.0f cycles/CTA (max %.0f)\n", names[s], sum / grid, mx);
+    }
+    {
+      double mx = 0, mn = 1e30;
+      for (int c = 0; c < grid; ++c) {
+        double t = 0;
+        for (int s = 0; s < 6; ++s) t += (double)h[(size_t)c * UM_PROF_SLOTS + s];
+        mx = std::max(mx, t);
+        mn = std::min(mn, t);
+      }
+      fprintf(stderr, "umma_prof mma role total per CTA: min %.0f max %.0f cycles\n", mn, mx);
     }
   }
   return SAGA_OK;

@@ -207,8 +207,10 @@ def _workspace(nbytes, device):
     return ws
 
 
-def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0):
-    """K2.  Returns dict(mag=[clips, n_bins, T] view, C=complex view if requested)."""
+def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0, fill=None):
+    """K2.  Returns dict(mag=[clips, n_bins, T] view, C=complex view if requested).
+    `fill` (tests): value the outputs are set to before the call, so that an element the kernels
+    failed to write cannot hide behind stale allocator contents."""
     wav, offs, lens_dev, max_len = _clip_table(wav, lens)
     n_clips = wav.shape[0]
     lib = _lib.lib()
@@ -218,6 +220,10 @@ def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0):
     alloc = torch.empty if lens is None else torch.zeros
     mag = alloc((n_clips, T, P), device=dev, dtype=torch.float32)
     cx = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_complex else None
+    if fill is not None:
+        mag.fill_(fill)
+        if cx is not None:
+            cx.fill_(fill)
     nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
     ws = _workspace(nbytes, dev)
     _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev) if lens is not None else None,

@@ -20,7 +20,7 @@ os.environ["SAGA_UMMA_DEBUG"] = "16"
 ops.cqt_batch(wav, plan, impl=2 | 0x200)
 torch.cuda.synchronize()
 '''
-for cfg in ("2,8,1", "4,4,1"):
+for cfg in ("0,4", "3,8"):
     env = dict(os.environ, SAGA_UMMA_CFG=cfg)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print("== cfg", cfg)

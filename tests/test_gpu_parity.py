@@ -217,6 +217,7 @@ CQT_CASES = [
     (44100, 1024, "A0", 87, 12, 88200),
     (44100, 1024, "A0", 174, 24, 66150),
     (44100, 1024, "D3", 36, 24, 66150),
+    (44100, 512, "C1", 84, 12, 512 * 133 + 100),    # 134 frames: the 6-frame partial tile goes to cqt_tail_kernel
 ]
 
 
@@ -231,7 +232,7 @@ def test_cqt_matches_oracle(saga, cfg1, sr, hop, low, n_bins, bpo, n, impl):
     ref = ocqt.cqt(y, sr=sr, hop_length=hop, fmin=fmin, n_bins=n_bins, bins_per_octave=bpo, filter_scale=2)
     plan = ops.CqtPlan(sr, hop, fmin, n_bins, bpo, filter_scale=2)
     try:
-        r = ops.cqt_batch(dev(y), plan, want_complex=True, impl=impl)
+        r = ops.cqt_batch(dev(y), plan, want_complex=True, impl=impl, fill=float("nan"))
     except SagaUnsupported:
         pytest.skip("bank does not fit the resident-B tensor path (falls back to fp32 under impl=0)")
     assert tuple(r["mag"].shape) == (1,) + ref.shape
@@ -251,12 +252,26 @@ def test_cqt_ragged_batch(saga):
     wav = np.zeros((len(lens), max(lens)), dtype=np.float32)
     for i, n in enumerate(lens):
         wav[i, :n] = piano_clip(40 + i, n)
-    r = ops.cqt_batch(dev(wav), plan, lens=lens)
+    r = ops.cqt_batch(dev(wav), plan, lens=lens, fill=float("nan"))
     for i, n in enumerate(lens):
         ref = np.abs(ocqt.cqt(wav[i, :n], sr=sr, hop_length=hop, fmin=fmin, n_bins=84, filter_scale=2))
         got = r["mag"][i].cpu().numpy()
         assert plan.num_frames(n) == ref.shape[1]
         check_mag(got[:, :ref.shape[1]], ref)
+
+
+@pytest.mark.parametrize("n", [66150, 512 * 300 + 7])
+def test_cqt_tensor_path_equals_fp32_path_on_a_batch(saga, n):
+    """Many tiles per persistent CTA (tile walk, stage ring wrap-around, octave interleaving, tail kernel):
+    the tcgen05 path against the CUDA-core path on 40 clips, outputs poisoned with NaN beforehand."""
+    ops, _ = saga
+    plan = ops.CqtPlan(44100, 512, osp.note_to_hz("C1"), 84, 12, filter_scale=2)
+    wav = dev(np.stack([piano_clip(500 + i, n) for i in range(40)]))
+    ref = ops.cqt_batch(wav, plan, impl=1, fill=float("nan"))["mag"]
+    got = ops.cqt_batch(wav, plan, impl=2, fill=float("nan"))["mag"]
+    assert not torch.isnan(got).any() and not torch.isnan(ref).any()
+    err = float((got - ref).abs().max() / ref.max())
+    assert err <= 1e-5, err
 
 
 # --------------------------------------------------------------------------- class flow
