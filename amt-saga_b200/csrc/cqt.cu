@@ -316,101 +316,7 @@ __global__ void __launch_bounds__(256) cqt_pad_kernel(const PadArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------
-// Partial last tiles with few valid frames (<= TAIL_MAX): the tensor-core kernel would pay a full
-// 128-row MMA sequence for them, so they are contracted here on the CUDA cores instead.  CTA =
-// (octave, clip); lane = output column, the 8 warps split n_fft; the signal value is a warp-uniform
-// (broadcast) load from the padded level buffer.
-// ---------------------------------------------------------------------------
-constexpr int TAIL_MAX = 16;
-constexpr int TAIL_TILE = 128;
-struct TailOct {
-  const float* sig;       // padded level signal, element 0 of a clip = sample -n_fft/2
-  int64_t sig_stride;
-  const float* bank;      // [n_fft][ncol]
-  int hop, n_fft, ncol, first_bin;
-};
-struct TailArgs {
-  TailOct oct[12];
-  const int32_t* clip_frames;
-  int uniform_T, n_bins;
-  float* mag_out;
-  float2* cplx_out;
-  int64_t frame_pitch, out_clip_stride;
-};
-
-constexpr int TAIL_KC = 256;   // kernel samples staged per pass
-
-__global__ void __launch_bounds__(256) cqt_tail_kernel(const TailArgs a) {
-  __shared__ __align__(16) float ysm[TAIL_MAX][TAIL_KC];   // signal rows of the tail frames
-  __shared__ float red[8][TAIL_MAX][32];
-  const TailOct& oc = a.oct[blockIdx.x];
-  const int clip = blockIdx.y;
-  const int T = a.uniform_T > 0 ? a.uniform_T : a.clip_frames[clip];
-  const int rem = T % TAIL_TILE;
-  if (rem == 0 || rem > TAIL_MAX) return;
-  const int t0 = T - rem;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* y = oc.sig + (int64_t)clip * oc.sig_stride + (int64_t)t0 * oc.hop;
-  for (int c0 = 0; c0 < oc.ncol; c0 += 32) {
-    const int col = c0 + lane;
-    float acc[TAIL_MAX];
-#pragma unroll
-    for (int f = 0; f < TAIL_MAX; ++f) acc[f] = 0.f;
-    for (int n0 = 0; n0 < oc.n_fft; n0 += TAIL_KC) {
-      __syncthreads();
-#pragma unroll
-      for (int f = 0; f < TAIL_MAX; ++f) {
-        const int n = n0 + (int)threadIdx.x;
-        if (f < rem) ysm[f][threadIdx.x] = n < oc.n_fft ? __ldg(y + f * oc.hop + n) : 0.f;
-      }
-      __syncthreads();
-      // warp w contracts samples [n0 + 32 w, n0 + 32 w + 32): coalesced bank rows; the signal is a broadcast
-      // 16-byte shared load per (frame, 4 samples); frames beyond `rem` are skipped (warp-uniform test)
-      const int nb = n0 + 32 * w;
-      float g[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        g[i] = (col < oc.ncol && nb + i < oc.n_fft) ? __ldg(oc.bank + (int64_t)(nb + i) * oc.ncol + col) : 0.f;
-#pragma unroll
-      for (int f = 0; f < TAIL_MAX; ++f) {
-        if (f < rem) {
-          const float4* yr = reinterpret_cast<const float4*>(&ysm[f][32 * w]);
-          float r = acc[f];
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 v = yr[i4];
-            r = fmaf(g[4 * i4 + 0], v.x, r);
-            r = fmaf(g[4 * i4 + 1], v.y, r);
-            r = fmaf(g[4 * i4 + 2], v.z, r);
-            r = fmaf(g[4 * i4 + 3], v.w, r);
-          }
-          acc[f] = r;
-        }
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int f = 0; f < TAIL_MAX; ++f) red[w][f][lane] = acc[f];
-    __syncthreads();
-    // thread -> (frame f, filter j of this column chunk)
-    const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
-    if (f < rem && c0 + 2 * j < oc.ncol) {
-      float re = 0.f, im = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < 8; ++ww) {
-        re += red[ww][f][2 * j];
-        im += red[ww][f][2 * j + 1];
-      }
-      const int bin = oc.first_bin + (c0 >> 1) + j;
-      if (bin >= 0 && bin < a.n_bins) {
-        const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)(t0 + f) * a.frame_pitch;
-        a.mag_out[row + bin] = sqrtf(re * re + im * im);
-        if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
-      }
-    }
-  }
-}
+constexpr int TAIL_MAX = 16;   // partial tiles up to this many frames go to cqt_tail_kernel (cqt_umma.cu), not to the MMAs
 
 }  // namespace saga
 
@@ -613,34 +519,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   if (impl != 1) {
     int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
                            out_clip_stride, impl == 3 ? 1 : 3, TAIL_MAX, st);
-    if (rc == SAGA_OK) {
-      const int rem = (int)(T_max % TAIL_TILE);
-      if (clip_lens || (rem > 0 && rem <= TAIL_MAX)) {   // some clip may end in a short partial tile
-        TailArgs ta;
-        if (p->oct.size() > 12) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: too many octaves");
-        for (size_t i = 0; i < p->oct.size(); ++i) {
-          const CqtOctaveDev& o = p->oct[i];
-          ta.oct[i].sig = lvl[o.level] + (pad[o.level] - o.n_fft / 2);
-          ta.oct[i].sig_stride = pitch[o.level];
-          ta.oct[i].bank = o.bank;
-          ta.oct[i].hop = o.hop;
-          ta.oct[i].n_fft = o.n_fft;
-          ta.oct[i].ncol = 2 * o.n_filters;
-          ta.oct[i].first_bin = o.first_bin;
-        }
-        ta.clip_frames = clip_frames;
-        ta.uniform_T = clip_lens ? 0 : (int)T_max;
-        ta.n_bins = p->n_bins;
-        ta.mag_out = C_mag_out;
-        ta.cplx_out = (float2*)C_cplx_out;
-        ta.frame_pitch = frame_pitch;
-        ta.out_clip_stride = out_clip_stride;
-        dim3 grid((unsigned)p->oct.size(), n_clips);
-        cqt_tail_kernel<<<grid, 256, 0, st>>>(ta);
-        SAGA_LAUNCH_CHECK();
-      }
-      return SAGA_OK;
-    }
+    if (rc == SAGA_OK) return SAGA_OK;
     if (rc != SAGA_ERR_UNSUPPORTED || impl >= 2) return rc;
   }
   bool first = true;

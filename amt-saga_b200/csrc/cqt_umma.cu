@@ -40,7 +40,7 @@
 // mbarrier pipelines: raw / full / empty per A stage, full / empty per TMEM buffer, one
 // for the bank.  The bank G_o stays resident in SMEM while the CTA works through tiles of
 // one octave (tiles are ordered octave-major) and is replaced by ONE bulk async copy.
-// Partial tiles with <= tail_max valid frames are left to cqt_tail_kernel (cqt.cu):
+// Partial tiles with <= tail_max valid frames are left to cqt_tail_kernel (below):
 // an MMA costs the same for 5 valid rows as for 128.
 #include <algorithm>
 #include <cmath>
@@ -60,6 +60,8 @@ constexpr int UM_EPI_WARPS = 4;
 constexpr int UM_LOAD_WARPS = 8;
 constexpr int UM_CONV_WARPS = 8;
 constexpr int UM_THREADS = 32 * (UM_MMA_WARPS + UM_EPI_WARPS + UM_LOAD_WARPS + UM_CONV_WARPS);
+constexpr int UM_TAIL_WARPS = 4;            // warps per CTA of cqt_tail_kernel
+constexpr int UM_TAIL_MAX = 16;             // largest partial tile (frames) left to cqt_tail_kernel
 constexpr int UM_MAX_STAGES = 8;            // barrier array capacity; the actual count is a plan parameter
 constexpr int UM_MAX_OCT = 12;
 constexpr int UM_MAX_COLS = 128;
@@ -71,6 +73,7 @@ struct UmmaOct {
   const float* sig;       // padded level signal, element 0 of a clip = sample -n_fft/2
   int64_t sig_stride;     // floats per clip
   const float* b_pack;    // packed [n_fft/4][n_main][4]: rows [0,ncol) = TF32 hi, [ncol,2ncol) = lo, rest 0
+  const float* bank_f32;  // [n_fft][ncol] fp32 bank of THIS octave (tail warps)
   uint32_t bank_bytes;
   int hop, n_fft, ncol, first_bin;
   int planes, n_stages, Q, rows, rows_pad;
@@ -694,6 +697,72 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cqt_umma_kernel(const __grid_co
   }
 }
 
+// A clip's last tile with <= tail_max valid frames would cost a full 128-row MMA sequence, so the
+// tensor-core kernel skips it and this kernel contracts it on the CUDA cores: ONE WARP per (octave, clip),
+// lane = output column, fp32 bank rows coalesced, signal values as 16-byte broadcast loads from the padded
+// level buffers.  No shared memory and <= 80 registers: launched on the plan's side stream it co-resides
+// with the persistent tensor-core kernel (which leaves ~10 k registers per SM unused) and hides under it.
+template <int NF>
+__device__ __forceinline__ void tail_item(const UmmaArgs& a, const UmmaOct& oc, int o, uint32_t clip, int rem, int t0,
+                                          int lane) {
+  const float* y = oc.sig + (int64_t)clip * oc.sig_stride + (int64_t)t0 * oc.hop;
+  // frame f reads y + f*hop + n; frames >= rem re-read the last valid one (branch-free loads, results unused)
+  int foff[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) foff[f] = min(f, rem - 1) * oc.hop;
+  for (int c0 = 0; c0 < oc.ncol; c0 += 32) {
+    const int col = c0 + lane;
+    const bool live = col < oc.ncol;
+    // shared-bank plans: every octave reads octave 0's bank (one 48 KB table for all warps of the SM) and
+    // applies its per-column scale at the end, like the tensor-core epilogue
+    const float* bk = (a.shared_bank ? a.oct[0].bank_f32 : oc.bank_f32) + (live ? col : 0);
+    const float cs = (a.shared_bank && live) ? __ldg(a.col_scale + o * UM_MAX_COLS + col) : 1.f;
+    float acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+#pragma unroll 1
+    for (int n = 0; n < oc.n_fft; n += 4) {
+      const float g0 = __ldg(bk + (int64_t)(n + 0) * oc.ncol), g1 = __ldg(bk + (int64_t)(n + 1) * oc.ncol);
+      const float g2 = __ldg(bk + (int64_t)(n + 2) * oc.ncol), g3 = __ldg(bk + (int64_t)(n + 3) * oc.ncol);
+      float4 v[NF];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) v[f] = __ldg(reinterpret_cast<const float4*>(y + foff[f] + n));
+#pragma unroll
+      for (int f = 0; f < NF; ++f) acc[f] = fmaf(g3, v[f].w, fmaf(g2, v[f].z, fmaf(g1, v[f].y, fmaf(g0, v[f].x, acc[f]))));
+    }
+    // lanes (2j, 2j+1) hold re / im of filter j
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      acc[f] *= cs;
+      const float im = __shfl_down_sync(0xffffffffu, acc[f], 1);
+      const int bin = oc.first_bin + (col >> 1);
+      if (f < rem && live && !(lane & 1) && bin >= 0 && bin < a.n_bins) {
+        const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)(t0 + f) * a.frame_pitch;
+        a.mag_out[row + bin] = sqrtf(acc[f] * acc[f] + im * im);
+        if (a.cplx_out) a.cplx_out[row + bin] = make_float2(acc[f], im);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * UM_TAIL_WARPS, 6) cqt_tail_kernel(const __grid_constant__ UmmaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t idx = blockIdx.x * UM_TAIL_WARPS + (threadIdx.x >> 5);
+  if (idx >= (uint32_t)a.n_oct * (uint32_t)a.n_clips) return;
+  const uint32_t clip = idx / (uint32_t)a.n_oct;
+  const int o = (int)(idx - clip * (uint32_t)a.n_oct);
+  const UmmaOct& oc = a.oct[o];
+  const int T = a.uniform_T > 0 ? a.uniform_T : a.clip_frames[clip];
+  const int rem = T % UM_TILE_M;
+  if (rem == 0 || rem > a.tail_max) return;
+  const int t0 = T - rem;
+  if (rem <= 4) {
+    tail_item<4>(a, oc, o, clip, rem, t0, lane);
+  } else {
+    for (int f0 = 0; f0 < rem; f0 += 8) tail_item<8>(a, oc, o, clip, min(rem - f0, 8), t0 + f0, lane);   // 8 frames per sweep
+  }
+}
+
 __global__ void cqt_zero_pad_kernel(float* mag, float2* cplx, const int32_t* clip_frames, int n_bins,
                                     int64_t pitch, int64_t clip_stride) {
   const int clip = blockIdx.y;
@@ -722,6 +791,7 @@ struct CqtUmmaState {
   int* d_error = nullptr;
   long long* d_prof = nullptr;
   float* d_col_scale = nullptr;
+  cudaStream_t side = nullptr;   // tail kernel runs here, concurrently with the persistent kernel
   bool shared_bank = false;
   int num_sms = 0;
   int stages = 0, pps = 4;   // pipeline shape (SAGA_UMMA_CFG="stages,planes" overrides; stages 0 = as many as fit)
@@ -855,6 +925,10 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
     cudaGetLastError();
     return;
   }
+  if (cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    st->side = nullptr;
+  }
   st->supported = true;
 }
 
@@ -864,6 +938,7 @@ void cqt_umma_plan_free(saga_cqt_plan* p) {
   cudaFree(p->umma->d_error);
   cudaFree(p->umma->d_prof);
   cudaFree(p->umma->d_col_scale);
+  if (p->umma->side) cudaStreamDestroy(p->umma->side);
   delete p->umma;
   p->umma = nullptr;
 }
@@ -889,7 +964,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.n_split = (n_split == 1) ? 1 : 3;
   a.clip_frames = lv.clip_frames;
   a.uniform_T = lv.clip_lens ? 0 : (int)T_max;
-  a.tail_max = tail_max;
+  a.tail_max = std::min(tail_max, UM_TAIL_MAX);
   a.mag_out = mag_out;
   a.cplx_out = cplx_out;
   a.frame_pitch = frame_pitch;
@@ -916,6 +991,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     u.sig = lv.lvl[o.level] + (lv.pad[o.level] - o.n_fft / 2);
     u.sig_stride = lv.pitch[o.level];
     u.b_pack = st->packs[i].d_pack;
+    u.bank_f32 = o.bank;
     u.bank_bytes = st->packs[i].bytes;
     u.hop = o.hop;
     u.n_fft = o.n_fft;
@@ -937,8 +1013,35 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     SAGA_LAUNCH_CHECK();
   }
   const int grid = (int)std::min<int64_t>(a.total_items, st->num_sms > 0 ? st->num_sms : 148);
+  // short partial tiles: forked onto the side stream BEFORE the persistent kernel so that both are resident
+  // together; joined back afterwards.  Events are per call (a plan may be driven from several streams).
+  const int rem = (int)(T_max % UM_TILE_M);
+  const bool tails = a.tail_max > 0 && (lv.clip_lens || (rem > 0 && rem <= a.tail_max));
+  cudaEvent_t ev_join = nullptr;
+  if (tails) {
+    const unsigned n_items = (unsigned)a.n_oct * (unsigned)n_clips;
+    const unsigned tgrid = (n_items + UM_TAIL_WARPS - 1) / UM_TAIL_WARPS;
+    cudaEvent_t ev_fork = nullptr;
+    if (st->side && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ev_fork, stream);
+      cudaStreamWaitEvent(st->side, ev_fork, 0);
+      cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, st->side>>>(a);
+      cudaEventRecord(ev_join, st->side);
+      cudaEventDestroy(ev_fork);
+    } else {
+      if (ev_fork) cudaEventDestroy(ev_fork);
+      ev_join = nullptr;
+      cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, stream>>>(a);
+    }
+    SAGA_LAUNCH_CHECK();
+  }
   cqt_umma_kernel<<<grid, UM_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
+  if (ev_join) {
+    cudaStreamWaitEvent(stream, ev_join, 0);
+    cudaEventDestroy(ev_join);
+  }
   if (a.debug & 16) {
     // profiling aid only: synchronous read-back of the per-role cycle counters, mean over CTAs
     std::vector<long long> h((size_t)grid * UM_PROF_SLOTS);

@@ -18,6 +18,7 @@
 //    per-clip maxima (ref_mag) are a by-product.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "fft_radix.cuh"
@@ -58,9 +59,16 @@ struct StftArgs {
   int hop, center, frames_per_cta, span_alloc, tiles_per_clip, max_frames;
 };
 
+// table element: read-only global path, or a plain (shared-memory) load when the CTA keeps the tables in SMEM
+template <bool GT>
+__device__ __forceinline__ float2 tab(const float2* p) {
+  if (GT) return __ldg(p);
+  return *p;
+}
+
 // One DIF pass over blocks of length L with radix R, in place in `buf`.
 // FIRST reads the windowed real samples instead of buf.
-template <int M, int L, int R, bool FIRST, bool LAST>
+template <int M, int L, int R, bool FIRST, bool LAST, bool GT = true>
 __device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const float2* __restrict__ win2,
                                          const float2* __restrict__ tw, int lane) {
   constexpr int LS = L / R;       // sub-block length after this pass
@@ -85,8 +93,7 @@ __device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const flo
           x.x = xs[2 * n];
           x.y = xs[2 * n + 1];
         }
-        const float2 w = __ldg(win2 + n);
-        v[r] = make_float2(x.x * w.x, x.y * w.y);
+        v[r] = pmul(x, tab<GT>(win2 + n));
       }
     } else {
 #pragma unroll
@@ -97,7 +104,7 @@ __device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const flo
     for (int i = 0; i < R; ++i) {
       const int rp = bitrev(i, R);
       float2 o = v[i];
-      if (!LAST && rp > 0) o = cmul(o, __ldg(tw + rp * LS + j));
+      if (!LAST && rp > 0) o = cmul(o, tab<GT>(tw + rp * LS + j));
       buf[pidx(base + rp * LS)] = o;
     }
   }
@@ -123,11 +130,93 @@ __device__ __forceinline__ float fast_sqrt(float x) {   // sqrt.approx: ~1 ulp, 
 // so with s = Zk + Zm (componentwise), d = Zk - Zm:  T = W^k * (s.y, -d.x),
 //   X[k] = (s.x + T.x, d.y + T.y),   X[M-k] = conj(s.x - T.x, d.y - T.y).
 __device__ __forceinline__ void split_pair(float2 zk, float2 zm, float2 w, float2& Xk, float2& Xm) {
-  const float sx = zk.x + zm.x, dx = zk.x - zm.x, sy = zk.y + zm.y, dy = zk.y - zm.y;
+  const float2 s = cadd(zk, zm), d = csub(zk, zm);
+  const float sx = s.x, dx = d.x, sy = s.y, dy = d.y;
   const float tx = fmaf(w.x, sy, w.y * dx);      // Re(w * (sy - i dx))
   const float ty = fmaf(w.y, sy, -(w.x * dx));   // Im
   Xk = make_float2(sx + tx, dy + ty);
   Xm = make_float2(sx - tx, ty - dy);
+}
+
+// Real-FFT split of one transformed frame (Z in `buf`, digit-reversed order) -> |X| (+ phasor / complex),
+// coalesced rows of the frame-major output, per-frame and per-clip maxima.
+template <int M, int R0, int R1, int R2, bool EXTRA, bool GT>
+__device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* twN, const StftArgs& a, int clip,
+                                               int64_t t, int lane) {
+  // smem positions of Z[lane + 32 i] and of its partner Z[M - lane - 32 i] (digit-reversed order):
+  //   zpos is affine in i for a fixed lane, so both are base + i * step
+  const int zk0 = pidx(zpos<M, R0, R1, R2>(lane));
+  const int zk1 = pidx(zpos<M, R0, R1, R2>(lane + 32));
+  const int zm0 = pidx(zpos<M, R0, R1, R2>((M - lane) & (M - 1)));
+  const int zm1 = pidx(zpos<M, R0, R1, R2>(M - lane - 32));
+  const int zm2 = pidx(zpos<M, R0, R1, R2>(M - lane - 64));
+  const int zk_step = zk1 - zk0, zm_step = zm2 - zm1;
+  // ---- real-FFT split, |X|, outputs -----------------------------------
+    const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
+  float* mag_up = a.mag_out + row + lane;           // bins lane + 32 i
+  float* mag_dn = a.mag_out + row + (M - lane);     // bins M - lane - 32 i
+  const float2* twp = twN + lane;
+  float vmax = 0.f;
+  constexpr int ITERS = M / 64;                     // k = lane + 32 i < M/2
+#pragma unroll 8
+  for (int i = 0; i < ITERS; ++i) {
+    float2 zk, zm;
+    if constexpr (R2 == 1) {      // two-pass shapes: both positions are affine in i
+      zk = buf[zk0 + i * zk_step];
+      zm = buf[i == 0 ? zm0 : zm1 + (i - 1) * zm_step];
+    } else {
+      const int k = lane + 32 * i;
+      zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
+      zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
+    }
+    float2 Xk, Xm;
+    split_pair(zk, zm, tab<GT>(twp + 32 * i), Xk, Xm);
+    const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
+    const float mm = fast_sqrt(fmaf(Xm.x, Xm.x, Xm.y * Xm.y));
+    vmax = fmaxf(vmax, fmaxf(mk, mm));
+    mag_up[32 * i] = mk;
+    mag_dn[-32 * i] = mm;
+    if (EXTRA) {
+      const int k = lane + 32 * i;
+      if (a.cplx_out) {
+        float2* c = a.cplx_out + row;
+        c[k] = Xk;
+        c[M - k] = Xm;
+      }
+      if (a.phase_out) {
+        float2* p = a.phase_out + row;
+        p[k] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
+        p[M - k] = mm > 0.f ? make_float2(Xm.x / mm, Xm.y / mm) : make_float2(1.f, 0.f);
+      }
+    }
+  }
+  if (lane == 0) {
+    // k = M/2 pairs with itself
+    const float2 z = buf[pidx(zpos<M, R0, R1, R2>(M / 2))];
+    float2 Xk, Xm;
+    split_pair(z, z, tab<GT>(twN + M / 2), Xk, Xm);
+    const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
+    vmax = fmaxf(vmax, mk);
+    a.mag_out[row + M / 2] = mk;
+    if (EXTRA) {
+      if (a.cplx_out) a.cplx_out[row + M / 2] = Xk;
+      if (a.phase_out)
+        a.phase_out[row + M / 2] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
+    }
+  }
+  // padding columns [M+1, frame_pitch) are defined as zero
+  for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += 32) {
+    a.mag_out[row + k] = 0.f;
+    if (EXTRA) {
+      if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+      if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
+    }
+  }
+  vmax = warp_max(vmax);
+  if (lane == 0) {
+    if (a.frame_max_out) a.frame_max_out[(int64_t)clip * a.max_frames + t] = vmax;
+    if (a.clip_max_out) atomic_max_nonneg(a.clip_max_out + clip, vmax);
+  }
 }
 
 template <int M, int R0, int R1, int R2, int WARPS, bool EXTRA>
@@ -172,15 +261,6 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* buf = bufs + warp * BUF;
   const float2* win2 = reinterpret_cast<const float2*>(a.window);
-  // smem positions of Z[lane + 32 i] and of its partner Z[M - lane - 32 i] (digit-reversed order):
-  //   zpos is affine in i for a fixed lane, so both are base + i * step
-  const int zk0 = pidx(zpos<M, R0, R1, R2>(lane));
-  const int zk1 = pidx(zpos<M, R0, R1, R2>(lane + 32));
-  const int zm0 = pidx(zpos<M, R0, R1, R2>((M - lane) & (M - 1)));
-  const int zm1 = pidx(zpos<M, R0, R1, R2>(M - lane - 32));
-  const int zm2 = pidx(zpos<M, R0, R1, R2>(M - lane - 64));
-  const int zk_step = zk1 - zk0, zm_step = zm2 - zm1;
-
   for (int f = warp; f < nF; f += WARPS) {
     const float* xs = span + f * a.hop;
     constexpr int L1 = M / R0, L2 = L1 / R1;
@@ -188,73 +268,7 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
     dif_pass<M, L1, R1, false, (R2 == 1)>(buf, nullptr, nullptr, a.tw1, lane);
     if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true>(buf, nullptr, nullptr, nullptr, lane);
 
-    // ---- real-FFT split, |X|, outputs -----------------------------------
-    const int64_t t = t0 + f;
-    const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
-    float* mag_up = a.mag_out + row + lane;           // bins lane + 32 i
-    float* mag_dn = a.mag_out + row + (M - lane);     // bins M - lane - 32 i
-    const float2* twp = a.twN + lane;
-    float vmax = 0.f;
-    constexpr int ITERS = M / 64;                     // k = lane + 32 i < M/2
-#pragma unroll 8
-    for (int i = 0; i < ITERS; ++i) {
-      float2 zk, zm;
-      if constexpr (R2 == 1) {      // two-pass shapes: both positions are affine in i
-        zk = buf[zk0 + i * zk_step];
-        zm = buf[i == 0 ? zm0 : zm1 + (i - 1) * zm_step];
-      } else {
-        const int k = lane + 32 * i;
-        zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
-        zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
-      }
-      float2 Xk, Xm;
-      split_pair(zk, zm, __ldg(twp + 32 * i), Xk, Xm);
-      const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
-      const float mm = fast_sqrt(fmaf(Xm.x, Xm.x, Xm.y * Xm.y));
-      vmax = fmaxf(vmax, fmaxf(mk, mm));
-      mag_up[32 * i] = mk;
-      mag_dn[-32 * i] = mm;
-      if (EXTRA) {
-        const int k = lane + 32 * i;
-        if (a.cplx_out) {
-          float2* c = a.cplx_out + row;
-          c[k] = Xk;
-          c[M - k] = Xm;
-        }
-        if (a.phase_out) {
-          float2* p = a.phase_out + row;
-          p[k] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
-          p[M - k] = mm > 0.f ? make_float2(Xm.x / mm, Xm.y / mm) : make_float2(1.f, 0.f);
-        }
-      }
-    }
-    if (lane == 0) {
-      // k = M/2 pairs with itself
-      const float2 z = buf[pidx(zpos<M, R0, R1, R2>(M / 2))];
-      float2 Xk, Xm;
-      split_pair(z, z, __ldg(a.twN + M / 2), Xk, Xm);
-      const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
-      vmax = fmaxf(vmax, mk);
-      a.mag_out[row + M / 2] = mk;
-      if (EXTRA) {
-        if (a.cplx_out) a.cplx_out[row + M / 2] = Xk;
-        if (a.phase_out)
-          a.phase_out[row + M / 2] = mk > 0.f ? make_float2(Xk.x / mk, Xk.y / mk) : make_float2(1.f, 0.f);
-      }
-    }
-    // padding columns [M+1, frame_pitch) are defined as zero
-    for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += 32) {
-      a.mag_out[row + k] = 0.f;
-      if (EXTRA) {
-        if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
-        if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
-      }
-    }
-    vmax = warp_max(vmax);
-    if (lane == 0) {
-      if (a.frame_max_out) a.frame_max_out[(int64_t)clip * a.max_frames + t] = vmax;
-      if (a.clip_max_out) atomic_max_nonneg(a.clip_max_out + clip, vmax);
-    }
+    stft_frame_out<M, R0, R1, R2, EXTRA, true>(buf, a.twN, a, clip, t0 + f, lane);
     __syncwarp();
   }
 }
