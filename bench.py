@@ -276,15 +276,22 @@ def run_saga(args):
         "cqt_cascade": {"ms": stage_ms.get("cqt_cascade"), "bound": "hbm", "GBps": casc_bytes / stage_ms["cqt_cascade"] / 1e6},
         "cqt_contract": {"ms": stage_ms.get("cqt_contract"), "bound": "tensor",
                          "TFLOPs_algorithmic": cqt_flops / stage_ms["cqt_contract"] / 1e9,
-                         "TFLOPs_issued_tf32": cqt_flops * (96.0 / 24.0) / stage_ms["cqt_contract"] / 1e9},
+                         # per 24 useful columns the kernel issues one N=48 ([hi|lo] bank) and one N=32 MMA
+                         "TFLOPs_issued_tf32": cqt_flops * (80.0 / 24.0) / stage_ms["cqt_contract"] / 1e9},
     }
-    for k, v in stages.items():
-        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs_algorithmic"] / tpeak)
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    kernels = {"stft": "stft_kernel<1024,32,32,1,8> (K1, window batch)", "stft_guess": "stft_kernel<1024,32,32,1,8> (K1, guess batch)",
+               "subtract_db": "subtract_chain_kernel + window_db_kernel (K3)",
+               "cqt_cascade": "decimate2_kernel x 7 levels + cqt_pad_kernel (K2a)",
+               "cqt_contract": "cqt_umma_kernel (tcgen05) + cqt_tail_kernel (K2b)"}
+    for k, v in stages.items():
+        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs_algorithmic"] / tpeak)
+        v["kernel"] = kernels.get(k, k)
+        v["traffic"] = traffic.get(k, {}).get("bytes")     # ncu DRAM bytes per launch (profiles/traffic.json)
     dom = max(stage_ms, key=stage_ms.get)
     tr = traffic.get(dom, {}).get("bytes")
     if stages[dom]["bound"] == "tensor":
@@ -292,11 +299,11 @@ def run_saga(args):
                 "achieved": stages[dom]["TFLOPs_algorithmic"], "peak": tpeak, "unit": "TFLOP/s",
                 "frac": stages[dom]["frac"], "traffic": tr,
                 "peak_source": "cuBLAS bf16 sustained, " + peak_src,
-                "note": "algorithmic flops = 172704/frame (SURVEY 8d); the 3xTF32 split issues 4x that (N=64 main + N=32 correction MMA per 24 useful columns); "
-                        "tcgen05 dispatch floor for N<=64 is 44-48 cycles/MMA (profiles/microbench)"}
+                "note": "algorithmic flops = 172704/frame (SURVEY 8d); the 3xTF32 split issues 3.33x that (N=48 main + N=32 correction MMA per 24 useful columns); "
+                        "an SS-mode tcgen05.mma is paced by the SMEM bytes it reads: 44-48 cycles for N<=64 (profiles/microbench)"}
     else:
         ach = stages[dom]["GBps"]
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+        roof = {"kernel": kernels.get(dom, dom), "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": tr, "peak_source": peak_src}
 
     cpu = None
