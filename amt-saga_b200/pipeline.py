@@ -63,6 +63,7 @@ class WindowFeaturePipeline:
         # host side of the e2e path (pinned), allocated on demand
         self._host = None
         self._streams = None
+        self._cqt_stream = None
 
     # algorithmic work per window (DESIGN.md / SURVEY.md section 8d)
     def stft_bytes_per_window(self):
@@ -74,17 +75,36 @@ class WindowFeaturePipeline:
     def cqt_flops_per_window(self):
         return self.Tc * sum(8 * o["n_filters"] * (o["n_fft"] // 2 + 1) for o in self.cqt.octaves)
 
-    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None):
+    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None, overlap=True):
         """wav [W, window_samples], guess_wav [W, guess_samples] CUDA float32 contiguous,
         offset_frames [W,1] int32 CUDA.  Results land in self.mag (subtracted,
         in place), self.D, self.C, self.ref.  `events`: optional list that
-        receives (stage, start_event, end_event) on the current stream.
-        `w0:w1` restricts the pass to that window range (chunked / overlapped use)."""
+        receives (stage, start_event, end_event) on the current stream (stages then run
+        one after the other).  `w0:w1` restricts the pass to that window range (chunked use).
+
+        The path is two independent chains -- STFT(window) -> STFT(guess) -> subtract/dB, and
+        decimation cascade -> CQT contraction -- that only share the read-only audio.  With
+        `overlap` (and no per-stage timing) the CQT chain is forked onto a second stream and
+        joined at the end: the chains stress different resources (shared-memory/issue-bound
+        FFTs and an HBM-bound dB pass on one side, a 1-CTA/SM tensor-core kernel that leaves
+        most of the HBM bandwidth idle on the other), so the block scheduler interleaves them."""
         w1 = self.W if w1 is None else w1
         p = lambda t: C.c_void_p(t[w0:].data_ptr())
         q = lambda t: C.c_void_p(t.data_ptr())
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        main = torch.cuda.current_stream()
+        st = C.c_void_p(main.cuda_stream)
         lib, W = self._lib, w1 - w0
+        fork = overlap and events is None
+        if fork:
+            if self._cqt_stream is None:
+                self._cqt_stream = torch.cuda.Stream(device=self.dev)
+            side = self._cqt_stream
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            st_cqt = C.c_void_p(side.cuda_stream)
+        else:
+            st_cqt = st
 
         def stage(name, fn):
             if events is None:
@@ -101,9 +121,9 @@ class WindowFeaturePipeline:
         def cqt(flags):
             _lib.check(lib.saga_cqt_exec(
                 self.cqt.handle, p(wav), q(self.offs_w), None, W, self.ns, p(self.C), None,
-                self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl | flags, st))
+                self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl | flags, st_cqt))
         if events is None:
-            cqt(0)
+            cqt(0)          # on the side stream when forked (st_cqt)
         else:       # timed separately: decimation cascade, then the kernel-bank contraction
             stage("cqt_cascade", lambda: cqt(0x100))
             stage("cqt_contract", lambda: cqt(0x200))
@@ -115,6 +135,10 @@ class WindowFeaturePipeline:
             p(offset_frames), None, p(self.gmax), p(self.clip_max), p(self.frame_max), self.T_clip,
             _lib.SUB_NORMALIZE | _lib.SUB_RELU, p(self.D), p(self.ref), W, 1, self.nb, self.T, self.P,
             1e-5, 80.0, st)))
+        if fork:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     # ---- end-to-end: host buffers in, host results out -----------------------------
     def host_buffers(self):
