@@ -73,25 +73,51 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   }
 }
 
-// Factor-2 specialisation (the kaiser_fast 2:1 stage: 63 taps, S = 31).  The staged tile is split
-// into its even and odd samples (polyphase form): output o needs xe[o-15 .. o+15] and xo[o-16 .. o+15],
-// i.e. unit-stride windows, so a thread producing 4 consecutive outputs pulls two 9 x float4 register
-// windows at a 16-byte lane stride (bank-conflict free) and the kernel is FMA-bound rather than
-// one shared load per MAC.  Taps live in registers; symmetric pairs are pre-added.
+// Factor-2 specialisation (the kaiser_fast 2:1 stage: 63 taps, S = 31), written for the packed fp32
+// pipe of sm_100a.  View the input as pairs P_k = (x[2k], x[2k+1]); output o is
+//     y[o] = sum_{k=-16}^{15}  te_k * x[2(o+k)] + to_k * x[2(o+k)+1],   te_k = h[|2k|] (0 for k = -16),
+//                                                                        to_k = h[|2k+1|]
+// i.e. 32 FFMA2 on natural (lo, hi) register pairs plus one final add of the two halves -- 33 issue
+// slots per output instead of 63 scalar ones (31 symmetric pre-adds + 32 FFMA).  A thread produces
+// DEC2_GROUPS x 4 consecutive outputs, each group from one 35-pair register window; the (te, to) pairs
+// arrive by value (constant bank).  With fewer instructions per byte the kernel is bound by the bytes it
+// keeps in flight (one-shot CTAs: load, barrier, filter), so a CTA stages DEC2_GROUPS tiles at once.
 constexpr int DEC2_THREADS = 256;
-constexpr int DEC2_OUT = 4;                         // outputs per thread
+constexpr int DEC2_OUT = 4;                         // consecutive outputs per register window
+constexpr int DEC2_GROUPS = 2;                      // windows per thread (4: 0.63 ms, 2: 0.585 ms, 1: 0.70 ms per cascade)
 constexpr int DEC2_S = 31;
-constexpr int DEC2_TILE = DEC2_THREADS * DEC2_OUT;  // outputs per CTA
-constexpr int DEC2_HALF = DEC2_TILE + 32;           // even (or odd) samples staged per CTA
-struct Dec2Taps { float t[DEC2_S + 1]; };           // by value: lives in the constant bank, feeds FFMA directly
+constexpr int DEC2_SUB = DEC2_THREADS * DEC2_OUT;   // outputs per group
+constexpr int DEC2_TILE = DEC2_SUB * DEC2_GROUPS;   // outputs per CTA
+constexpr int DEC2_NIN = 2 * DEC2_TILE + 64;        // staged samples: [2*o0 - 32, 2*o0 + 2*TILE + 32)
+struct Dec2Taps { float t[DEC2_S + 1]; };           // h[0..31], centre first
+struct Dec2Pairs { float2 p[32]; };                 // (te_k, to_k), k = -16..15
+
+static Dec2Pairs dec2_pairs(const float* h) {
+  Dec2Pairs r;
+  for (int kk = 0; kk < 32; ++kk) {
+    const int k = kk - 16;
+    const int me = std::abs(2 * k), mo = std::abs(2 * k + 1);
+    r.p[kk] = make_float2(me <= DEC2_S ? h[me] : 0.f, h[mo]);
+  }
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 __global__ void __launch_bounds__(DEC2_THREADS)
 decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
                  const int64_t* __restrict__ clip_lens, int64_t max_len, int in_shift, int in_factor_total,
-                 float* __restrict__ out, int64_t out_stride, const Dec2Taps taps) {
-  // tile covers input samples [2*o0 - 32, 2*o0 + 2*TILE + 32)
-  __shared__ __align__(16) float xe[DEC2_HALF + 4];
-  __shared__ __align__(16) float xo[DEC2_HALF + 4];
+                 float* __restrict__ out, int64_t out_stride, const Dec2Pairs taps) {
+  // staged tile split by pair parity: xa = pairs 0, 2, 4, ..., xb = pairs 1, 3, 5, ...  A thread's 35-pair
+  // window then is two unit-stride runs at a 16-byte lane stride: conflict-free 128-bit loads (the plain
+  // contiguous layout has a 32-byte lane stride = 2-way conflicts, which made the shared-memory pipe the
+  // bound: ncu r1 v7, 98.6 M wavefronts per 79 M outputs)
+  __shared__ __align__(16) float2 xa[DEC2_NIN / 4];
+  __shared__ __align__(16) float2 xb[DEC2_NIN / 4];
   const int clip = blockIdx.y;
   int64_t len = clip_lens ? clip_lens[clip] : max_len;   // NULL = equal-length batch
   if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;
@@ -101,52 +127,56 @@ decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_of
   if (o0 >= n_out) return;
   const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
   const int64_t i0 = 2 * o0 - 32;
-  constexpr int NIN = 2 * DEC2_HALF;
-  if (i0 >= 0 && i0 + NIN <= len && ((reinterpret_cast<uintptr_t>(x + i0) & 15) == 0)) {
+  if (i0 >= 0 && i0 + DEC2_NIN <= len && ((reinterpret_cast<uintptr_t>(x + i0) & 15) == 0)) {
     const float4* src = reinterpret_cast<const float4*>(x + i0);
-    for (int i = threadIdx.x; i < NIN / 4; i += DEC2_THREADS) {
+#pragma unroll
+    for (int i = threadIdx.x; i < DEC2_NIN / 4; i += DEC2_THREADS) {
       const float4 v = __ldg(src + i);
-      *reinterpret_cast<float2*>(xe + 2 * i) = make_float2(v.x, v.z);
-      *reinterpret_cast<float2*>(xo + 2 * i) = make_float2(v.y, v.w);
+      xa[i] = make_float2(v.x, v.y);
+      xb[i] = make_float2(v.z, v.w);
     }
   } else {
-    for (int i = threadIdx.x; i < NIN; i += DEC2_THREADS) {
+    for (int i = threadIdx.x; i < DEC2_NIN; i += DEC2_THREADS) {
       const int64_t s = i0 + i;
-      const float v = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
-      if (i & 1) xo[i >> 1] = v; else xe[i >> 1] = v;
+      const float v = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;      // zeros outside the signal (resampy)
+      float* dst = reinterpret_cast<float*>((i & 2) ? xb : xa);
+      dst[2 * (i >> 2) + (i & 1)] = v;
     }
   }
-  const float* tp = taps.t;
   __syncthreads();
-  // output lo = 4*tid + u has its centre at even index c = lo + 16
-  float we[36], wo[36];
-  const float4* es = reinterpret_cast<const float4*>(xe + 4 * threadIdx.x);
-  const float4* os = reinterpret_cast<const float4*>(xo + 4 * threadIdx.x);
-#pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    const float4 a = es[j], b = os[j];
-    we[4 * j] = a.x; we[4 * j + 1] = a.y; we[4 * j + 2] = a.z; we[4 * j + 3] = a.w;
-    wo[4 * j] = b.x; wo[4 * j + 1] = b.y; wo[4 * j + 2] = b.z; wo[4 * j + 3] = b.w;
-  }
-  float acc[DEC2_OUT];
-#pragma unroll
-  for (int u = 0; u < DEC2_OUT; ++u) {
-    const int c = u + 16;
-    float r = tp[0] * we[c];
-#pragma unroll
-    for (int j = 1; j <= 15; ++j) r = fmaf(tp[2 * j], we[c - j] + we[c + j], r);       // even taps m = +-2j
-#pragma unroll
-    for (int j = 0; j <= 15; ++j) r = fmaf(tp[2 * j + 1], wo[c + j] + wo[c - 1 - j], r);  // odd taps m = 2j+1, -(2j+1)
-    acc[u] = r;
-  }
   float* y = out + (int64_t)clip * out_stride;
-  const int64_t ob = o0 + 4 * (int64_t)threadIdx.x;
-  if (ob + 3 < n_full && ((reinterpret_cast<uintptr_t>(y + ob) & 15) == 0)) {
-    *reinterpret_cast<float4*>(y + ob) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  } else {
 #pragma unroll
-    for (int u = 0; u < DEC2_OUT; ++u)
-      if (ob + u < n_out) y[ob + u] = (ob + u < n_full) ? acc[u] : 0.f;
+  for (int grp = 0; grp < DEC2_GROUPS; ++grp) {
+    // output lo = grp*SUB + 4*tid + u reads pairs lo + kk, kk = 0..31, of the staged tile
+    const int p0 = grp * DEC2_SUB + 4 * threadIdx.x;          // first pair of the window (multiple of 4)
+    unsigned long long w[36];
+    const ulonglong2* wa = reinterpret_cast<const ulonglong2*>(xa + (p0 >> 1));
+    const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(xb + (p0 >> 1));
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const ulonglong2 a = wa[j], b = wb[j];
+      w[4 * j] = a.x;          // pair p0 + 4j
+      w[4 * j + 1] = b.x;      //         + 4j + 1
+      w[4 * j + 2] = a.y;
+      w[4 * j + 3] = b.y;
+    }
+    float acc[DEC2_OUT];
+#pragma unroll
+    for (int u = 0; u < DEC2_OUT; ++u) {
+      unsigned long long r = 0ull;       // (+0.f, +0.f)
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk)
+        r = ffma2(w[u + kk], *reinterpret_cast<const unsigned long long*>(&taps.p[kk]), r);
+      acc[u] = __uint_as_float((unsigned)(r & 0xffffffffull)) + __uint_as_float((unsigned)(r >> 32));
+    }
+    const int64_t ob = o0 + p0;
+    if (ob + 3 < n_full && ((reinterpret_cast<uintptr_t>(y + ob) & 15) == 0)) {
+      *reinterpret_cast<float4*>(y + ob) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < DEC2_OUT; ++u)
+        if (ob + u < n_out) y[ob + u] = (ob + u < n_full) ? acc[u] : 0.f;
+    }
   }
 }
 
@@ -464,7 +494,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     if (p->early_factor == 2 && p->n_early_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
       decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
-                                                    pitch[0], *reinterpret_cast<const Dec2Taps*>(p->early_taps2));
+                                                    pitch[0], dec2_pairs(p->early_taps2));
     } else {
       decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
                                                        pitch[0], p->d_early_taps, p->n_early_taps, p->early_factor);
@@ -481,7 +511,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
       decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
                                                     from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
                                                     clip_lens, max_len, l - 1, p->early_factor, lvl[l] + pad[l], pitch[l],
-                                                    *reinterpret_cast<const Dec2Taps*>(p->half_taps2));
+                                                    dec2_pairs(p->half_taps2));
     } else {
       decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
                                                        from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
