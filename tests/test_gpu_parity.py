@@ -274,6 +274,31 @@ def test_cqt_tensor_path_equals_fp32_path_on_a_batch(saga, n):
     assert err <= 1e-5, err
 
 
+def test_cqt_tensor_path_without_shared_bank():
+    """Plans whose octave banks are not multiples of one another keep octave-major tiles and swap the
+    resident bank with a bulk copy per octave; force that path (the plan reads the switch at creation)."""
+    import subprocess, sys, os
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import amt_saga_b200
+from amt_saga_b200 import ops
+from amt_saga_b200.util_audio import note_to_hz
+from tests.synth import piano_clip
+plan = ops.CqtPlan(44100, 512, note_to_hz("C1"), 84, 12, filter_scale=2)
+wav = torch.as_tensor(np.stack([piano_clip(700 + i, 512 * 140 + 3) for i in range(12)]), device="cuda")
+ref = ops.cqt_batch(wav, plan, impl=1, fill=float("nan"))["mag"]
+got = ops.cqt_batch(wav, plan, impl=2, fill=float("nan"))["mag"]
+assert not torch.isnan(got).any()
+print("ERR", float((got - ref).abs().max() / ref.max()))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SAGA_UMMA_NO_SHARED_BANK="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    err = float(r.stdout.strip().split("ERR")[-1])
+    assert err <= 1e-5, err
+
+
 # --------------------------------------------------------------------------- class flow
 def test_audio_complete_loop_matches_oracle(saga):
     """The producer loop's call sequence (training.py:265-449) on both containers."""
