@@ -183,7 +183,11 @@ int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* plan, int n_clips, int64_t
  *       3 = tensor path with a single TF32 pass (measured 1.1e-4 of peak: NOT parity-grade)
  *       | SAGA_CQT_SKIP_CONTRACT: run only the decimation cascade (fills the workspace)
  *       | SAGA_CQT_SKIP_CASCADE:  run only the contraction on a workspace filled by an earlier call
- *       (the two flags let a caller time / overlap the phases separately) */
+ *       (the two flags let a caller time / overlap the phases separately; both calls must pass the same
+ *       impl, because the cascade phase of the tensor path also writes the reflect margins of the
+ *       per-level buffers in the workspace)
+ * The tensor path launches one short kernel on a plan-owned side stream, forked from and joined back
+ * into `stream` with per-call events: from the caller's point of view all work is ordered on `stream`. */
 int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
                   const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
                   void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
