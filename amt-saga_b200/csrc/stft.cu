@@ -516,7 +516,7 @@ static void stft_shape(int n_fft, int* radix, int* n_pass, int* warps) {
     case 128: radix[0] = 16; radix[1] = 8; break;
     case 256: radix[0] = 16; radix[1] = 16; break;
     case 512: radix[0] = 32; radix[1] = 16; break;
-    case 1024: radix[0] = 32; radix[1] = 32; break;
+    case 1024: radix[0] = 32; radix[1] = 32; *warps = 10; break;
     case 2048: radix[0] = 16; radix[1] = 16; radix[2] = 8; *n_pass = 3; *warps = 8; break;
     case 4096: radix[0] = 16; radix[1] = 16; radix[2] = 16; *n_pass = 3; *warps = 4; break;
     default: radix[0] = 0;
@@ -579,7 +579,7 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
 
   // frames per CTA: as many as fit a ~100 KB CTA (two CTAs per SM), at most 1 per warp
   const size_t buf_bytes = (size_t)warps * (M + M / 32) * sizeof(float2);
-  const size_t budget = (M <= 1024 ? 104 * 1024 : 200 * 1024);
+  const size_t budget = (M <= 1024 ? 112 * 1024 : 200 * 1024);
   int F = 1;
   if (budget > buf_bytes + (size_t)n_fft * 4) {
     const size_t span_floats = (budget - buf_bytes) / 4;
@@ -656,7 +656,7 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
     case 128: return launch_stft<128, 16, 8, 1, 8>(p, a, n_clips, st);
     case 256: return launch_stft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
-    case 1024: return launch_stft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
+    case 1024: return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
     case 2048: return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
     case 4096: return launch_stft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
   }
