@@ -14,8 +14,13 @@
 // memory, so a step only touches the guess's column range, and the window max
 // needed by the next step / by the dB floor is a block reduction, not a re-read.
 #include <algorithm>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "saga_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace saga {
 
@@ -194,6 +199,206 @@ __global__ void __launch_bounds__(SUB_THREADS) subtract_chain_kernel(const SubAr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Multi-step chains (n_steps >= 2, e.g. BASELINE cfg4: 16 guesses per window): a CLUSTER of 4 CTAs owns one
+// window (row t belongs to CTA t % 4, so any guess slab spreads evenly), 1 CTA per SM.  Only 37 windows
+// (78 MB) are then in flight on the chip, so a window stays L2-resident across its steps and the fused dB
+// epilogue reads it from L2 as well: DRAM sees each window once in, once out, plus the guesses -- the
+// algorithmic traffic of SURVEY 8(d) -- where one CTA per window with ~440 windows in flight re-reads and
+// re-writes every slab from HBM (cfg4, 4096 windows x 16 guesses: 22.1 ms; this kernel: 17.0 ms; an L2
+// prefetch of the next step's guess rows made it slower, 18.2 ms).  The per-step window maximum (the reference's ref_mag) is a
+// DSMEM exchange + cluster barrier; arithmetic and operation order per element are those of
+// subtract_chain_kernel (bit-exact against the numpy float32 replay).
+// ---------------------------------------------------------------------------
+constexpr int SUBC_CTAS = 4;
+constexpr int SUBC_THREADS = 512;      // 128 registers per thread: 16 outstanding 16-byte loads per lane
+constexpr int SUBC_UNR = 8;            // float4 per lane kept in flight per operand
+constexpr int SUBC_WARPS = SUBC_THREADS / 32;
+
+__device__ __forceinline__ float block_max_c(float v, float* red) {
+  v = warp_max(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < SUBC_WARPS; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+
+// cluster-wide max of one value per CTA: write it into slot [parity][rank] of every CTA, barrier, read back
+__device__ __forceinline__ float cluster_max(cg::cluster_group& cluster, float v, float (*xch)[SUBC_CTAS], int parity,
+                                             int rank) {
+  if (threadIdx.x < SUBC_CTAS) {
+    float* remote = cluster.map_shared_rank(&xch[parity][rank], threadIdx.x);
+    *remote = v;
+  }
+  cluster.sync();
+  float r = xch[parity][0];
+#pragma unroll
+  for (int i = 1; i < SUBC_CTAS; ++i) r = fmaxf(r, xch[parity][i]);
+  return r;
+}
+
+__global__ void __cluster_dims__(SUBC_CTAS, 1, 1) __launch_bounds__(SUBC_THREADS, 1)
+subtract_chain_cluster_kernel(const SubArgs a) {
+  extern __shared__ float fmax_s[];          // maxima of the rows this CTA owns: row t -> fmax_s[t / SUBC_CTAS]
+  __shared__ float red[SUBC_WARPS];
+  __shared__ float xch[2][SUBC_CTAS];
+  __shared__ float xch_g[2][SUBC_CTAS];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int w = blockIdx.x / SUBC_CTAS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t P = a.frame_pitch;
+  const int T = a.n_frames, B = a.n_bins;
+  const int n_own = (T - rank + SUBC_CTAS - 1) / SUBC_CTAS;           // rows rank, rank + 4, ...
+  float* win = a.win_mag + (a.win_offsets ? a.win_offsets[w] : (int64_t)w * a.win_stride);
+  const bool relu = (a.flags & SAGA_SUB_RELU) != 0;
+  const bool normalize = (a.flags & SAGA_SUB_NORMALIZE) != 0;
+
+  if (a.frame_max_in) {
+    for (int i = threadIdx.x; i < n_own; i += SUBC_THREADS)
+      fmax_s[i] = a.frame_max_in[(int64_t)w * a.frame_max_stride + rank + SUBC_CTAS * i];
+  } else {
+    for (int i = warp; i < n_own; i += SUBC_WARPS) {
+      const float m = row_max<true>(win + (int64_t)(rank + SUBC_CTAS * i) * P, B, lane);
+      if (lane == 0) fmax_s[i] = m;
+    }
+  }
+  cluster.sync();      // every CTA of the cluster is resident (its shared memory is addressable) from here on
+
+  int parity = 0;
+  for (int j = 0; j < a.n_steps; ++j) {
+    const int64_t idx = (int64_t)w * a.n_steps + j;
+    const float* g = a.guess_mag + (a.guess_offsets ? a.guess_offsets[idx] : idx * a.guess_stride);
+    const int Tg_full = a.guess_frames ? a.guess_frames[idx] : a.guess_frames_all;
+    const int off = a.offset_frames[idx];
+    // ---- ref of the current window and of the subtrahend (util_audio.py:239) ----
+    float ref, gref;
+    const bool need_ref = !(j == 0 && a.ref_init && a.ref_init[w] >= 0.f);
+    if (need_ref || !a.guess_ref) {
+      float m = 0.f, mg = 0.f;
+      if (need_ref)
+        for (int i = threadIdx.x; i < n_own; i += SUBC_THREADS) m = fmaxf(m, fmax_s[i]);
+      if (!a.guess_ref)
+        for (int tg = rank + SUBC_CTAS * warp; tg < Tg_full; tg += SUBC_CTAS * SUBC_WARPS)
+          mg = fmaxf(mg, row_max<true>(g + (int64_t)tg * P, B, lane));
+      m = block_max_c(m, red);
+      mg = block_max_c(mg, red);
+      if (threadIdx.x < SUBC_CTAS) *cluster.map_shared_rank(&xch_g[parity][rank], threadIdx.x) = mg;
+      ref = cluster_max(cluster, m, xch, parity, rank);
+      gref = xch_g[parity][0];
+#pragma unroll
+      for (int i = 1; i < SUBC_CTAS; ++i) gref = fmaxf(gref, xch_g[parity][i]);
+      parity ^= 1;
+    }
+    if (!need_ref) ref = a.ref_init[w];
+    if (a.guess_ref) gref = a.guess_ref[idx];
+    const float scale = normalize ? __fdiv_rn(ref, gref) : 1.0f;
+    const float ok = a.overkill ? a.overkill[idx] : 1.0f;
+    int Tg = Tg_full;
+    if (off < 0 || off >= T) Tg = 0;
+    else if (off + Tg > T) Tg = T - off;
+    // guess rows whose window row (off + tg) this CTA owns
+    const int tg0 = (((rank - off) % SUBC_CTAS) + SUBC_CTAS) % SUBC_CTAS;
+    for (int tg = tg0 + SUBC_CTAS * warp; tg < Tg; tg += SUBC_CTAS * SUBC_WARPS) {
+      float4* w4 = reinterpret_cast<float4*>(win + (int64_t)(off + tg) * P);
+      const float4* g4 = reinterpret_cast<const float4*>(g + (int64_t)tg * P);
+      float* wr = reinterpret_cast<float*>(w4);
+      const float* gr = reinterpret_cast<const float*>(g4);
+      float m = 0.f;
+      const int n4 = B >> 2;
+      // the CTA is alone on its SM: all loads of a row chunk are issued before the first use
+      for (int i0 = lane; i0 < n4; i0 += 32 * SUBC_UNR) {
+        float4 x[SUBC_UNR], y[SUBC_UNR];
+#pragma unroll
+        for (int u = 0; u < SUBC_UNR; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < n4) {
+            x[u] = w4[i];
+            y[u] = __ldcs(g4 + i);            // guesses are read once: do not let them evict the windows
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < SUBC_UNR; ++u) {
+          const int i = i0 + 32 * u;
+          if (i < n4) {
+            float4 v = x[u];
+            v.x = __fsub_rn(v.x, __fmul_rn(__fmul_rn(y[u].x, scale), ok));
+            v.y = __fsub_rn(v.y, __fmul_rn(__fmul_rn(y[u].y, scale), ok));
+            v.z = __fsub_rn(v.z, __fmul_rn(__fmul_rn(y[u].z, scale), ok));
+            v.w = __fsub_rn(v.w, __fmul_rn(__fmul_rn(y[u].w, scale), ok));
+            if (relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            w4[i] = v;
+          }
+        }
+      }
+      for (int k = (n4 << 2) + lane; k < B; k += 32) {
+        float x = __fsub_rn(wr[k], __fmul_rn(__fmul_rn(__ldg(gr + k), scale), ok));
+        if (relu) x = fmaxf(x, 0.f);
+        m = fmaxf(m, x);
+        wr[k] = x;
+      }
+      m = warp_max(m);
+      if (lane == 0) fmax_s[(off + tg) / SUBC_CTAS] = m;
+    }
+    __syncthreads();
+  }
+
+  // ---- final window max (== ref_mag after the chain) and the dB image of the owned rows ----
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n_own; i += SUBC_THREADS) m = fmaxf(m, fmax_s[i]);
+  m = block_max_c(m, red);
+  const float vmax = cluster_max(cluster, m, xch, parity, rank);
+  if (rank == 0 && threadIdx.x == 0) {
+    if (a.ref_out) a.ref_out[w] = vmax;
+    if (a.vmax_scratch) a.vmax_scratch[w] = vmax;
+  }
+  if (a.D_out) {
+    float* D = a.D_out + (a.win_offsets ? a.win_offsets[w] : (int64_t)w * a.win_stride);
+    const float amin2 = a.amin * a.amin;
+    const float ref_db = db_abs(vmax, amin2);
+    const float floor_db = (a.top_db >= 0.f) ? (0.0f - a.top_db) : -INFINITY;
+    const int Pq = (int)(P >> 2);
+    for (int i = warp; i < n_own; i += SUBC_WARPS) {
+      const int64_t t = rank + SUBC_CTAS * i;
+      const float4* w4 = reinterpret_cast<const float4*>(win + t * P);
+      float4* d4 = reinterpret_cast<float4*>(D + t * P);
+      for (int q0 = lane; q0 < Pq; q0 += 32 * SUBC_UNR) {
+        float4 x[SUBC_UNR];
+#pragma unroll
+        for (int u = 0; u < SUBC_UNR; ++u)
+          if (q0 + 32 * u < Pq) x[u] = w4[q0 + 32 * u];
+#pragma unroll
+        for (int u = 0; u < SUBC_UNR; ++u) {
+          const int q = q0 + 32 * u;
+          if (q < Pq) {
+            float4 d;
+            d.x = fmaxf(db_of(x[u].x, amin2, ref_db), floor_db);
+            d.y = fmaxf(db_of(x[u].y, amin2, ref_db), floor_db);
+            d.z = fmaxf(db_of(x[u].z, amin2, ref_db), floor_db);
+            d.w = fmaxf(db_of(x[u].w, amin2, ref_db), floor_db);
+            const int c = q << 2;                 // keep the padding columns at zero
+            if (c + 3 >= B) {
+              if (c >= B) d.x = 0.f;
+              if (c + 1 >= B) d.y = 0.f;
+              if (c + 2 >= B) d.z = 0.f;
+              if (c + 3 >= B) d.w = 0.f;
+            }
+            __stcs(d4 + q, d);
+          }
+        }
+      }
+    }
+  }
+  cluster.sync();      // no CTA of the cluster may exit while a peer can still address its shared memory
+}
+
 // dB epilogue as its own flat, perfectly balanced pass (a window per CTA leaves the last
 // wave nearly empty: 600 windows over 296 resident CTAs = 2.03 waves).
 //   D = 10 log10(max(amin^2, w^2)) - 10 log10(max(amin^2, ref^2)),  floor at max(D) - top_db,
@@ -325,6 +530,16 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   float* vmax = ref_out;
   if (D_out && !vmax) SAGA_CUDA_OK(cudaMallocAsync(&vmax, sizeof(float) * n_windows, st));
   a.vmax_scratch = (vmax != ref_out) ? vmax : nullptr;
+  const bool clustered = vec && n_steps >= 2 && !getenv("SAGA_SUB_NO_CLUSTER");
+  if (clustered) {
+    // >= 120 KB of dynamic shared memory per CTA keeps it alone on its SM: 37 windows in flight, L2-resident
+    const size_t csmem = std::max<size_t>(sizeof(float) * ((size_t)n_frames / SUBC_CTAS + 2), 120 * 1024);
+    SAGA_CUDA_OK(cudaFuncSetAttribute(subtract_chain_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    subtract_chain_cluster_kernel<<<(unsigned)n_windows * SUBC_CTAS, SUBC_THREADS, csmem, st>>>(a);
+    SAGA_LAUNCH_CHECK();
+    if (D_out && vmax != ref_out) SAGA_CUDA_OK(cudaFreeAsync(vmax, st));
+    return SAGA_OK;           // the dB image was written by the same kernel
+  }
   if (vec) {
     if (smem > 40 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(subtract_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
