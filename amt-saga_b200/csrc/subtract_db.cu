@@ -530,7 +530,9 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   float* vmax = ref_out;
   if (D_out && !vmax) SAGA_CUDA_OK(cudaMallocAsync(&vmax, sizeof(float) * n_windows, st));
   a.vmax_scratch = (vmax != ref_out) ? vmax : nullptr;
-  const bool clustered = vec && n_steps >= 2 && !getenv("SAGA_SUB_NO_CLUSTER");
+  int min_steps = 2;
+  if (const char* e = getenv("SAGA_SUB_CLUSTER_MIN_STEPS")) min_steps = atoi(e);       // tuning aid
+  const bool clustered = vec && n_steps >= min_steps && n_steps >= 1 && !getenv("SAGA_SUB_NO_CLUSTER");
   if (clustered) {
     // >= 120 KB of dynamic shared memory per CTA keeps it alone on its SM: 37 windows in flight, L2-resident
     const size_t csmem = std::max<size_t>(sizeof(float) * ((size_t)n_frames / SUBC_CTAS + 2), 120 * 1024);
