@@ -192,6 +192,44 @@ def test_subtract_chain_bit_exact(saga, B, T, Tg, S):
         assert float(st[:, :, B:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("normalize,relu", [(True, True), (False, True), (True, False)])
+def test_subtract_cluster_kernel_equals_single_cta_kernel(saga, normalize, relu):
+    """Multi-step chains run on clusters of 4 CTAs per window; every optional input (ragged guess lengths,
+    caller-provided guess / initial reference levels, K1 frame maxima) must give bit-identical results to
+    the one-CTA-per-window kernel."""
+    import os
+    ops, _ = saga
+    rng = np.random.default_rng(5)
+    W, B, T, Tg, S = 9, 1025, 131, 40, 5
+    P = ops.frame_pitch(B)
+    win = torch.zeros((W, T, P), device="cuda")
+    win[:, :, :B] = dev(rng.random((W, T, B), dtype=np.float32) ** 3)
+    g = torch.zeros((W, S, Tg, P), device="cuda")
+    g[:, :, :, :B] = dev(rng.random((W, S, Tg, B), dtype=np.float32) ** 2)
+    offs = dev(rng.integers(-2, T + 3, size=(W, S)).astype(np.int32))
+    gframes = dev(rng.integers(1, Tg + 1, size=(W, S)).astype(np.int32))
+    gref = g.amax(dim=(2, 3)) * 1.25
+    ref_init = dev(np.where(rng.random(W) < 0.5, -1.0, 3.0).astype(np.float32))
+    fmax = win.amax(dim=2).contiguous()
+    out = {}
+    for mode in ("cluster", "single"):
+        if mode == "single":
+            os.environ["SAGA_SUB_NO_CLUSTER"] = "1"
+        try:
+            res = []
+            for kw in (dict(), dict(guess_ref=gref), dict(guess_frames=gframes, ref_init=ref_init),
+                       dict(frame_max=fmax, guess_ref=gref, guess_frames=gframes)):
+                st = win.clone()
+                D, ref = ops.subtract_db_batch(st, g, offs, B, normalize=normalize, relu=relu, **kw)
+                res.append((st.cpu().numpy(), D.cpu().numpy(), ref.cpu().numpy()))
+            out[mode] = res
+        finally:
+            os.environ.pop("SAGA_SUB_NO_CLUSTER", None)
+    for a, b in zip(out["cluster"], out["single"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_subtract_matches_oracle_class(saga):
     """audio_complete.subtract vs the oracle container, incl. the stale song-level
     ref_mag a `section` hands to its first subtraction (util_audio.py:323)."""
