@@ -1028,35 +1028,34 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
     SAGA_LAUNCH_CHECK();
   }
   const int grid = (int)std::min<int64_t>(a.total_items, st->num_sms > 0 ? st->num_sms : 148);
-  // short partial tiles: forked onto the side stream BEFORE the persistent kernel so that both are resident
-  // together; joined back afterwards.  Events are per call (a plan may be driven from several streams).
+  // short partial tiles: cqt_tail_kernel runs on the side stream, forked before and joined after the
+  // persistent kernel.  The persistent kernel is ENQUEUED FIRST: its 148 CTAs each need a whole SM's shared
+  // memory and 55 k registers, so tail CTAs that got there first (six fit per SM) would hold it back until
+  // they retire; the other way round the tail kernel fills the ~10 k registers per SM that are left over.
+  // Events are per call (a plan may be driven from several streams).
   const int rem = (int)(T_max % UM_TILE_M);
   const bool tails = a.tail_max > 0 && (lv.clip_lens || (rem > 0 && rem <= a.tail_max));
-  cudaEvent_t ev_join = nullptr;
-  if (tails) {
-    const unsigned n_items = (unsigned)a.n_oct * (unsigned)n_clips;
-    const unsigned tgrid = (n_items + UM_TAIL_WARPS - 1) / UM_TAIL_WARPS;
-    cudaEvent_t ev_fork = nullptr;
-    if (st->side && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess) {
-      cudaEventRecord(ev_fork, stream);
-      cudaStreamWaitEvent(st->side, ev_fork, 0);
-      cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, st->side>>>(a);
-      cudaEventRecord(ev_join, st->side);
-      cudaEventDestroy(ev_fork);
-    } else {
-      if (ev_fork) cudaEventDestroy(ev_fork);
-      ev_join = nullptr;
-      cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, stream>>>(a);
-    }
-    SAGA_LAUNCH_CHECK();
+  const unsigned n_items = (unsigned)a.n_oct * (unsigned)n_clips;
+  const unsigned tgrid = (n_items + UM_TAIL_WARPS - 1) / UM_TAIL_WARPS;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool forked = tails && st->side && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess;
+  if (forked) {
+    cudaEventRecord(ev_fork, stream);
+    cudaStreamWaitEvent(st->side, ev_fork, 0);
   }
   cqt_umma_kernel<<<grid, UM_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
-  if (ev_join) {
-    cudaStreamWaitEvent(stream, ev_join, 0);
-    cudaEventDestroy(ev_join);
+  if (tails) {
+    cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, forked ? st->side : stream>>>(a);
+    SAGA_LAUNCH_CHECK();
   }
+  if (forked) {
+    cudaEventRecord(ev_join, st->side);
+    cudaStreamWaitEvent(stream, ev_join, 0);
+  }
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (a.debug & 16) {
     // profiling aid only: synchronous read-back of the per-role cycle counters, mean over CTAs
     std::vector<long long> h((size_t)grid * UM_PROF_SLOTS);
