@@ -42,10 +42,20 @@ def guess_offsets(n_windows, seed=7):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+_BLAS_LIMIT = None
+
+
 def _cpu_window(args):
     """One window-feature on the CPU through the oracle (the reference's algorithm)."""
     seed, off = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    global _BLAS_LIMIT
+    if _BLAS_LIMIT is None:      # numpy is already imported: pin its BLAS / OpenMP pools to ONE thread per process,
+        try:                     # so that `cores` in the JSON line is the number of threads actually used
+            from threadpoolctl import threadpool_limits
+            _BLAS_LIMIT = threadpool_limits(limits=1)
+        except Exception:
+            _BLAS_LIMIT = False
     from oracle import cqt as ocqt, spectral as osp
     from tests.synth import piano_clip
     y = piano_clip(seed, WIN_SAMPLES)
@@ -66,14 +76,16 @@ def _cpu_window(args):
     return time.perf_counter() - t0, float(C.sum() + D.sum())
 
 
-def cpu_sample(n_windows, procs):
+def cpu_sample(n_windows, procs, pool=None):
     offs = guess_offsets(n_windows)[:, 0]
     jobs = [(50000 + i, int(offs[i])) for i in range(n_windows)]
     t0 = time.perf_counter()
-    if procs > 1:
+    if pool is not None:
+        pool.map(_cpu_window, jobs, chunksize=1)
+    elif procs > 1:
         import multiprocessing as mp
-        with mp.get_context("fork").Pool(procs) as pool:
-            pool.map(_cpu_window, jobs)
+        with mp.get_context("fork").Pool(procs) as p:
+            p.map(_cpu_window, jobs, chunksize=1)
     else:
         for j in jobs:
             _cpu_window(j)
@@ -85,18 +97,23 @@ def run_reference(args):
     if rank != 0:
         return
     os.environ["OMP_NUM_THREADS"] = "1"
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     per_step = procs                       # one window per worker per step
-    _cpu_window((1, 10))                   # import / table warm-up in the parent
-    for _ in range(args.warmup):
-        cpu_sample(min(per_step, 2 * procs), procs)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_sample(per_step, procs)
-    dt = time.perf_counter() - t0
+    _cpu_window((1, 10))                   # import / table warm-up in the parent (inherited by the forked workers)
+    # ONE pool for the whole run, like the reference's Pool(synth_worker_count) (training.py:623): worker
+    # start-up is not part of a step
+    with mp.get_context("fork").Pool(procs) as pool:
+        for _ in range(max(args.warmup, 1)):
+            cpu_sample(per_step, procs, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_sample(per_step, procs, pool)
+        dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = "%d windows/step (1 per worker) x %d steps of the same 6 s window workload" % (per_step, args.steps)
+    sample = "%d windows/step (1 per worker, %d workers) x %d steps of the same 6 s window workload" % (
+        per_step, procs, args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "window-features/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
