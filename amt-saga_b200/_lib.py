@@ -30,13 +30,15 @@ class CqtDesc(C.Structure):
                 ("n_octaves", C.c_int), ("octaves", C.POINTER(CqtOctave))]
 
 
-_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); must list every symbol include/saga_b200.h declares
 SIGNATURES = {
     "saga_last_error_string": (C.c_char_p, []),
     "saga_abi_version": (_I, []),
     "saga_launch_count": (_L, []),
+    "saga_pcm16_absmax_exec": (_I, [_P, _L, _I, _I, _L, _P, _P]),
+    "saga_pcm16_ingest_exec": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _P, _P, _D, _D, _P]),
     "saga_stft_plan_create": (_I, [C.POINTER(_P), _I, _I, _I, _P]),
     "saga_stft_plan_destroy": (_I, [_P]),
     "saga_stft_num_frames": (_L, [_P, _L]),

@@ -310,6 +310,66 @@ def amplitude_to_db_batch(mag_storage, n_bins, ref=None, amin=1e-5, top_db=80.0)
     return D
 
 
+# ---------------------------------------------------------------------------
+# K0: PCM ingest
+# ---------------------------------------------------------------------------
+def pcm16_absmax(pcm, channel_stride=1, out=None):
+    """np.abs(pcm).max() per clip (int32 CUDA tensor) of int16 PCM [clips, samples*channel_stride];
+    channel_stride=2 looks at the left channel of interleaved stereo (util_audio.py:894 `[::2]`)."""
+    _require_cuda(pcm, "pcm")
+    if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.stride(1) != 1:
+        raise TypeError("pcm must be a [clips, samples] int16 CUDA tensor with contiguous rows")
+    n_clips, width = pcm.shape
+    n = (width + channel_stride - 1) // channel_stride
+    if out is None:
+        out = torch.empty((n_clips,), device=pcm.device, dtype=torch.int32)
+    if n_clips == 0:
+        return out
+    if n == 0:
+        return out.zero_()
+    _lib.check(_lib.lib().saga_pcm16_absmax_exec(_ptr(pcm), pcm.stride(0), channel_stride, n_clips, n,
+                                                 _ptr(out), _stream()))
+    return out
+
+
+def pcm16_to_wave(pcm, mul=1.0, div=32768.0, channel_stride=1, out=None):
+    """float32( (float64(pcm) * mul) / div ) per clip: the one scaling the reference applies to its PCM
+    (util_audio.py:776-781 for fluidsynth renders, soundfile's /32768 for files), bit-exact.
+    mul / div: python floats, or per-clip CUDA tensors (float64; div may also be the int32 tensor
+    pcm16_absmax returns, i.e. `/ np.abs(wf).max()`)."""
+    _require_cuda(pcm, "pcm")
+    if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.stride(1) != 1:
+        raise TypeError("pcm must be a [clips, samples] int16 CUDA tensor with contiguous rows")
+    n_clips, width = pcm.shape
+    n = (width + channel_stride - 1) // channel_stride
+    if out is None:
+        out = torch.empty((n_clips, n), device=pcm.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or out.shape != (n_clips, n) or out.stride(1) != 1:
+        raise ValueError("out must be float32 [clips, samples] with contiguous rows")
+    if n_clips == 0 or n == 0:
+        return out
+    mul_t = div_t = peak_t = None
+    mul_all = div_all = 1.0
+    if isinstance(mul, torch.Tensor):
+        mul_t = mul.to(device=pcm.device, dtype=torch.float64).contiguous()
+    else:
+        mul_all = float(mul)
+    if isinstance(div, torch.Tensor):
+        if div.dtype == torch.int32:
+            peak_t = div.to(device=pcm.device).contiguous()
+        else:
+            div_t = div.to(device=pcm.device, dtype=torch.float64).contiguous()
+    else:
+        div_all = float(div)
+    for t in (mul_t, div_t, peak_t):
+        if t is not None and t.shape != (n_clips,):
+            raise ValueError("per-clip scales must be [clips]")
+    _lib.check(_lib.lib().saga_pcm16_ingest_exec(_ptr(pcm), pcm.stride(0), channel_stride, _ptr(out), out.stride(0),
+                                                 n_clips, n, _ptr(mul_t), _ptr(div_t), _ptr(peak_t),
+                                                 mul_all, div_all, _stream()))
+    return out
+
+
 def launch_count():
     return int(_lib.lib().saga_launch_count())
 

@@ -155,15 +155,35 @@ class WindowFeaturePipeline:
                 d_offs=torch.empty((self.W, 1), device=self.dev, dtype=torch.int32))
         return self._host
 
-    def run_host(self, chunks=6):
+    def host_pcm_buffers(self):
+        """Extra buffers of the PCM-ingest variant of the e2e path: the windows and the rendered guesses
+        as int16 PCM plus the float64 factor of util_audio.py:781 per clip (pinned host + device)."""
+        h = self.host_buffers()
+        if "wav_pcm" not in h:
+            pin, d = dict(pin_memory=True), self.dev
+            h.update(
+                wav_pcm=torch.empty((self.W, self.ns), dtype=torch.int16, **pin),
+                guess_pcm=torch.empty((self.W, self.ng), dtype=torch.int16, **pin),
+                mul=torch.ones((2, self.W), dtype=torch.float64, **pin),
+                d_wav_pcm=torch.empty((self.W, self.ns), device=d, dtype=torch.int16),
+                d_guess_pcm=torch.empty((self.W, self.ng), device=d, dtype=torch.int16),
+                d_mul=torch.empty((2, self.W), device=d, dtype=torch.float64),
+                d_peak=torch.empty((2, self.W), device=d, dtype=torch.int32))
+        return h
+
+    def run_host(self, chunks=6, pcm16=False):
         """Pinned host inputs -> device -> hot path -> features back on the host
         (CQT magnitudes + post-subtraction ref_mag; the subtracted window and its dB
         image stay resident for the next loop iteration, as in training.py:449).
 
         The batch is cut into `chunks` window ranges; H2D copies, kernels and D2H
         copies run on three streams so PCIe transfers overlap the compute (the
-        path is PCIe-bound: 1.3 MB of audio in per window)."""
-        h = self.host_buffers()
+        path is PCIe-bound: 1.3 MB of audio in per window).
+
+        `pcm16`: the host holds the audio as 16-bit PCM (what fluidsynth and the audio files deliver,
+        util_audio.py:894 / :964) plus the per-clip float64 factor; K0 rebuilds the reference's float
+        waveform `pcm * mul / max|pcm|` (util_audio.py:781) on the device, which halves the PCIe bytes."""
+        h = self.host_pcm_buffers() if pcm16 else self.host_buffers()
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
             self._last_compute = None
@@ -178,9 +198,15 @@ class WindowFeaturePipeline:
         bounds = [(i * self.W // n, (i + 1) * self.W // n) for i in range(n)]
         ev_in, ev_cmp = [], []
         with torch.cuda.stream(s_in):
+            if pcm16:
+                h["d_mul"].copy_(h["mul"], non_blocking=True)
             for a, b in bounds:
-                h["d_wav"][a:b].copy_(h["wav"][a:b], non_blocking=True)
-                h["d_guess"][a:b].copy_(h["guess"][a:b], non_blocking=True)
+                if pcm16:
+                    h["d_wav_pcm"][a:b].copy_(h["wav_pcm"][a:b], non_blocking=True)
+                    h["d_guess_pcm"][a:b].copy_(h["guess_pcm"][a:b], non_blocking=True)
+                else:
+                    h["d_wav"][a:b].copy_(h["wav"][a:b], non_blocking=True)
+                    h["d_guess"][a:b].copy_(h["guess"][a:b], non_blocking=True)
                 h["d_offs"][a:b].copy_(h["offs"][a:b], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(s_in)
@@ -188,6 +214,10 @@ class WindowFeaturePipeline:
         with torch.cuda.stream(s_cmp):
             for (a, b), e in zip(bounds, ev_in):
                 s_cmp.wait_event(e)
+                if pcm16:
+                    for k, (src, dst) in enumerate((("d_wav_pcm", "d_wav"), ("d_guess_pcm", "d_guess"))):
+                        peak = ops.pcm16_absmax(h[src][a:b], out=h["d_peak"][k, a:b])
+                        ops.pcm16_to_wave(h[src][a:b], mul=h["d_mul"][k, a:b], div=peak, out=h[dst][a:b])
                 self.run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
                 e2 = torch.cuda.Event()
                 e2.record(s_cmp)
@@ -202,7 +232,9 @@ class WindowFeaturePipeline:
         cur.wait_event(done)
         cur.wait_event(ev_in[-1])
 
-    def h2d_bytes(self):
+    def h2d_bytes(self, pcm16=False):
+        if pcm16:
+            return self.W * (2 * (self.ns + self.ng) + 4 + 16)
         return 4 * self.W * (self.ns + self.ng + 1)
 
     def d2h_bytes(self):

@@ -116,6 +116,23 @@ class audio_complete:
         self.hl = hop_length if hop_length is not None else int(np.floor(n_fft / 4))
         self._fft_freq = np.linspace(0, float(sample_rate) / 2, int(1 + n_fft // 2), endpoint=True)
 
+    @classmethod
+    def from_pcm16(cls, pcm, n_fft, hop_length=None, center=True, sample_rate=44100, mul=1.0, div=32768.0,
+                   channel_stride=1, device=None, carrier="torch"):
+        """Container over 16-bit PCM scaled on the device (K0): waveform = float32((float64(pcm) * mul) / div),
+        the one scaling the reference applies to fluidsynth frames (`wf*(vel_max/128.0)**4/np.abs(wf).max()`,
+        util_audio.py:776-781; pass div='peak') or to a decoded file (`/ 32768`, util_audio.py:964).
+        channel_stride=2 keeps the left channel of interleaved stereo like util_audio.py:894 `[::2]`."""
+        dev = _device(device)
+        t = torch.as_tensor(np.asarray(pcm) if not isinstance(pcm, torch.Tensor) else pcm)
+        if t.dtype != torch.int16:
+            raise TypeError("from_pcm16 expects int16 samples")
+        t = t.reshape(1, -1).to(dev).contiguous()
+        if div == "peak":
+            div = ops.pcm16_absmax(t, channel_stride)
+        wave = ops.pcm16_to_wave(t, mul=mul, div=div, channel_stride=channel_stride)[0]
+        return cls(wave, n_fft, hop_length, center, sample_rate, device=dev, carrier=carrier)
+
     # ------------------------------------------------------------------ plumbing
     def _wave_in(self, w):
         if w is None:

@@ -42,6 +42,26 @@ int saga_abi_version(void);
 int64_t saga_launch_count(void);
 
 /* ------------------------------------------------------------------------
+ * K0  PCM ingest: 16-bit PCM -> the float32 waveform audio_complete analyses.
+ * The reference's waveforms are integer PCM scaled exactly once in float64:
+ *   util_audio.py:894   fluidsynth `get_samples(n)[::2]` (int16, left channel of interleaved stereo)
+ *   util_audio.py:776-781  `wf * (vel_max/128.0)**4 / np.abs(wf).max()`
+ *   util_audio.py:964   librosa.load / soundfile: int16 / 32768
+ * so the PCM itself can cross PCIe (half the bytes of float32) and
+ *   wav_out[c][i] = float32( (float64(pcm[c*in_clip_stride + i*in_stride]) * mul_c) / div_c )
+ * is the reference's number bit for bit.  mul_c = mul ? mul[c] : mul_all;
+ * div_c = peak_div ? (double)peak_div[c] : div ? div[c] : div_all  (mul, div, peak_div: device arrays).
+ * in_stride = 2 takes the left channel of an interleaved stereo stream (the reference's `[::2]`).
+ * saga_pcm16_absmax_exec writes np.abs(pcm).max() per clip (int32), ready to be passed as peak_div.
+ * ---------------------------------------------------------------------- */
+int saga_pcm16_absmax_exec(const int16_t* pcm, int64_t in_clip_stride, int in_stride, int n_clips,
+                           int64_t clip_len, int32_t* peak_out, void* stream);
+int saga_pcm16_ingest_exec(const int16_t* pcm, int64_t in_clip_stride, int in_stride, float* wav_out,
+                           int64_t out_clip_stride, int n_clips, int64_t clip_len, const double* mul,
+                           const double* div, const int32_t* peak_div, double mul_all, double div_all,
+                           void* stream);
+
+/* ------------------------------------------------------------------------
  * K1  batched windowed real FFT -> magnitude (/ unit phasor / complex)
  * replaces librosa.stft + magphase reached from
  *   util_audio.py:127-128 (F), :147 (mag, ph), :173 (ref_mag = max(mag))
