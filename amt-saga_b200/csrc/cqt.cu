@@ -14,6 +14,7 @@
 // validation path for the tcgen05 kernel in cqt_umma.cu).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "cqt_plan.cuh"
@@ -176,6 +177,120 @@ decimate2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_of
 #pragma unroll
       for (int u = 0; u < DEC2_OUT; ++u)
         if (ob + u < n_out) y[ob + u] = (ob + u < n_full) ? acc[u] : 0.f;
+    }
+  }
+}
+
+// Two cascade levels in one pass: level l -> l+1 -> l+2.  The level-(l+1) tile a CTA has just produced stays in
+// shared memory (same pair-parity layout) and feeds the second filter, so level l+1 is written once and never
+// read back from HBM (the cascade is bound by the bytes its one-shot CTAs keep in flight).
+// A CTA owns DEC2X2_OUT2 = 992 outputs of level l+2; they need level-(l+1) samples [2*o2 - 32, 2*o2 + 2016) --
+// exactly one 2048-output tile of the single-level kernel, computed by the same instruction sequence -- of which
+// the middle 1984 are this CTA's to store (the 32-sample halos belong to the neighbours: 3 % recompute).
+// Every output is produced by the same FFMA2 chain as in decimate2_kernel: results are bit-identical.
+constexpr int DEC2X2_OUT2 = DEC2_TILE / 2 - 32;       // 992
+static_assert(DEC2_GROUPS == 2 && DEC2X2_OUT2 % 4 == 0 && DEC2X2_OUT2 / 4 <= DEC2_THREADS, "fused tile shape");
+
+__device__ __forceinline__ void dec2_window(const float2* xa, const float2* xb, int p0, const Dec2Pairs& taps,
+                                            float (&acc)[DEC2_OUT]) {
+  unsigned long long w[36];
+  const ulonglong2* wa = reinterpret_cast<const ulonglong2*>(xa + (p0 >> 1));
+  const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(xb + (p0 >> 1));
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const ulonglong2 a = wa[j], b = wb[j];
+    w[4 * j] = a.x;
+    w[4 * j + 1] = b.x;
+    w[4 * j + 2] = a.y;
+    w[4 * j + 3] = b.y;
+  }
+#pragma unroll
+  for (int u = 0; u < DEC2_OUT; ++u) {
+    unsigned long long r = 0ull;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk)
+      r = ffma2(w[u + kk], *reinterpret_cast<const unsigned long long*>(&taps.p[kk]), r);
+    acc[u] = __uint_as_float((unsigned)(r & 0xffffffffull)) + __uint_as_float((unsigned)(r >> 32));
+  }
+}
+
+__global__ void __launch_bounds__(DEC2_THREADS)
+decimate2x2_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
+                   const int64_t* __restrict__ clip_lens, int64_t max_len, int in_shift, int in_factor_total,
+                   float* __restrict__ out1, int64_t out1_stride, float* __restrict__ out2, int64_t out2_stride,
+                   const Dec2Pairs taps1, const Dec2Pairs taps2) {
+  __shared__ __align__(16) float2 xa[DEC2_NIN / 4];
+  __shared__ __align__(16) float2 xb[DEC2_NIN / 4];
+  __shared__ __align__(16) float2 ya[DEC2_TILE / 4];     // level l+1 tile, even pairs
+  __shared__ __align__(16) float2 yb[DEC2_TILE / 4];     //                 odd pairs
+  const int clip = blockIdx.y;
+  int64_t len = clip_lens ? clip_lens[clip] : max_len;
+  if (in_factor_total > 1) len = (len + in_factor_total - 1) / in_factor_total;
+  for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;
+  const int64_t n_full1 = len >> 1, n_out1 = (len + 1) >> 1;
+  const int64_t n_full2 = n_out1 >> 1, n_out2 = (n_out1 + 1) >> 1;
+  const int64_t o2_0 = (int64_t)blockIdx.x * DEC2X2_OUT2;
+  if (o2_0 >= n_out2 && 2 * o2_0 >= n_out1) return;
+  const int64_t o0 = 2 * o2_0 - 32;                      // first level-(l+1) sample of the tile (may be < 0)
+  const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
+  const int64_t i0 = 2 * o0 - 32;
+  if (i0 >= 0 && i0 + DEC2_NIN <= len && ((reinterpret_cast<uintptr_t>(x + i0) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(x + i0);
+#pragma unroll
+    for (int i = threadIdx.x; i < DEC2_NIN / 4; i += DEC2_THREADS) {
+      const float4 v = __ldg(src + i);
+      xa[i] = make_float2(v.x, v.y);
+      xb[i] = make_float2(v.z, v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < DEC2_NIN; i += DEC2_THREADS) {
+      const int64_t s = i0 + i;
+      const float v = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+      float* dst = reinterpret_cast<float*>((i & 2) ? xb : xa);
+      dst[2 * (i >> 2) + (i & 1)] = v;
+    }
+  }
+  __syncthreads();
+  float* y1 = out1 + (int64_t)clip * out1_stride;
+#pragma unroll
+  for (int grp = 0; grp < DEC2_GROUPS; ++grp) {
+    const int p0 = grp * DEC2_SUB + 4 * threadIdx.x;
+    float acc[DEC2_OUT];
+    dec2_window(xa, xb, p0, taps1, acc);
+    const int64_t ob = o0 + p0;                          // multiple of 4 (possibly negative)
+    // the level as the next stage sees it: zero outside [0, n_full1) (resampy zero extension; the sample
+    // past floor(len/2) that librosa's fix-length appends is zero as well)
+#pragma unroll
+    for (int u = 0; u < DEC2_OUT; ++u)
+      if (ob + u < 0 || ob + u >= n_full1) acc[u] = 0.f;
+    ya[p0 >> 2] = make_float2(acc[0], acc[1]);
+    yb[p0 >> 2] = make_float2(acc[2], acc[3]);
+    const bool own = p0 >= 32 && p0 < DEC2_TILE - 32;     // the halo groups belong to the neighbouring CTAs
+    if (own && ob < n_out1) {
+      if (ob + 3 < n_out1 && ((reinterpret_cast<uintptr_t>(y1 + ob) & 15) == 0)) {
+        *reinterpret_cast<float4*>(y1 + ob) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < DEC2_OUT; ++u)
+          if (ob + u < n_out1) y1[ob + u] = acc[u];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < DEC2X2_OUT2 / 4) {
+    const int p0 = 4 * threadIdx.x;
+    const int64_t ob = o2_0 + p0;
+    if (ob < n_out2) {
+      float acc[DEC2_OUT];
+      dec2_window(ya, yb, p0, taps2, acc);
+      float* y2 = out2 + (int64_t)clip * out2_stride;
+      if (ob + 3 < n_full2 && ((reinterpret_cast<uintptr_t>(y2 + ob) & 15) == 0)) {
+        *reinterpret_cast<float4*>(y2 + ob) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < DEC2_OUT; ++u)
+          if (ob + u < n_out2) y2[ob + u] = (ob + u < n_full2) ? acc[u] : 0.f;
+      }
     }
   }
 }
@@ -484,14 +599,38 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
 
   // ---- decimation cascade ----------------------------------------------------------
   const int tile_out = DEC_THREADS * DEC_PER_THREAD;
-  if (do_cascade && p->early_factor > 1) {
+  // levels 1..max_level: 2:1 stages, fused two at a time (decimate2x2_kernel) when both are the 63-tap filter
+  const bool fuse = p->n_half_taps == DEC2_S + 1 && getenv("SAGA_DEC_NO_FUSE") == nullptr;
+  // Which pairs: bit i set = the pair whose FIRST output is level i is fused.  Default: pairs whose second output
+  // still has >= 8192 samples per clip -- for the short deep levels the fused kernel's smaller grid costs more in
+  // the overlapped step than the saved launch (profiles/microbench/cascade_fuse_b200.txt: 3.068 ms with the two
+  // large pairs fused, 3.099 none, 3.09-3.13 all three).  SAGA_DEC_FUSE_MASK overrides (tuning aid).
+  unsigned fuse_mask = 0;
+  for (int i = 0; i + 1 <= p->max_level; ++i)
+    if (level_len(max_len, p->early_factor, i + 1) >= 8192) fuse_mask |= 1u << i;
+  if (const char* e = getenv("SAGA_DEC_FUSE_MASK")) fuse_mask = (unsigned)strtoul(e, nullptr, 0);
+  int l = 1;
+  // the early stage itself can be the first half of a fused pair (early factor 2 with the same kind of filter)
+  const bool early_is_dec2 = do_cascade && p->early_factor == 2 && p->n_early_taps == DEC2_S + 1;
+  bool early_done = !(do_cascade && p->early_factor > 1);
+  if (early_is_dec2 && fuse && (fuse_mask & 1u) && p->max_level >= 1) {
+    const int64_t n_out2 = level_len(max_len, p->early_factor, 1);
+    dim3 g((unsigned)((n_out2 + DEC2X2_OUT2 - 1) / DEC2X2_OUT2), n_clips);
+    decimate2x2_kernel<<<g, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
+                                                   pitch[0], lvl[1] + pad[1], pitch[1], dec2_pairs(p->early_taps2),
+                                                   dec2_pairs(p->half_taps2));
+    SAGA_LAUNCH_CHECK();
+    early_done = true;
+    l = 2;
+  }
+  if (!early_done) {
     const int64_t n_out = level_len(max_len, p->early_factor, 0);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
     const size_t smem = sizeof(float) * (((p->n_early_taps + 3) & ~3) + tile_out * p->early_factor + 2 * (p->n_early_taps - 1));
     if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
     if (smem > 48 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (p->early_factor == 2 && p->n_early_taps == DEC2_S + 1) {
+    if (early_is_dec2) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
       decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
                                                     pitch[0], dec2_pairs(p->early_taps2));
@@ -501,22 +640,29 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     }
     SAGA_LAUNCH_CHECK();
   }
-  for (int l = 1; do_cascade && l <= p->max_level; ++l) {
+  for (; do_cascade && l <= p->max_level; ++l) {
     const int64_t n_out = level_len(max_len, p->early_factor, l);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
     const size_t smem = sizeof(float) * (((p->n_half_taps + 3) & ~3) + tile_out * 2 + 2 * (p->n_half_taps - 1));
     const bool from_wav = (l == 1 && p->early_factor == 1);
-    if (p->n_half_taps == DEC2_S + 1) {
+    const float* src = from_wav ? wav : lvl[l - 1] + pad[l - 1];
+    const int64_t* src_offs = from_wav ? clip_offsets : nullptr;
+    const int64_t src_stride = from_wav ? 0 : pitch[l - 1];
+    if (fuse && ((fuse_mask >> l) & 1u) && l + 1 <= p->max_level) {
+      const int64_t n_out2 = level_len(max_len, p->early_factor, l + 1);
+      dim3 g((unsigned)((n_out2 + DEC2X2_OUT2 - 1) / DEC2X2_OUT2), n_clips);
+      decimate2x2_kernel<<<g, DEC2_THREADS, 0, st>>>(src, src_offs, src_stride, clip_lens, max_len, l - 1, p->early_factor,
+                                                     lvl[l] + pad[l], pitch[l], lvl[l + 1] + pad[l + 1], pitch[l + 1],
+                                                     dec2_pairs(p->half_taps2), dec2_pairs(p->half_taps2));
+      ++l;
+    } else if (p->n_half_taps == DEC2_S + 1) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
-      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
-                                                    from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
-                                                    clip_lens, max_len, l - 1, p->early_factor, lvl[l] + pad[l], pitch[l],
-                                                    dec2_pairs(p->half_taps2));
+      decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(src, src_offs, src_stride, clip_lens, max_len, l - 1, p->early_factor,
+                                                    lvl[l] + pad[l], pitch[l], dec2_pairs(p->half_taps2));
     } else {
-      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(from_wav ? wav : lvl[l - 1] + pad[l - 1],
-                                                       from_wav ? clip_offsets : nullptr, from_wav ? 0 : pitch[l - 1],
-                                                       clip_lens, max_len, l - 1, p->early_factor, lvl[l] + pad[l],
-                                                       pitch[l], p->d_half_taps, p->n_half_taps, 2);
+      decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(src, src_offs, src_stride, clip_lens, max_len, l - 1,
+                                                       p->early_factor, lvl[l] + pad[l], pitch[l], p->d_half_taps,
+                                                       p->n_half_taps, 2);
     }
     SAGA_LAUNCH_CHECK();
   }

@@ -312,6 +312,44 @@ def test_cqt_tensor_path_equals_fp32_path_on_a_batch(saga, n):
     assert err <= 1e-5, err
 
 
+@pytest.mark.parametrize("sr,hop,low,n_bins,bpo", [(44100, 512, "C1", 84, 12), (16000, 512, "C1", 84, 12),
+                                                  (44100, 1024, "A0", 87, 12), (44100, 256, "C2", 60, 12)])
+def test_cqt_fused_cascade_is_bit_identical_to_level_by_level(saga, sr, hop, low, n_bins, bpo):
+    """decimate2x2_kernel (two cascade levels per launch, the intermediate level kept in shared memory) must
+    leave exactly the numbers of the level-by-level cascade: ragged lengths (odd, shorter than one tile,
+    longer than several), early factor 1 and 2, odd and even numbers of levels."""
+    import os
+    ops, _ = saga
+    plan = ops.CqtPlan(sr, hop, osp.note_to_hz(low), n_bins, bpo, filter_scale=2)
+    lens = [264600, 264599, 7937, 7938, 7939, 3968, 1985, 701, 133001, 100003]
+    wav = np.zeros((len(lens), max(lens)), dtype=np.float32)
+    for i, n in enumerate(lens):
+        wav[i, :n] = piano_clip(60 + i, n, sr=sr)
+    out = {}
+    for mode in ("fused", "default", "levels"):
+        if mode == "levels":
+            os.environ["SAGA_DEC_NO_FUSE"] = "1"
+        if mode == "fused":                       # every pair, also the short deep levels the default leaves alone
+            os.environ["SAGA_DEC_FUSE_MASK"] = "0xffff"
+        try:
+            res = []
+            for kw in (dict(lens=lens), dict()):                 # ragged and equal-length (clip_lens NULL) batches
+                for impl in (1, 0):
+                    r = ops.cqt_batch(dev(wav), plan, want_complex=True, impl=impl, fill=float("nan"), **kw)
+                    res.append((r["mag"].cpu().numpy(), r["C"].cpu().numpy()))
+            out[mode] = res
+        finally:
+            os.environ.pop("SAGA_DEC_NO_FUSE", None)
+            os.environ.pop("SAGA_DEC_FUSE_MASK", None)
+    for mode in ("fused", "default"):
+        for a, b in zip(out[mode], out["levels"]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y, equal_nan=True)
+    ref = np.abs(ocqt.cqt(wav[2, :lens[2]], sr=sr, hop_length=hop, fmin=osp.note_to_hz(low), n_bins=n_bins,
+                          bins_per_octave=bpo, filter_scale=2))
+    check_mag(out["fused"][0][0][2][:, :ref.shape[1]], ref)
+
+
 def test_cqt_tensor_path_without_shared_bank():
     """Plans whose octave banks are not multiples of one another keep octave-major tiles and swap the
     resident bank with a bulk copy per octave; force that path (the plan reads the switch at creation)."""

@@ -167,4 +167,4 @@ def test_run_host_pcm16_equals_float_path(saga):
         torch.cuda.synchronize()
         assert torch.equal(h["d_wav"].cpu(), torch.from_numpy(wf))
         assert torch.equal(h["C"], C0) and torch.equal(h["ref"], ref0)
-        assert torch.equal(pipe.mag, mag0) and torch.equal(pipe.D, D0)
+        assert torch.equal(pipe.mag, mag0) and torch.equal(pipe.D[:, :pipe.T], D0[:, :pipe.T])   # row T of D is never written
