@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libsaga_b200.so")
 
 SAGA_OK, SAGA_ERR_INVALID, SAGA_ERR_UNSUPPORTED, SAGA_ERR_CUDA, SAGA_ERR_NOMEM = 0, -1, -2, -3, -4
 SUB_NORMALIZE, SUB_RELU, SUB_OFFSETS_ALIGNED = 1, 2, 4
+SUB_SKIP_DB, SUB_ONLY_DB = 0x100, 0x200
 
 
 class SagaError(RuntimeError):

@@ -454,6 +454,169 @@ __global__ void __launch_bounds__(256) window_db_kernel(const float* __restrict_
   }
 }
 
+// Single-step subtraction as a flat pass (the producer loop's common case: one guessed note per window, K1 having
+// left the per-frame maxima and the guess maximum behind).  With one step there is no sequential dependence inside
+// a window, so the slab is cut into `chunks` row ranges per window -- 2400 small CTAs instead of 600 large ones
+// (1.35 waves) -- and every thread keeps SF_UNR window + SF_UNR guess 16-byte loads in flight.  Element arithmetic
+// is that of subtract_chain_kernel (bit-identical); the window's new maximum is assembled with atomicMax on the
+// bit patterns (ReLU output and magnitudes are >= 0), the untouched frames contributing their K1 maxima.
+constexpr int SF_THREADS = 256;
+constexpr int SF_UNR = 6;
+__global__ void __launch_bounds__(SF_THREADS) subtract_single_flat_kernel(const SubArgs a, float* __restrict__ vmax_out,
+                                                                          int chunks) {
+  __shared__ float red[SUB_WARPS];
+  const int w = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int64_t P = a.frame_pitch;
+  const int T = a.n_frames, B = a.n_bins;
+  float* win = a.win_mag + (a.win_offsets ? a.win_offsets[w] : (int64_t)w * a.win_stride);
+  const float* g = a.guess_mag + (a.guess_offsets ? a.guess_offsets[w] : (int64_t)w * a.guess_stride);
+  const float* fmax_in = a.frame_max_in + (int64_t)w * a.frame_max_stride;
+  const int Tg_full = a.guess_frames ? a.guess_frames[w] : a.guess_frames_all;
+  const int off = a.offset_frames[w];
+  const bool normalize = (a.flags & SAGA_SUB_NORMALIZE) != 0;
+  float ref = 0.f;
+  if (a.ref_init && a.ref_init[w] >= 0.f) {
+    ref = a.ref_init[w];
+  } else if (normalize) {
+    float m = 0.f;
+    for (int t = threadIdx.x; t < T; t += SF_THREADS) m = fmaxf(m, fmax_in[t]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    ref = red[0];
+#pragma unroll
+    for (int i = 1; i < SF_THREADS / 32; ++i) ref = fmaxf(ref, red[i]);
+    __syncthreads();
+  }
+  const float scale = normalize ? __fdiv_rn(ref, a.guess_ref[w]) : 1.0f;
+  const float ok = a.overkill ? a.overkill[w] : 1.0f;
+  int Tg = Tg_full;
+  if (off < 0 || off >= T) Tg = 0;
+  else if (off + Tg > T) Tg = T - off;
+
+  float m = 0.f;
+  // this CTA's share of the frames the subtraction does not touch
+  {
+    const int per = (T + chunks - 1) / chunks;
+    for (int t = chunk * per + threadIdx.x; t < min(T, (chunk + 1) * per); t += SF_THREADS)
+      if (t < off || t >= off + Tg) m = fmaxf(m, fmax_in[t]);
+  }
+  // this CTA's rows of the slab, as one flat run of 16-byte vectors (rows are whole pitches, hence contiguous)
+  const int rows = (Tg + chunks - 1) / chunks;
+  const int r0 = chunk * rows, r1 = min(Tg, r0 + rows);
+  if (r0 < r1) {
+    const int Pq = (int)(P >> 2);
+    float4* w4 = reinterpret_cast<float4*>(win + (int64_t)(off + r0) * P);
+    const float4* g4 = reinterpret_cast<const float4*>(g + (int64_t)r0 * P);
+    const int n4 = (r1 - r0) * Pq;
+    const int s1 = SF_THREADS % Pq, sk = (SF_THREADS * SF_UNR) % Pq;
+    int c0 = threadIdx.x % Pq;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += SF_THREADS * SF_UNR) {
+      float4 x[SF_UNR], y[SF_UNR];
+#pragma unroll
+      for (int u = 0; u < SF_UNR; ++u)
+        if (i0 + u * SF_THREADS < n4) {
+          x[u] = w4[i0 + u * SF_THREADS];
+          y[u] = __ldcs(g4 + i0 + u * SF_THREADS);
+        }
+      int cu = c0;
+#pragma unroll
+      for (int u = 0; u < SF_UNR; ++u) {
+        const int i = i0 + u * SF_THREADS;
+        if (i < n4) {
+          float4 v;
+          v.x = fmaxf(__fsub_rn(x[u].x, __fmul_rn(__fmul_rn(y[u].x, scale), ok)), 0.f);
+          v.y = fmaxf(__fsub_rn(x[u].y, __fmul_rn(__fmul_rn(y[u].y, scale), ok)), 0.f);
+          v.z = fmaxf(__fsub_rn(x[u].z, __fmul_rn(__fmul_rn(y[u].z, scale), ok)), 0.f);
+          v.w = fmaxf(__fsub_rn(x[u].w, __fmul_rn(__fmul_rn(y[u].w, scale), ok)), 0.f);
+          const int c = cu << 2;
+          if (c + 3 >= B) {                  // padding columns: neither changed nor counted
+            if (c >= B) v.x = x[u].x;
+            if (c + 1 >= B) v.y = x[u].y;
+            if (c + 2 >= B) v.z = x[u].z;
+            v.w = x[u].w;
+            m = fmaxf(m, fmaxf(c < B ? v.x : 0.f, fmaxf(c + 1 < B ? v.y : 0.f, c + 2 < B ? v.z : 0.f)));
+          } else {
+            m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+          }
+          w4[i] = v;
+        }
+        cu += s1;
+        if (cu >= Pq) cu -= Pq;
+      }
+      c0 += sk;
+      if (c0 >= Pq) c0 -= Pq;
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = red[0];
+#pragma unroll
+    for (int i = 1; i < SF_THREADS / 32; ++i) r = fmaxf(r, red[i]);
+    atomic_max_nonneg(vmax_out + w, r);
+  }
+}
+
+// The same pass with the bytes in flight coming from depth instead of occupancy: every thread keeps DBL_UNR 16-byte
+// loads outstanding.  Written to run beside the tensor-core CQT contraction (128 threads x 80 registers is what fits
+// next to its 768-thread CTA) -- that co-residency turned out to be worth nothing (the two kernels together take as
+// long as one after the other, profiles/microbench/db_umma_overlap_b200.txt), but the deep-load shape itself is
+// 20 % faster than the shallow kernel on an empty GPU, so it is the default.  Same arithmetic, same results.
+template <int DBL_THREADS, int DBL_UNR>
+__global__ void __launch_bounds__(DBL_THREADS) window_db_lean_kernel(const float* __restrict__ win_mag,
+                                                                      const int64_t* __restrict__ win_offsets,
+                                                                      int64_t win_stride, float* __restrict__ D_out,
+                                                                      const float* __restrict__ vmax_w, int n_bins,
+                                                                      int n_frames, int64_t P, float amin, float top_db,
+                                                                      int chunks_per_window) {
+  const int w = blockIdx.x / chunks_per_window, chunk = blockIdx.x % chunks_per_window;
+  const int64_t base = win_offsets ? win_offsets[w] : (int64_t)w * win_stride;
+  const float amin2 = amin * amin;
+  const float ref_db = db_abs(vmax_w[w], amin2);
+  const float floor_db = (top_db >= 0.f) ? (0.0f - top_db) : -INFINITY;
+  const int rows = (n_frames + chunks_per_window - 1) / chunks_per_window;
+  const int t0 = chunk * rows, t1 = min(n_frames, t0 + rows);
+  if (t0 >= t1) return;
+  const int Pq = (int)(P >> 2);
+  const float4* w4 = reinterpret_cast<const float4*>(win_mag + base + (int64_t)t0 * P);
+  float4* d4 = reinterpret_cast<float4*>(D_out + base + (int64_t)t0 * P);
+  const int n4 = (t1 - t0) * Pq;
+  const int s1 = DBL_THREADS % Pq, sk = (DBL_THREADS * DBL_UNR) % Pq;
+  int c0 = threadIdx.x % Pq;               // float4 column of the batch's first element, advanced incrementally
+  for (int i0 = threadIdx.x; i0 < n4; i0 += DBL_THREADS * DBL_UNR) {
+    float4 x[DBL_UNR];
+#pragma unroll
+    for (int u = 0; u < DBL_UNR; ++u)
+      if (i0 + u * DBL_THREADS < n4) x[u] = __ldcs(w4 + i0 + u * DBL_THREADS);
+    int cu = c0;
+#pragma unroll
+    for (int u = 0; u < DBL_UNR; ++u) {
+      const int i = i0 + u * DBL_THREADS;
+      if (i < n4) {
+        float4 d;
+        d.x = fmaxf(db_of(x[u].x, amin2, ref_db), floor_db);
+        d.y = fmaxf(db_of(x[u].y, amin2, ref_db), floor_db);
+        d.z = fmaxf(db_of(x[u].z, amin2, ref_db), floor_db);
+        d.w = fmaxf(db_of(x[u].w, amin2, ref_db), floor_db);
+        const int c = cu << 2;               // keep the padding columns at zero
+        if (c + 3 >= n_bins) {
+          if (c >= n_bins) d.x = 0.f;
+          if (c + 1 >= n_bins) d.y = 0.f;
+          if (c + 2 >= n_bins) d.z = 0.f;
+          d.w = 0.f;
+        }
+        __stcs(d4 + i, d);
+      }
+      cu += s1;
+      if (cu >= Pq) cu -= Pq;
+    }
+    c0 += sk;
+    if (c0 >= Pq) c0 -= Pq;
+  }
+}
+
 // ---- stand-alone amplitude_to_db -------------------------------------------------
 __global__ void clip_max_kernel(const float* mag, float* out, int n_bins, int n_frames,
                                 int64_t P, int64_t clip_stride, int rows_per_cta) {
@@ -507,6 +670,13 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   if (n_windows < 0 || n_steps < 0 || n_bins < 1 || n_frames < 0 || frame_pitch < n_bins)
     return set_error(SAGA_ERR_INVALID, "subtract_db_exec: bad shape");
   if (n_windows == 0 || n_frames == 0) return SAGA_OK;
+  // phase flags (as SAGA_CQT_SKIP_*): let a caller put the chain and the dB pass on different streams
+  const bool skip_db = (flags & SAGA_SUB_SKIP_DB) != 0, only_db = (flags & SAGA_SUB_ONLY_DB) != 0;
+  if (skip_db && only_db) return set_error(SAGA_ERR_INVALID, "subtract_db_exec: SKIP_DB and ONLY_DB together");
+  if (only_db && (!D_out || !ref_out))
+    return set_error(SAGA_ERR_INVALID, "subtract_db_exec: ONLY_DB needs D_out and the ref_out an earlier SKIP_DB call filled");
+  if (skip_db) D_out = nullptr;
+  flags &= 0xFF;
   SubArgs a;
   a.win_mag = win_mag; a.win_offsets = win_offsets; a.win_stride = win_stride;
   a.guess_mag = guess_mag; a.guess_offsets = guess_offsets; a.guess_stride = guess_stride;
@@ -532,7 +702,7 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   a.vmax_scratch = (vmax != ref_out) ? vmax : nullptr;
   int min_steps = 2;
   if (const char* e = getenv("SAGA_SUB_CLUSTER_MIN_STEPS")) min_steps = atoi(e);       // tuning aid
-  const bool clustered = vec && n_steps >= min_steps && n_steps >= 1 && !getenv("SAGA_SUB_NO_CLUSTER");
+  const bool clustered = vec && n_steps >= min_steps && n_steps >= 1 && !getenv("SAGA_SUB_NO_CLUSTER") && !skip_db && !only_db;
   if (clustered) {
     // >= 120 KB of dynamic shared memory per CTA keeps it alone on its SM: 37 windows in flight, L2-resident
     const size_t csmem = std::max<size_t>(sizeof(float) * ((size_t)n_frames / SUBC_CTAS + 2), 120 * 1024);
@@ -542,21 +712,44 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
     if (D_out && vmax != ref_out) SAGA_CUDA_OK(cudaFreeAsync(vmax, st));
     return SAGA_OK;           // the dB image was written by the same kernel
   }
-  if (vec) {
+  // one step, ReLU, K1's by-products at hand: the flat single-step kernel (values >= 0 make the atomic max valid)
+  const bool flat = vec && !only_db && n_steps == 1 && (flags & SAGA_SUB_RELU) && frame_max_in && guess_ref && vmax &&
+                    !getenv("SAGA_SUB_NO_FLAT");
+  if (only_db) {
+    // the chain ran in an earlier call (SAGA_SUB_SKIP_DB) and left every window's final max in ref_out
+  } else if (flat) {
+    SAGA_CUDA_OK(cudaMemsetAsync(vmax, 0, sizeof(float) * n_windows, st));
+    const int fchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, guess_frames_all), (148 * 16 + n_windows - 1) / n_windows));
+    subtract_single_flat_kernel<<<(unsigned)((int64_t)n_windows * fchunks), SF_THREADS, 0, st>>>(a, vmax, fchunks);
+    SAGA_LAUNCH_CHECK();
+  } else if (vec) {
     if (smem > 40 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(subtract_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     subtract_chain_kernel<true><<<n_windows, SUB_THREADS, smem, st>>>(a);
+    SAGA_LAUNCH_CHECK();
   } else {
     if (smem > 40 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(subtract_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     subtract_chain_kernel<false><<<n_windows, SUB_THREADS, smem, st>>>(a);
+    SAGA_LAUNCH_CHECK();
   }
-  SAGA_LAUNCH_CHECK();
   if (D_out) {
     // ~8 CTAs of 256 threads per SM in flight, whole chunks of rows per CTA
     int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames, (148 * 16 + n_windows - 1) / n_windows));
-    const int64_t blocks = (int64_t)n_windows * chunks;
-    if (vec)
+    // default: 256 threads x 12 outstanding 16-byte loads, ~32 CTAs of whole row chunks per SM slot (0.54 -> 0.42 ms for
+    // 600 windows = 6.05 TB/s, profiles/microbench/db_lean_sweep_b200.txt); SAGA_DB_LEAN=0 restores the shallow kernel
+    const char* lean = getenv("SAGA_DB_LEAN");
+    const int lv = lean ? atoi(lean) : 4;
+    if (vec && lv > 0) chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames, (148 * 32 + n_windows - 1) / n_windows));
+    if (const char* e = getenv("SAGA_DB_CHUNKS")) chunks = std::max(1, std::min(n_frames, atoi(e)));
+    const int64_t blocks = (int64_t)n_windows * chunks, lblocks = blocks;
+#define SAGA_DBL(T, U) window_db_lean_kernel<T, U><<<(unsigned)lblocks, T, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins, n_frames, frame_pitch, amin, top_db, chunks)
+    if (vec && lv == 1) SAGA_DBL(128, 12);
+    else if (vec && lv == 2) SAGA_DBL(128, 16);
+    else if (vec && lv == 3) SAGA_DBL(256, 8);
+    else if (vec && lv >= 4) SAGA_DBL(256, 12);
+#undef SAGA_DBL
+    else if (vec)
       window_db_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins,
                                                               n_frames, frame_pitch, amin, top_db, chunks);
     else

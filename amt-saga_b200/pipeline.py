@@ -64,6 +64,12 @@ class WindowFeaturePipeline:
         self._host = None
         self._streams = None
         self._cqt_stream = None
+        # "serial": one stream, kernel after kernel (default: fastest, 2.99 ms per bench step);
+        # "chains": the CQT chain forked onto a second stream (3.12 ms); "db_with_contraction": the contraction
+        # held back to run beside the dB pass (3.13 ms) -- profiles/microbench/schedule_variants_b200.txt.
+        # Every kernel of the step fills the GPU by itself, and the pairs that could share an SM (tensor-core
+        # contraction + dB pass) take as long together as one after the other (db_umma_overlap_b200.txt).
+        self.schedule = "serial"
 
     # algorithmic work per window (DESIGN.md / SURVEY.md section 8d)
     def stft_bytes_per_window(self):
@@ -83,18 +89,19 @@ class WindowFeaturePipeline:
         one after the other).  `w0:w1` restricts the pass to that window range (chunked use).
 
         The path is two independent chains -- STFT(window) -> STFT(guess) -> subtract/dB, and
-        decimation cascade -> CQT contraction -- that only share the read-only audio.  With
-        `overlap` (and no per-stage timing) the CQT chain is forked onto a second stream and
-        joined at the end: the chains stress different resources (shared-memory/issue-bound
-        FFTs and an HBM-bound dB pass on one side, a 1-CTA/SM tensor-core kernel that leaves
-        most of the HBM bandwidth idle on the other), so the block scheduler interleaves them."""
+        decimation cascade -> CQT contraction -- that only share the read-only audio.  `self.schedule`
+        picks how they are enqueued: "serial" (default) on the caller's stream one after the other;
+        "chains" / "db_with_contraction" fork the CQT chain onto a second stream (needs `overlap`
+        and no per-stage timing) and join it at the end.  Measured on B200 the forked schedules are
+        4 % slower: each kernel saturates the SMs' registers or shared memory on its own, so the block
+        scheduler time-slices whole SMs and the interleaving only adds tail effects and L2 thrash."""
         w1 = self.W if w1 is None else w1
         p = lambda t: C.c_void_p(t[w0:].data_ptr())
         q = lambda t: C.c_void_p(t.data_ptr())
         main = torch.cuda.current_stream()
         st = C.c_void_p(main.cuda_stream)
         lib, W = self._lib, w1 - w0
-        fork = overlap and events is None
+        fork = overlap and events is None and self.schedule != "serial"
         if fork:
             if self._cqt_stream is None:
                 self._cqt_stream = torch.cuda.Stream(device=self.dev)
@@ -122,19 +129,39 @@ class WindowFeaturePipeline:
             _lib.check(lib.saga_cqt_exec(
                 self.cqt.handle, p(wav), q(self.offs_w), None, W, self.ns, p(self.C), None,
                 self.Pc, self.Tc * self.Pc, q(self.ws), self.ws.numel(), self.cqt_impl | flags, st_cqt))
-        if events is None:
-            cqt(0)          # on the side stream when forked (st_cqt)
-        else:       # timed separately: decimation cascade, then the kernel-bank contraction
+        def guess_stft():
+            _lib.check(lib.saga_stft_exec(
+                self.stft.handle, p(guess_wav), q(self.offs_g), q(self.lens_g), W, self.ng, p(self.gmag), None,
+                None, self.P, self.Tg * self.P, None, p(self.gmax), st))
+
+        def subtract(phase):
+            _lib.check(lib.saga_subtract_db_exec(
+                p(self.mag), None, self.T_clip * self.P, p(self.gmag), None, self.Tg * self.P, None, self.Tg,
+                p(offset_frames), None, p(self.gmax), p(self.clip_max), p(self.frame_max), self.T_clip,
+                _lib.SUB_NORMALIZE | _lib.SUB_RELU | phase, p(self.D), p(self.ref), W, 1, self.nb, self.T, self.P,
+                1e-5, 80.0, st))
+
+        if events is not None:       # timed separately: decimation cascade, then the kernel-bank contraction
             stage("cqt_cascade", lambda: cqt(0x100))
             stage("cqt_contract", lambda: cqt(0x200))
-        stage("stft_guess", lambda: _lib.check(lib.saga_stft_exec(
-            self.stft.handle, p(guess_wav), q(self.offs_g), q(self.lens_g), W, self.ng, p(self.gmag), None,
-            None, self.P, self.Tg * self.P, None, p(self.gmax), st)))
-        stage("subtract_db", lambda: _lib.check(lib.saga_subtract_db_exec(
-            p(self.mag), None, self.T_clip * self.P, p(self.gmag), None, self.Tg * self.P, None, self.Tg,
-            p(offset_frames), None, p(self.gmax), p(self.clip_max), p(self.frame_max), self.T_clip,
-            _lib.SUB_NORMALIZE | _lib.SUB_RELU, p(self.D), p(self.ref), W, 1, self.nb, self.T, self.P,
-            1e-5, 80.0, st)))
+            stage("stft_guess", guess_stft)
+            stage("subtract_db", lambda: subtract(0))
+        elif fork and self.schedule == "db_with_contraction":
+            # cascade beside the two STFTs and the chain; then the tensor-core contraction (one 208 KB CTA per SM,
+            # 17 % of the DRAM bandwidth) beside the HBM-bound dB pass (no shared memory, 30 registers): the only
+            # two kernels of the step that fit on an SM together
+            cqt(0x100)
+            guess_stft()
+            subtract(_lib.SUB_SKIP_DB)
+            ev2 = torch.cuda.Event()
+            ev2.record(main)
+            side.wait_event(ev2)
+            cqt(0x200)
+            subtract(_lib.SUB_ONLY_DB)
+        else:
+            cqt(0)          # on the side stream when forked (st_cqt)
+            guess_stft()
+            subtract(0)
         if fork:
             ev = torch.cuda.Event()
             ev.record(side)

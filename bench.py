@@ -338,8 +338,8 @@ def run_saga(args):
     except Exception:
         pass
     kernels = {"stft": "stft_kernel<1024,32,32,1,10> (K1, window batch)", "stft_guess": "stft_kernel<1024,32,32,1,10> (K1, guess batch)",
-               "subtract_db": "subtract_chain_kernel + window_db_kernel (K3)",
-               "cqt_cascade": "decimate2_kernel x 7 levels + cqt_pad_kernel (K2a)",
+               "subtract_db": "subtract_single_flat_kernel + window_db_lean_kernel<256,12> (K3)",
+               "cqt_cascade": "decimate2x2_kernel x 2 + decimate2_kernel x 3 + cqt_pad_kernel (K2a)",
                "cqt_contract": "cqt_umma_kernel (tcgen05) + cqt_tail_kernel (K2b)"}
     for k, v in stages.items():
         v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs_algorithmic"] / tpeak)
@@ -373,8 +373,9 @@ def run_saga(args):
                    "frames_per_s": world * W * pipe.T / (ms_step * 1e-3),
                    "l2": "inputs 635 MB/step per GPU > 126 MB L2 (no flush needed)",
                    "parallelism": "window shards, 1 process/GPU, no collective on the path",
-                   "streams": "STFT->subtract/dB chain and cascade->CQT chain overlap on two streams in the timed loop; "
-                              "`stages` are timed in a separate serial pass (sum %.3f ms)" % sum(stage_ms.values()),
+                   "streams": "schedule=%s (kernels of a step enqueued on one stream; forking the CQT chain onto a second "
+                              "stream measured 4 %% slower); `stages` are timed in a separate pass with events between "
+                              "the kernels (sum %.3f ms)" % (pipe.schedule, sum(stage_ms.values())),
                    "cqt_impl": args.cqt_impl},
         "e2e": {"value": e2e_value, "unit": "window-features/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                 "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": e2e_steps,

@@ -119,6 +119,12 @@ int saga_istft_exec(const saga_stft_plan* plan, const void* cplx_in, const float
 #define SAGA_SUB_RELU 2
 /* caller guarantees every win/guess offset is a multiple of 4 elements (16-byte vector path) */
 #define SAGA_SUB_OFFSETS_ALIGNED 4
+/* phase flags: SKIP_DB runs only the chain (ref_out receives every window's final max, D_out is ignored);
+ * ONLY_DB runs only the dB pass over the windows as they are, with the ref_out such a call filled.
+ * Lets a caller order the two phases on different streams (pipeline.py overlaps the HBM-bound dB pass with
+ * the tensor-core CQT contraction). */
+#define SAGA_SUB_SKIP_DB 0x100
+#define SAGA_SUB_ONLY_DB 0x200
 
 int saga_subtract_db_exec(
     float* win_mag,                /* in/out: window w at win_mag + win_offsets[w] (or w*win_stride) */

@@ -192,6 +192,61 @@ def test_subtract_chain_bit_exact(saga, B, T, Tg, S):
         assert float(st[:, :, B:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B,T,Tg", [(1025, 516, 128), (2049, 258, 54), (129, 33, 40), (1025, 7, 3)])
+def test_subtract_single_step_flat_kernel_bit_exact(saga, B, T, Tg):
+    """One guessed note per window with K1's by-products at hand (the producer loop's case) runs on the flat
+    single-step kernel: bit-identical to the numpy replay, to the one-CTA-per-window chain kernel and to both dB
+    kernels, for offsets outside / at the edge of the window, ragged guess lengths, optional ref_init / overkill,
+    and garbage in the window's padding columns (neither changed nor counted)."""
+    import os
+    ops, _ = saga
+    rng = np.random.default_rng(B + T + Tg)
+    W = 11
+    P = ops.frame_pitch(B)
+    win = rng.random((W, B, T), dtype=np.float32) ** 4
+    gs = rng.random((W, 1, B, Tg), dtype=np.float32) ** 3
+    offs = rng.integers(0, T, size=(W, 1)).astype(np.int32)
+    offs[0, 0], offs[1, 0], offs[2, 0], offs[3, 0] = 0, T - 1, T + 5, -3
+    gframes = rng.integers(1, Tg + 1, size=(W, 1)).astype(np.int32)
+    ok = (1.0 + rng.random((W, 1))).astype(np.float32)
+    ref_init = np.where(rng.random(W) < 0.5, -1.0, 2.5).astype(np.float32)
+    st0 = torch.zeros((W, T, P), device="cuda")
+    st0[:, :, :B] = dev(win).transpose(1, 2)
+    st0[:, :, B:] = 7.0                                   # garbage where the layout says padding
+    g = torch.zeros((W, 1, Tg, P), device="cuda")
+    g[:, :, :, :B] = dev(gs).transpose(2, 3)
+    fmax = st0[:, :, :B].amax(dim=2).contiguous()
+    out = {}
+    for mode in ("flat", "chain", "shallow_db"):
+        env = {"chain": "SAGA_SUB_NO_FLAT", "shallow_db": "SAGA_DB_LEAN"}.get(mode)
+        if env:
+            os.environ[env] = "1" if mode == "chain" else "0"
+        try:
+            res = []
+            for kw in (dict(), dict(overkill=dev(ok)), dict(guess_frames=dev(gframes), ref_init=dev(ref_init))):
+                st = st0.clone()
+                gref = torch.stack([g[w, 0, :int(gframes[w, 0]) if "guess_frames" in kw else Tg].amax() for w in range(W)])
+                D, ref = ops.subtract_db_batch(st, g, dev(offs), B, frame_max=fmax, guess_ref=gref.reshape(W, 1), **kw)
+                res.append((st.cpu().numpy(), D[:, :, :B].cpu().numpy(), ref.cpu().numpy()))
+            out[mode] = res
+        finally:
+            if env:
+                os.environ.pop(env, None)
+    for mode in ("chain", "shallow_db"):
+        for a, b in zip(out["flat"], out[mode]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), mode
+    assert np.all(out["flat"][0][0][:, :, B:] == 7.0)
+    got = out["flat"][1][0][:, :, :B].transpose(0, 2, 1)
+    for w in range(W):
+        if 0 <= offs[w, 0] < T:
+            exp = _numpy_chain(win[w], gs[w], offs[w], ok[w])
+        else:
+            exp = win[w]
+        assert np.array_equal(got[w], exp)
+        assert float(out["flat"][1][2][w]) == float(exp.max())
+
+
 @pytest.mark.parametrize("normalize,relu", [(True, True), (False, True), (True, False)])
 def test_subtract_cluster_kernel_equals_single_cta_kernel(saga, normalize, relu):
     """Multi-step chains run on clusters of 4 CTAs per window; every optional input (ragged guess lengths,
