@@ -601,13 +601,11 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   const int tile_out = DEC_THREADS * DEC_PER_THREAD;
   // levels 1..max_level: 2:1 stages, fused two at a time (decimate2x2_kernel) when both are the 63-tap filter
   const bool fuse = p->n_half_taps == DEC2_S + 1 && getenv("SAGA_DEC_NO_FUSE") == nullptr;
-  // Which pairs: bit i set = the pair whose FIRST output is level i is fused.  Default: pairs whose second output
-  // still has >= 8192 samples per clip -- for the short deep levels the fused kernel's smaller grid costs more in
-  // the overlapped step than the saved launch (profiles/microbench/cascade_fuse_b200.txt: 3.068 ms with the two
-  // large pairs fused, 3.099 none, 3.09-3.13 all three).  SAGA_DEC_FUSE_MASK overrides (tuning aid).
-  unsigned fuse_mask = 0;
-  for (int i = 0; i + 1 <= p->max_level; ++i)
-    if (level_len(max_len, p->early_factor, i + 1) >= 8192) fuse_mask |= 1u << i;
+  // Which pairs: bit i set = the pair whose FIRST output is level i is fused.  Default: every pair (one stream, kernel
+  // after kernel: cascade 0.582 -> 0.516 ms, step 3.038 -> 2.971 ms; when the CQT chain ran beside the STFT chain on a
+  // second stream only the two large pairs paid -- profiles/microbench/cascade_fuse_b200.txt).  SAGA_DEC_FUSE_MASK
+  // overrides (tuning aid).
+  unsigned fuse_mask = ~0u;
   if (const char* e = getenv("SAGA_DEC_FUSE_MASK")) fuse_mask = (unsigned)strtoul(e, nullptr, 0);
   int l = 1;
   // the early stage itself can be the first half of a fused pair (early factor 2 with the same kind of filter)

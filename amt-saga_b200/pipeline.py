@@ -81,7 +81,7 @@ class WindowFeaturePipeline:
     def cqt_flops_per_window(self):
         return self.Tc * sum(8 * o["n_filters"] * (o["n_fft"] // 2 + 1) for o in self.cqt.octaves)
 
-    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None, overlap=True):
+    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None, overlap=True, parts=("stft", "cqt")):
         """wav [W, window_samples], guess_wav [W, guess_samples] CUDA float32 contiguous,
         offset_frames [W,1] int32 CUDA.  Results land in self.mag (subtracted,
         in place), self.D, self.C, self.ref.  `events`: optional list that
@@ -122,9 +122,10 @@ class WindowFeaturePipeline:
             b.record()
             events.append((name, a, b))
 
-        stage("stft", lambda: _lib.check(lib.saga_stft_exec(
-            self.stft.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.mag), None, None,
-            self.P, self.T_clip * self.P, p(self.frame_max), p(self.clip_max), st)))
+        if "stft" in parts:
+            stage("stft", lambda: _lib.check(lib.saga_stft_exec(
+                self.stft.handle, p(wav), q(self.offs_w), q(self.lens_w), W, self.ns, p(self.mag), None, None,
+                self.P, self.T_clip * self.P, p(self.frame_max), p(self.clip_max), st)))
         def cqt(flags):
             _lib.check(lib.saga_cqt_exec(
                 self.cqt.handle, p(wav), q(self.offs_w), None, W, self.ns, p(self.C), None,
@@ -159,9 +160,11 @@ class WindowFeaturePipeline:
             cqt(0x200)
             subtract(_lib.SUB_ONLY_DB)
         else:
-            cqt(0)          # on the side stream when forked (st_cqt)
-            guess_stft()
-            subtract(0)
+            if "cqt" in parts:
+                cqt(0)          # on the side stream when forked (st_cqt)
+            if "stft" in parts:
+                guess_stft()
+                subtract(0)
         if fork:
             ev = torch.cuda.Event()
             ev.record(side)
