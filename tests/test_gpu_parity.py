@@ -616,6 +616,36 @@ def test_full_size_properties_one_hour(saga):
     assert float(d[:, 100:228].max()) > 0.0
 
 
+def test_pipeline_schedules_and_phase_flags_give_identical_results(saga):
+    """The step's kernels can be enqueued on one stream ("serial", default), with the CQT chain forked onto a second
+    stream ("chains"), or with the contraction held back beside the dB pass ("db_with_contraction", which uses the
+    SAGA_SUB_SKIP_DB / SAGA_SUB_ONLY_DB phase flags of K3): all bit-identical, also when run chunk by chunk."""
+    from amt_saga_b200.pipeline import WindowFeaturePipeline
+    W, ns, ng = 9, 44100, 16384
+    pipe = WindowFeaturePipeline(W, ns, ng)
+    wav = dev(np.stack([piano_clip(300 + i, ns, n_notes=5) for i in range(W)]))
+    gue = dev(np.stack([piano_clip(400 + i, ng, n_notes=1) for i in range(W)]))
+    offs = dev((np.arange(W, dtype=np.int32) * 11 % 80).reshape(-1, 1))
+    ref = None
+    for sched in ("serial", "chains", "db_with_contraction", "serial-chunks"):
+        pipe.schedule = sched.split("-")[0]
+        for t in (pipe.mag, pipe.D, pipe.C, pipe.ref):
+            t.fill_(float("nan"))
+        if sched.endswith("chunks"):
+            pipe.run(wav, gue, offs, parts=("cqt",))
+            for a in range(0, W, 4):
+                pipe.run(wav, gue, offs, w0=a, w1=min(W, a + 4), parts=("stft",))
+        else:
+            pipe.run(wav, gue, offs)
+        torch.cuda.synchronize()
+        out = [pipe.mag.clone(), pipe.D[:, :pipe.T].clone(), pipe.C.clone(), pipe.ref.clone()]
+        assert not any(torch.isnan(t).any() for t in out)
+        if ref is None:
+            ref = out
+        for x, y in zip(out, ref):
+            assert torch.equal(x, y), sched
+
+
 def test_run_host_chunked_equals_resident_run(saga):
     """The overlapped host path (chunks on three streams) returns exactly what the
     resident single-shot pass computes."""
