@@ -66,18 +66,29 @@ __device__ __forceinline__ float2 tab(const float2* p) {
   return *p;
 }
 
+// LANES threads work on one frame: a warp, or -- for the long transforms, whose 17 / 34 KB exchange buffers allow
+// only a handful of frames per SM -- 2 or 4 warps that meet at a named barrier (id = 1 + frame slot of the CTA).
+template <int LANES>
+__device__ __forceinline__ void group_sync(int group) {
+  if constexpr (LANES == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(LANES) : "memory");
+  }
+}
+
 // One DIF pass over blocks of length L with radix R, in place in `buf`.
 // FIRST reads the windowed real samples instead of buf.
-template <int M, int L, int R, bool FIRST, bool LAST, bool GT = true>
+template <int M, int L, int R, bool FIRST, bool LAST, bool GT = true, int LANES = 32>
 __device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const float2* __restrict__ win2,
-                                         const float2* __restrict__ tw, int lane) {
+                                         const float2* __restrict__ tw, int lane, int group = 0) {
   constexpr int LS = L / R;       // sub-block length after this pass
   constexpr int ITEMS = M / R;    // small FFTs in this pass
-  constexpr int ITERS = (ITEMS + 31) / 32;
+  constexpr int ITERS = (ITEMS + LANES - 1) / LANES;
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
-    const int q = lane + 32 * it;
-    if ((ITEMS % 32) != 0 && q >= ITEMS) break;
+    const int q = lane + LANES * it;
+    if ((ITEMS % LANES) != 0 && q >= ITEMS) break;
     const int b = q / LS, j = q % LS;
     const int base = b * L + j;
     float2 v[R];
@@ -108,7 +119,7 @@ __device__ __forceinline__ void dif_pass(float2* buf, const float* xs, const flo
       buf[pidx(base + rp * LS)] = o;
     }
   }
-  __syncwarp();
+  group_sync<LANES>(group);
 }
 
 // position of Z[k] in buf after the digit-reversing in-place passes
@@ -140,9 +151,10 @@ __device__ __forceinline__ void split_pair(float2 zk, float2 zm, float2 w, float
 
 // Real-FFT split of one transformed frame (Z in `buf`, digit-reversed order) -> |X| (+ phasor / complex),
 // coalesced rows of the frame-major output, per-frame and per-clip maxima.
-template <int M, int R0, int R1, int R2, bool EXTRA, bool GT>
+template <int M, int R0, int R1, int R2, bool EXTRA, bool GT, int LANES = 32>
 __device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* twN, const StftArgs& a, int clip,
-                                               int64_t t, int lane) {
+                                               int64_t t, int lane, int group = 0, float* gmax = nullptr) {
+  static_assert(LANES == 32 || R2 > 1, "multi-warp frames use the generic position map");
   // smem positions of Z[lane + 32 i] and of its partner Z[M - lane - 32 i] (digit-reversed order):
   //   zpos is affine in i for a fixed lane, so both are base + i * step
   const int zk0 = pidx(zpos<M, R0, R1, R2>(lane));
@@ -153,11 +165,11 @@ __device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* 
   const int zk_step = zk1 - zk0, zm_step = zm2 - zm1;
   // ---- real-FFT split, |X|, outputs -----------------------------------
     const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
-  float* mag_up = a.mag_out + row + lane;           // bins lane + 32 i
-  float* mag_dn = a.mag_out + row + (M - lane);     // bins M - lane - 32 i
+  float* mag_up = a.mag_out + row + lane;           // bins lane + LANES i
+  float* mag_dn = a.mag_out + row + (M - lane);     // bins M - lane - LANES i
   const float2* twp = twN + lane;
   float vmax = 0.f;
-  constexpr int ITERS = M / 64;                     // k = lane + 32 i < M/2
+  constexpr int ITERS = M / (2 * LANES);            // k = lane + LANES i < M/2
 #pragma unroll 8
   for (int i = 0; i < ITERS; ++i) {
     float2 zk, zm;
@@ -165,19 +177,19 @@ __device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* 
       zk = buf[zk0 + i * zk_step];
       zm = buf[i == 0 ? zm0 : zm1 + (i - 1) * zm_step];
     } else {
-      const int k = lane + 32 * i;
+      const int k = lane + LANES * i;
       zk = buf[pidx(zpos<M, R0, R1, R2>(k))];
       zm = buf[pidx(zpos<M, R0, R1, R2>((M - k) & (M - 1)))];
     }
     float2 Xk, Xm;
-    split_pair(zk, zm, tab<GT>(twp + 32 * i), Xk, Xm);
+    split_pair(zk, zm, tab<GT>(twp + LANES * i), Xk, Xm);
     const float mk = fast_sqrt(fmaf(Xk.x, Xk.x, Xk.y * Xk.y));
     const float mm = fast_sqrt(fmaf(Xm.x, Xm.x, Xm.y * Xm.y));
     vmax = fmaxf(vmax, fmaxf(mk, mm));
-    mag_up[32 * i] = mk;
-    mag_dn[-32 * i] = mm;
+    mag_up[LANES * i] = mk;
+    mag_dn[-LANES * i] = mm;
     if (EXTRA) {
-      const int k = lane + 32 * i;
+      const int k = lane + LANES * i;
       if (a.cplx_out) {
         float2* c = a.cplx_out + row;
         c[k] = Xk;
@@ -205,7 +217,7 @@ __device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* 
     }
   }
   // padding columns [M+1, frame_pitch) are defined as zero
-  for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += 32) {
+  for (int64_t k = M + 1 + lane; k < a.frame_pitch; k += LANES) {
     a.mag_out[row + k] = 0.f;
     if (EXTRA) {
       if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
@@ -213,6 +225,14 @@ __device__ __forceinline__ void stft_frame_out(const float2* buf, const float2* 
     }
   }
   vmax = warp_max(vmax);
+  if constexpr (LANES > 32) {      // the frame's warps combine their maxima through shared memory
+    if ((lane & 31) == 0) gmax[threadIdx.x >> 5] = vmax;
+    group_sync<LANES>(group);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 1; i < LANES / 32; ++i) vmax = fmaxf(vmax, gmax[(threadIdx.x >> 5) + i]);
+    }
+  }
   if (lane == 0) {
     if (a.frame_max_out) a.frame_max_out[(int64_t)clip * a.max_frames + t] = vmax;
     if (a.clip_max_out) atomic_max_nonneg(a.clip_max_out + clip, vmax);
@@ -303,8 +323,11 @@ __device__ __forceinline__ void stft_frame_out_regs(const float2 (&v)[R], const 
   }
 }
 
+// threads that share one frame of the forward transform
+__host__ __device__ constexpr int stft_lanes(int M) { return M <= 1024 ? 32 : (M == 2048 ? 64 : 128); }
+
 template <int M, int R0, int R1, int R2, int WARPS, bool EXTRA>
-__global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(const StftArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, 2) stft_kernel(const StftArgs a) {
   constexpr int N = 2 * M;
   constexpr int BUF = M + M / 32;
   extern __shared__ __align__(16) float smem[];
@@ -342,24 +365,28 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) stft_kernel(c
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* buf = bufs + warp * BUF;
+  // LANES threads per frame (see group_sync): one warp up to n_fft 2048, two warps for 4096, four for 8192
+  constexpr int LANES = stft_lanes(M);
+  constexpr int GROUPS = WARPS * 32 / LANES;
+  __shared__ float gmax[WARPS];
+  const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  float2* buf = bufs + group * BUF;
   const float2* win2 = reinterpret_cast<const float2*>(a.window);
-  for (int f = warp; f < nF; f += WARPS) {
+  for (int f = group; f < nF; f += GROUPS) {
     const float* xs = span + f * a.hop;
     constexpr int L1 = M / R0, L2 = L1 / R1;
-    dif_pass<M, M, R0, true, false>(buf, xs, win2, a.tw0, lane);
+    dif_pass<M, M, R0, true, false, true, LANES>(buf, xs, win2, a.tw0, lane, group);
     if constexpr (R0 == 32 && R2 == 1) {
       // last pass stays in registers; bins k / M-k are paired by warp shuffles
       float2 v[R1];
       dif_pass_last_regs<M, L1, R1>(buf, v, lane);
       stft_frame_out_regs<M, R1, EXTRA, true>(v, a.twN, a, clip, t0 + f, lane);
     } else {
-      dif_pass<M, L1, R1, false, (R2 == 1)>(buf, nullptr, nullptr, a.tw1, lane);
-      if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true>(buf, nullptr, nullptr, nullptr, lane);
-      stft_frame_out<M, R0, R1, R2, EXTRA, true>(buf, a.twN, a, clip, t0 + f, lane);
+      dif_pass<M, L1, R1, false, (R2 == 1), true, LANES>(buf, nullptr, nullptr, a.tw1, lane, group);
+      if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true, true, LANES>(buf, nullptr, nullptr, nullptr, lane, group);
+      stft_frame_out<M, R0, R1, R2, EXTRA, true, LANES>(buf, a.twN, a, clip, t0 + f, lane, group, gmax);
     }
-    __syncwarp();
+    group_sync<LANES>(group);
   }
 }
 
@@ -517,8 +544,10 @@ static void stft_shape(int n_fft, int* radix, int* n_pass, int* warps) {
     case 256: radix[0] = 16; radix[1] = 16; break;
     case 512: radix[0] = 32; radix[1] = 16; break;
     case 1024: radix[0] = 32; radix[1] = 32; *warps = 10; break;
+    // long transforms: 2 / 4 warps per frame (stft_lanes), so that the few frames whose exchange buffers fit an SM
+    // still bring 16 warps with them
     case 2048: radix[0] = 16; radix[1] = 16; radix[2] = 8; *n_pass = 3; *warps = 8; break;
-    case 4096: radix[0] = 16; radix[1] = 16; radix[2] = 16; *n_pass = 3; *warps = 4; break;
+    case 4096: radix[0] = 16; radix[1] = 16; radix[2] = 16; *n_pass = 3; *warps = 8; break;
     default: radix[0] = 0;
   }
 }
@@ -578,14 +607,15 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
   SAGA_CUDA_OK(cudaMemcpy(p->d_twN, twN.data(), sizeof(float2) * twN.size(), cudaMemcpyHostToDevice));
 
   // frames per CTA: as many as fit a ~100 KB CTA (two CTAs per SM), at most 1 per warp
-  const size_t buf_bytes = (size_t)warps * (M + M / 32) * sizeof(float2);
-  const size_t budget = (M <= 1024 ? 112 * 1024 : 200 * 1024);
+  const int groups = warps * 32 / saga::stft_lanes(M);      // frames in flight per CTA (one exchange buffer each)
+  const size_t buf_bytes = (size_t)groups * (M + M / 32) * sizeof(float2);
+  const size_t budget = 112 * 1024;      // two CTAs per SM for every shape
   int F = 1;
   if (budget > buf_bytes + (size_t)n_fft * 4) {
     const size_t span_floats = (budget - buf_bytes) / 4;
     F = (int)((span_floats - n_fft) / hop) + 1;
   }
-  if (F > warps) F = warps;     // one frame per warp: measured equal to two per warp on long clips (1.04 ms) and
+  if (F > groups) F = groups;   // one frame per warp (group): measured equal to two per warp on long clips (1.04 ms) and
                                 // better on short ones (128-frame guesses: 0.30 vs 0.32 ms) -- finer tiles, same overlap reuse
   if (const char* e = getenv("SAGA_STFT_FRAMES")) F = std::max(1, std::min(F, atoi(e)));   // tuning aid
   if (F < 1) F = 1;
@@ -658,7 +688,7 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
     case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
     case 1024: return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
     case 2048: return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
-    case 4096: return launch_stft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
+    case 4096: return launch_stft<4096, 16, 16, 16, 8>(p, a, n_clips, st);
   }
   return set_error(SAGA_ERR_UNSUPPORTED, "stft_exec: unsupported n_fft");
 }
