@@ -32,6 +32,7 @@ struct saga_stft_plan {
   float* d_window_half;  // 0.5 * window (forward kernel)
   float2* d_tw[3];   // per pass: [R][L/R] inter-pass twiddles (last pass: unused)
   float2* d_twN;     // M/2 + 1 entries exp(-2*pi*i*k/n_fft)
+  float2* d_tw_eo;   // n_fft 4096 only: [32][32] exp(-2*pi*i*rp*j/1024), first-pass twiddles of the two 1024-point halves
   int warps;         // warps per CTA
   int frames_per_cta;
   int span_alloc;    // floats reserved for the staged span
@@ -55,6 +56,7 @@ struct StftArgs {
   const float2* tw0;
   const float2* tw1;
   const float2* twN;
+  const float2* tw_eo;
   int64_t frame_pitch, out_clip_stride;
   int hop, center, frames_per_cta, span_alloc, tiles_per_clip, max_frames;
 };
@@ -390,6 +392,177 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft_kernel(const StftArgs a) {
   }
 }
 
+// ---- n_fft = 4096 (the reference's default N): even / odd split on the tuned 1024-point path ------------------
+// The frame's 2048 complex points z[n] = (x[2n], x[2n+1]) * window are split by parity; the two warps that share
+// the frame each run the two-pass radix-32 x radix-32 transform of n_fft 2048 on one half (last pass in registers),
+// leave E[k] / O[k] in natural order in their exchange buffers, and the 64 lanes then finish together:
+//     Z[k] = E[k] + W2048^k O[k],   Z[k + 1024] = E[k] - W2048^k O[k],
+// real-FFT split of the pairs (k, 2048 - k) and (1024 - k, 1024 + k) -- four output bins from E, O at k and 1024 - k --
+// magnitudes (+ phasor / complex), maxima.  2.9 k warp instructions per frame instead of 5.7 k for the three-pass
+// radix-16/16/8 form.  W2048^k = twN[2k], W4096^k = twN[k]; W2048^(1024-k) = -conj(W2048^k).
+template <bool EXTRA>
+__device__ __forceinline__ void eo_store(const StftArgs& a, int64_t row, int k, float2 X, float& vmax) {
+  const float m = fast_sqrt(fmaf(X.x, X.x, X.y * X.y));
+  vmax = fmaxf(vmax, m);
+  a.mag_out[row + k] = m;
+  if (EXTRA) {
+    if (a.cplx_out) a.cplx_out[row + k] = X;
+    if (a.phase_out) a.phase_out[row + k] = m > 0.f ? make_float2(X.x / m, X.y / m) : make_float2(1.f, 0.f);
+  }
+}
+
+template <int WARPS, bool EXTRA>
+__global__ void __launch_bounds__(WARPS * 32, 2) stft_eo4096_kernel(const StftArgs a) {
+  constexpr int M = 2048, N = 4096, MH = 1024, BUFH = MH + MH / 32, GROUPS = WARPS / 2;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float gmax[WARPS];
+  float* span = smem;
+  float2* bufs = reinterpret_cast<float2*>(smem + a.span_alloc);
+
+  const int clip = blockIdx.x / a.tiles_per_clip;
+  const int tile = blockIdx.x % a.tiles_per_clip;
+  const int64_t len = a.clip_lens[clip];
+  int64_t T;
+  if (len <= 0) T = 0;
+  else if (a.center) T = 1 + len / a.hop;
+  else T = len >= N ? 1 + (len - N) / a.hop : 0;
+  const int64_t t0 = (int64_t)tile * a.frames_per_cta;
+  if (t0 >= T) return;
+  const int nF = (int)min((int64_t)a.frames_per_cta, T - t0);
+  const float* x = a.wav + a.clip_offsets[clip];
+
+  const int64_t s0 = t0 * a.hop - (a.center ? N / 2 : 0);
+  const int span_len = (nF - 1) * a.hop + N;
+  const bool interior = (s0 >= 0) && (s0 + span_len <= len);
+  if (interior && ((reinterpret_cast<uintptr_t>(x + s0) & 15) == 0)) {
+    const float4* src = reinterpret_cast<const float4*>(x + s0);
+    float4* dst = reinterpret_cast<float4*>(span);
+    const int n4 = span_len >> 2;
+    for (int i = threadIdx.x; i < n4; i += WARPS * 32) dst[i] = __ldg(src + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < span_len; i += WARPS * 32) span[i] = __ldg(x + s0 + i);
+  } else {
+    for (int i = threadIdx.x; i < span_len; i += WARPS * 32) {
+      int64_t s = s0 + i;
+      if (s < 0 || s >= len) s = reflect_index(s, len);
+      span[i] = __ldg(x + s);
+    }
+  }
+  __syncthreads();
+
+  const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63, par = lane64 >> 5, lane = threadIdx.x & 31;
+  float2* bufE = bufs + group * (2 * BUFH);
+  float2* bufO = bufE + BUFH;
+  float2* mybuf = par ? bufO : bufE;
+  const float2* win2 = reinterpret_cast<const float2*>(a.window);
+  for (int f = group; f < nF; f += GROUPS) {
+    const float* xs = span + f * a.hop;
+    {
+      // first pass of this warp's half: points m = lane + 32 r are the frame's pairs 2m + par
+      float2 v[32];
+      const bool al = ((reinterpret_cast<uintptr_t>(xs) & 7) == 0);
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const int n = 2 * (lane + 32 * r) + par;
+        float2 xv;
+        if (al) {
+          xv = *reinterpret_cast<const float2*>(xs + 2 * n);
+        } else {
+          xv.x = xs[2 * n];
+          xv.y = xs[2 * n + 1];
+        }
+        v[r] = pmul(xv, __ldg(win2 + n));
+      }
+      fft_reg<32>(v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int rp = bitrev(i, 32);
+        float2 o = v[i];
+        if (rp > 0) o = cmul(o, __ldg(a.tw_eo + rp * 32 + lane));
+        mybuf[pidx(lane + rp * 32)] = o;
+      }
+      __syncwarp();
+      // second pass in registers: v[bitrev(rp)] = half-transform bin lane + 32 rp; back to the buffer in natural order
+      dif_pass_last_regs<MH, 32, 32>(mybuf, v, lane);
+      __syncwarp();
+#pragma unroll
+      for (int rp = 0; rp < 32; ++rp) mybuf[pidx(lane + 32 * rp)] = v[bitrev(rp, 32)];
+    }
+    group_sync<64>(group);
+
+    // ---- combine the halves + real-FFT split, 64 lanes: k = lane64 + 64 i in [0, 512) --------------------
+    const int64_t t = t0 + f;
+    const int64_t row = (int64_t)clip * a.out_clip_stride + t * a.frame_pitch;
+    float vmax = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int k = lane64 + 64 * i;
+      const int km = (MH - k) & (MH - 1);              // 1024 - k (0 for k = 0)
+      const float2 Ek = bufE[pidx(k)], Ok = bufO[pidx(k)];
+      const float2 Em = bufE[pidx(km)], Om = bufO[pidx(km)];
+      const float2 wk = __ldg(a.twN + 2 * k);          // W2048^k
+      const float2 T1 = cmul(wk, Ok);
+      const float2 T2 = cmul(make_float2(-wk.x, wk.y), Om);   // W2048^(1024-k) = -conj(W2048^k)
+      const float2 Zk = cadd(Ek, T1), Zk1 = csub(Ek, T1);      // bins k, k + 1024
+      const float2 Zm = cadd(Em, T2), Zm1 = csub(Em, T2);      // bins 1024 - k, 2048 - k
+      float2 Xa, Xb, Xc, Xd;
+      if (k != 0) {
+        split_pair(Zk, Zm1, __ldg(a.twN + k), Xa, Xb);         // X[k], X[2048 - k]
+        split_pair(Zm, Zk1, __ldg(a.twN + MH - k), Xc, Xd);    // X[1024 - k], X[1024 + k]
+        eo_store<EXTRA>(a, row, k, Xa, vmax);
+        eo_store<EXTRA>(a, row, M - k, Xb, vmax);
+        eo_store<EXTRA>(a, row, MH - k, Xc, vmax);
+        eo_store<EXTRA>(a, row, MH + k, Xd, vmax);
+      } else {
+        // k = 0: Z[0] = E0 + O0 pairs with itself (bins 0 and 2048), Z[1024] = E0 - O0 with itself (bin 1024)
+        split_pair(Zk, Zk, __ldg(a.twN), Xa, Xb);
+        split_pair(Zk1, Zk1, __ldg(a.twN + MH), Xc, Xd);
+        eo_store<EXTRA>(a, row, 0, Xa, vmax);
+        eo_store<EXTRA>(a, row, M, Xb, vmax);
+        eo_store<EXTRA>(a, row, MH, Xc, vmax);
+      }
+    }
+    if (lane64 == 0) {
+      // k = 512: 1024 - k = k, one pair (512, 1536)
+      const float2 Ek = bufE[pidx(512)], Ok = bufO[pidx(512)];
+      const float2 T1 = cmul(__ldg(a.twN + 1024), Ok);
+      float2 Xa, Xb;
+      split_pair(cadd(Ek, T1), csub(Ek, T1), __ldg(a.twN + 512), Xa, Xb);
+      eo_store<EXTRA>(a, row, 512, Xa, vmax);
+      eo_store<EXTRA>(a, row, 1536, Xb, vmax);
+    }
+    for (int64_t k = M + 1 + lane64; k < a.frame_pitch; k += 64) {
+      a.mag_out[row + k] = 0.f;
+      if (EXTRA) {
+        if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+        if (a.phase_out) a.phase_out[row + k] = make_float2(0.f, 0.f);
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0) gmax[threadIdx.x >> 5] = vmax;
+    group_sync<64>(group);
+    if (lane64 == 0) {
+      vmax = fmaxf(vmax, gmax[(threadIdx.x >> 5) + 1]);
+      if (a.frame_max_out) a.frame_max_out[(int64_t)clip * a.max_frames + t] = vmax;
+      if (a.clip_max_out) atomic_max_nonneg(a.clip_max_out + clip, vmax);
+    }
+    group_sync<64>(group);
+  }
+}
+
+template <int WARPS>
+static int launch_stft_eo4096(const saga_stft_plan* p, const StftArgs& a, int n_clips, cudaStream_t st) {
+  const bool extra = a.phase_out || a.cplx_out;
+  auto kern = extra ? stft_eo4096_kernel<WARPS, true> : stft_eo4096_kernel<WARPS, false>;
+  SAGA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int64_t blocks = (int64_t)n_clips * a.tiles_per_clip;
+  if (blocks <= 0) return SAGA_OK;
+  if (blocks > 0x7fffffffLL) return set_error(SAGA_ERR_INVALID, "stft: grid too large");
+  if (a.frames_per_cta > WARPS / 2) return set_error(SAGA_ERR_INVALID, "stft: more frames per CTA than frame slots");
+  kern<<<(unsigned)blocks, WARPS * 32, p->smem_bytes, st>>>(a);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
 template <int M, int R0, int R1, int R2, int WARPS>
 static int launch_stft(const saga_stft_plan* p, const StftArgs& a, int n_clips, cudaStream_t st) {
   const bool extra = a.phase_out || a.cplx_out;
@@ -568,6 +741,7 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
   p->M = n_fft / 2;
   p->n_pass = n_pass;
   for (int i = 0; i < 3; ++i) { p->radix[i] = radix[i]; p->d_tw[i] = nullptr; }
+  p->d_tw_eo = nullptr;
   p->warps = warps;
   const int M = p->M;
   const double PI = 3.14159265358979323846;
@@ -597,6 +771,16 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
     SAGA_CUDA_OK(cudaMalloc(&p->d_tw[ps], sizeof(float2) * L));
     SAGA_CUDA_OK(cudaMemcpy(p->d_tw[ps], tw.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
     L = LS;
+  }
+  if (M == 2048) {      // first-pass twiddles of the 1024-point halves (stft_eo4096_kernel)
+    std::vector<float2> tw(1024);
+    for (int rp = 0; rp < 32; ++rp)
+      for (int j = 0; j < 32; ++j) {
+        const double ang = -2.0 * PI * (double)((j * rp) % 1024) / 1024.0;
+        tw[(size_t)rp * 32 + j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      }
+    SAGA_CUDA_OK(cudaMalloc(&p->d_tw_eo, sizeof(float2) * 1024));
+    SAGA_CUDA_OK(cudaMemcpy(p->d_tw_eo, tw.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
   }
   std::vector<float2> twN(M / 2 + 1);
   for (int k = 0; k <= M / 2; ++k) {
@@ -635,6 +819,7 @@ extern "C" int saga_stft_plan_destroy(saga_stft_plan* p) {
   cudaFree(p->d_window);
   cudaFree(p->d_window_half);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_tw[i]);
+  cudaFree(p->d_tw_eo);
   cudaFree(p->d_twN);
   delete p;
   return SAGA_OK;
@@ -674,6 +859,7 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
   a.tw0 = p->d_tw[0];
   a.tw1 = p->d_tw[1];
   a.twN = p->d_twN;
+  a.tw_eo = p->d_tw_eo;
   a.frame_pitch = frame_pitch;
   a.out_clip_stride = out_clip_stride;
   a.hop = p->hop;
@@ -687,7 +873,9 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
     case 256: return launch_stft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
     case 1024: return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
-    case 2048: return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
+    case 2048:
+      if (getenv("SAGA_STFT_NO_EO")) return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // three-pass form (A/B)
+      return launch_stft_eo4096<8>(p, a, n_clips, st);
     case 4096: return launch_stft<4096, 16, 16, 16, 8>(p, a, n_clips, st);
   }
   return set_error(SAGA_ERR_UNSUPPORTED, "stft_exec: unsupported n_fft");

@@ -79,12 +79,12 @@ def test_stft_db_within_tolerance(saga, cfg1):
         check_db(D[0, :, :plan.n_bins].T.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 1024), (8192, 2048)])
 @pytest.mark.parametrize("center", [True, False])
-def test_stft_ragged_batch_and_edges(saga, center):
+def test_stft_ragged_batch_and_edges(saga, center, n_fft, hop):
     ops, _ = saga
     rng = np.random.default_rng(3)
-    n_fft, hop = 2048, 512
-    lens = [5000, 2048, 2049, 1, 300, 44100, 1023, 4095, 0 + 2048 * 3 + 7]
+    lens = [5000, 2048, 2049, 1, 300, 44100, 1023, 4095, 0 + 2048 * 3 + 7, 8192, 8193, 4096 * 5 + 1]
     if not center:
         lens = [x for x in lens if x >= n_fft]
     width = max(lens)
@@ -102,9 +102,10 @@ def test_stft_ragged_batch_and_edges(saga, center):
         assert np.all(got[:, T:] == 0)
 
 
-def test_stft_all_zero_clip(saga):
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 1024)])
+def test_stft_all_zero_clip(saga, n_fft, hop):
     ops, _ = saga
-    plan = ops.StftPlan(2048, 512, True)
+    plan = ops.StftPlan(n_fft, hop, True)
     r = ops.stft_batch(torch.zeros(1, 8000, device="cuda"), plan, want_phase=True)
     assert float(r["mag"].abs().max()) == 0.0
     ph = r["phase"][0].cpu().numpy()
@@ -113,15 +114,44 @@ def test_stft_all_zero_clip(saga):
     assert np.all(D[0, :, :plan.n_bins].cpu().numpy() == 0.0)   # max(amin, 0) path: D == 0 everywhere
 
 
-def test_stft_piano_noise_floor_db(saga):
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 1024)])
+def test_stft_piano_noise_floor_db(saga, n_fft, hop):
     ops, _ = saga
     y = piano_clip(11, 44100 * 2)
-    plan = ops.StftPlan(2048, 512, True)
+    plan = ops.StftPlan(n_fft, hop, True)
     r = ops.stft_batch(dev(y), plan)
-    ref = np.abs(osp.stft(y, 2048, 512))
+    ref = np.abs(osp.stft(y, n_fft, hop))
     check_mag(r["mag"][0].cpu().numpy(), ref)
     D = ops.amplitude_to_db_batch(r["mag_storage"], plan.n_bins)
     check_db(D[0, :, :plan.n_bins].T.cpu().numpy(), osp.amplitude_to_db(ref, ref=ref.max()))
+
+
+def test_stft_4096_split_kernel_against_three_pass_form(saga):
+    """n_fft 4096 (the reference's default N) runs as two 1024-point half transforms + one combine stage; the
+    three-pass radix-16/16/8 kernel stays available (SAGA_STFT_NO_EO) and both must agree to fp32 rounding on
+    magnitude, phase and complex outputs, including the clip-edge tiles and the per-clip / per-frame maxima."""
+    import os
+    ops, _ = saga
+    y = np.stack([piano_clip(70 + i, 44100) for i in range(3)])
+    plan = ops.StftPlan(4096, 1024, True)
+    out = {}
+    for mode in ("split", "three_pass"):
+        if mode == "three_pass":
+            os.environ["SAGA_STFT_NO_EO"] = "1"
+        try:
+            r = ops.stft_batch(dev(y), plan, want_phase=True, want_complex=True, want_max=True)
+            out[mode] = {k: r[k].cpu().numpy() for k in ("mag", "phase", "F", "clip_max", "frame_max") if k in r}
+        finally:
+            os.environ.pop("SAGA_STFT_NO_EO", None)
+    a, b = out["split"], out["three_pass"]
+    peak = float(b["mag"].max())
+    assert np.abs(a["mag"] - b["mag"]).max() <= 2e-6 * peak
+    assert np.abs(a["F"] - b["F"]).max() <= 2e-6 * peak
+    assert np.allclose(a["clip_max"], b["clip_max"], rtol=2e-6)
+    ref = np.stack([osp.stft(y[i], 4096, 1024) for i in range(3)])
+    check_mag(a["F"], ref, tol=2e-6)
+    strong = np.abs(ref) > 1e-3 * peak                     # phase is only meaningful away from the noise floor
+    assert np.abs(a["phase"][strong] - ref[strong] / np.abs(ref[strong])).max() <= 1e-3
 
 
 # --------------------------------------------------------------------------- K4
