@@ -53,9 +53,12 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   for (int i = threadIdx.x; i < n_taps; i += DEC_THREADS) tp[i] = taps[i];
   const int64_t i0 = o0 * factor - S;
   const int tile_in = tile_out * factor + 2 * S;
+  // the tile is stored skewed, sample i at i + i/32: consecutive outputs read samples `factor` apart, and a
+  // power-of-two stride (the early stage of a 24-bins-per-octave CQT from D3 decimates by 16) would otherwise put a
+  // warp's 32 reads on 32/factor banks (16-way conflicts: 9.1 ms for 600 windows; skewed: conflict-free)
   for (int i = threadIdx.x; i < tile_in; i += DEC_THREADS) {
     const int64_t s = i0 + i;
-    xs[i] = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+    xs[i + (i >> 5)] = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
   }
   __syncthreads();
   float* y = out + (int64_t)clip * out_stride;
@@ -66,12 +69,20 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
     if (o >= n_out) break;
     float acc = 0.f;
     if (o < n_full) {
-      const float* c = xs + lo * factor + S;  // centre sample
-      acc = tp[0] * c[0];
-      for (int m = 1; m <= S; ++m) acc = fmaf(tp[m], c[-m] + c[m], acc);
+      const int c = lo * factor + S;          // centre sample
+      acc = tp[0] * xs[c + (c >> 5)];
+      for (int m = 1; m <= S; ++m) {
+        const int a = c - m, b = c + m;
+        acc = fmaf(tp[m], xs[a + (a >> 5)] + xs[b + (b >> 5)], acc);
+      }
     }
     y[o] = acc;
   }
+}
+
+static size_t decimate_smem_bytes(int n_taps, int factor) {
+  const size_t tile_in = (size_t)DEC_THREADS * DEC_PER_THREAD * factor + 2 * (size_t)(n_taps - 1);
+  return sizeof(float) * (((n_taps + 3) & ~3) + tile_in + tile_in / 32 + 1);
 }
 
 // Factor-2 specialisation (the kaiser_fast 2:1 stage: 63 taps, S = 31), written for the packed fp32
@@ -312,6 +323,7 @@ struct ContractArgs {
   const float* bank;            // [n_fft][ncol]
   int n_fft, ncol, hop, first_bin, n_bins;
   int zero_pad;                 // this launch also zeroes the padding columns [n_bins, frame_pitch)
+  int padded;                   // sig points into a reflect-padded level buffer: samples [-n_fft/2, len + n_fft/2) are there
   float* mag_out;
   float2* cplx_out;
   int64_t frame_pitch, out_clip_stride;
@@ -387,6 +399,132 @@ cqt_contract_kernel(const ContractArgs a) {
       if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
     }
 }
+
+// Register-tiled form of the fp32 contraction, for the banks the resident-bank tensor path cannot hold (24 / 48 / 192
+// bins per octave: the reference's per-note CQTs, training.py:340-388).  CTA = 128 frames x up to 128 output columns:
+// warp w owns columns [16w, 16w + 16) -- every lane reads the same bank vector, a broadcast -- and lane l owns frames
+// l, l+32, l+64, l+96: per kernel sample 4 conflict-free LDS + 4 broadcast LDS.128 feed 64 FFMA (the first version
+// issued 9 LDS per 32 FFMA and staged the Hankel tile once per 32 columns instead of once per 128).
+constexpr int CT2_KC = 32;
+constexpr int CT2_MAXW = 8;            // warps per CTA = ceil(columns / 16), at most 8
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;                       // src-size 0: the 4 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+template <int FPL>                      // frames per lane: CTA tile = 32 * FPL frames
+__global__ void __launch_bounds__(CT2_MAXW * 32)
+cqt_contract2_kernel(const ContractArgs a, int n_warps) {
+  constexpr int TF = 32 * FPL;
+  constexpr int YS = CT2_KC * (TF + 1), GS = CT2_KC * CT2_MAXW * 16, STAGE = YS + GS;   // floats per stage
+  extern __shared__ __align__(16) float ct2_smem[];   // two stages: [ys | gs] [ys | gs], filled by cp.async
+  const int clip = blockIdx.z;
+  const int t0 = blockIdx.x * TF;
+  const int c0 = blockIdx.y * (n_warps * 16);
+  const int T = a.clip_frames[clip];
+  if (t0 >= T) return;
+  int64_t len = a.clip_lens ? a.clip_lens[clip] : a.max_len;
+  if (a.early_factor > 1) len = (len + a.early_factor - 1) / a.early_factor;
+  for (int s = 0; s < a.level; ++s) len = (len + 1) >> 1;
+  const float* y = a.sig + (a.sig_offsets ? a.sig_offsets[clip] : (int64_t)clip * a.sig_stride);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = n_warps * 32;
+  const int ncols_cta = n_warps * 16;
+  float acc[FPL][16];
+#pragma unroll
+  for (int j = 0; j < FPL; ++j)
+#pragma unroll
+    for (int f = 0; f < 16; ++f) acc[j][f] = 0.f;
+  const int half = a.n_fft >> 1;
+  const int nT = min(TF, T - t0);        // valid frames of this tile
+  const int n_chunks = a.n_fft / CT2_KC;
+
+  // Hankel tile ys[kk][t] = y[(t0+t)*hop + n0 + kk - n_fft/2] and bank rows gs[kk][c] of one K-chunk, copied
+  // asynchronously (the level buffers carry their reflect margins: cqt_pad_kernel); the next chunk's copies are
+  // in flight while this chunk is contracted
+  auto issue = [&](int chunk, int stage) {
+    float* ys = ct2_smem + stage * STAGE;
+    float* gs = ys + YS;
+    const int n0 = chunk * CT2_KC;
+    if (a.padded) {
+      const float* yb = y + (int64_t)t0 * a.hop + n0 - half;
+      for (int i = tid; i < CT2_KC * TF; i += nthr) {
+        const int kk = i % CT2_KC, t = i / CT2_KC;
+        cp_async4(ys + kk * (TF + 1) + t, yb + (int64_t)t * a.hop + kk, t < nT);
+      }
+    } else {
+      for (int i = tid; i < CT2_KC * TF; i += nthr) {
+        const int kk = i % CT2_KC, t = i / CT2_KC;
+        int64_t s = (int64_t)(t0 + t) * a.hop + n0 + kk - half;
+        if (t < nT && (s < 0 || s >= len)) s = reflect_index(s, len);
+        cp_async4(ys + kk * (TF + 1) + t, y + (t < nT ? s : 0), t < nT);
+      }
+    }
+    for (int i = tid; i < CT2_KC * ncols_cta; i += nthr) {
+      const int kk = i / ncols_cta, f = i % ncols_cta;
+      const bool ok = c0 + f < a.ncol;
+      cp_async4(gs + kk * (CT2_MAXW * 16) + f, a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(0, 0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) {
+      issue(c + 1, (c + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* ys = ct2_smem + (c & 1) * STAGE;
+    const float* gs = ys + YS;
+#pragma unroll 2
+    for (int kk = 0; kk < CT2_KC; ++kk) {
+      float v[FPL];
+#pragma unroll
+      for (int j = 0; j < FPL; ++j) v[j] = ys[kk * (TF + 1) + lane + 32 * j];
+      const float4* g4 = reinterpret_cast<const float4*>(gs + kk * (CT2_MAXW * 16) + warp * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = g4[q];
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+          acc[j][4 * q + 0] = fmaf(v[j], g.x, acc[j][4 * q + 0]);
+          acc[j][4 * q + 1] = fmaf(v[j], g.y, acc[j][4 * q + 1]);
+          acc[j][4 * q + 2] = fmaf(v[j], g.z, acc[j][4 * q + 2]);
+          acc[j][4 * q + 3] = fmaf(v[j], g.w, acc[j][4 * q + 3]);
+        }
+      }
+    }
+    __syncthreads();       // everyone is done with this stage before chunk c + 2 is copied over it
+  }
+#pragma unroll
+  for (int j = 0; j < FPL; ++j) {
+    const int t = t0 + lane + 32 * j;
+    if (t >= T) continue;
+    const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)t * a.frame_pitch;
+#pragma unroll
+    for (int f = 0; f < 16; f += 2) {
+      const int col = c0 + warp * 16 + f;
+      const int bin = a.first_bin + (col >> 1);
+      if (col < a.ncol && bin >= 0 && bin < a.n_bins) {
+        const float re = acc[j][f], im = acc[j][f + 1];
+        a.mag_out[row + bin] = sqrtf(re * re + im * im);
+        if (a.cplx_out) a.cplx_out[row + bin] = make_float2(re, im);
+      }
+    }
+    if (a.zero_pad && blockIdx.y == 0 && warp == 0)
+      for (int64_t k = a.n_bins; k < a.frame_pitch; ++k) {
+        a.mag_out[row + k] = 0.f;
+        if (a.cplx_out) a.cplx_out[row + k] = make_float2(0.f, 0.f);
+      }
+  }
+}
+
+template <int FPL>
+static size_t ct2_smem_bytes() { return sizeof(float) * 2 * (size_t)(CT2_KC * (32 * FPL + 1) + CT2_KC * CT2_MAXW * 16); }
 
 // per-clip output frame count = min over octaves of 1 + len_o // hop_o (librosa __trim_stack)
 __global__ void cqt_frames_kernel(const int64_t* clip_lens, int64_t max_len, int n_clips, int early_factor,
@@ -624,7 +762,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   if (!early_done) {
     const int64_t n_out = level_len(max_len, p->early_factor, 0);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
-    const size_t smem = sizeof(float) * (((p->n_early_taps + 3) & ~3) + tile_out * p->early_factor + 2 * (p->n_early_taps - 1));
+    const size_t smem = decimate_smem_bytes(p->n_early_taps, p->early_factor);
     if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
     if (smem > 48 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -641,7 +779,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   for (; do_cascade && l <= p->max_level; ++l) {
     const int64_t n_out = level_len(max_len, p->early_factor, l);
     dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
-    const size_t smem = sizeof(float) * (((p->n_half_taps + 3) & ~3) + tile_out * 2 + 2 * (p->n_half_taps - 1));
+    const size_t smem = decimate_smem_bytes(p->n_half_taps, 2);
     const bool from_wav = (l == 1 && p->early_factor == 1);
     const float* src = from_wav ? wav : lvl[l - 1] + pad[l - 1];
     const int64_t* src_offs = from_wav ? clip_offsets : nullptr;
@@ -666,8 +804,8 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   }
 
   const bool tensor_path = (impl != 1) && cqt_umma_supported(p);
-  if (do_cascade && tensor_path) {
-    // reflect margins (and the padded copy of a raw level 0): part of the cascade phase
+  if (do_cascade) {
+    // reflect margins (and the padded copy of a raw level 0): part of the cascade phase, for both contraction paths
     PadArgs pa;
     for (int l = 0; l < PAD_MAX_LEVELS; ++l) {
       const bool on = l <= p->max_level;
@@ -700,9 +838,13 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   for (auto& o : p->oct) {
     ContractArgs a;
     const bool raw = (o.level == 0 && p->early_factor == 1);
-    a.sig = raw ? wav : lvl[o.level] + pad[o.level];
-    a.sig_offsets = raw ? clip_offsets : nullptr;
-    a.sig_stride = raw ? 0 : pitch[o.level];
+    // the level buffers (a raw level 0 included: cqt_pad_kernel copies it) carry reflect margins of n_fft/2 samples;
+    // a contraction-only call after a cascade-only call finds them in the workspace
+    a.sig = lvl[o.level] + pad[o.level];
+    a.sig_offsets = nullptr;
+    a.sig_stride = pitch[o.level];
+    a.padded = getenv("SAGA_CQT_CONTRACT_V1") ? 0 : 1;
+    (void)raw;
     a.clip_lens = clip_lens;
     a.max_len = max_len;
     a.early_factor = p->early_factor;
@@ -720,8 +862,26 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     a.frame_pitch = frame_pitch;
     a.out_clip_stride = out_clip_stride;
     a.clip_frames = clip_frames;
-    dim3 grid((unsigned)((T_max + CT_FRAMES - 1) / CT_FRAMES), (a.ncol + CT_FC - 1) / CT_FC, n_clips);
-    cqt_contract_kernel<<<grid, CT_FRAMES, 0, st>>>(a);
+    if (getenv("SAGA_CQT_CONTRACT_V1")) {          // first-generation kernel (A/B)
+      dim3 grid((unsigned)((T_max + CT_FRAMES - 1) / CT_FRAMES), (a.ncol + CT_FC - 1) / CT_FC, n_clips);
+      cqt_contract_kernel<<<grid, CT_FRAMES, 0, st>>>(a);
+    } else {
+      const int ny0 = (a.ncol + CT2_MAXW * 16 - 1) / (CT2_MAXW * 16);              // column blocks at full width
+      const int n_warps = std::max(1, ((a.ncol + ny0 - 1) / ny0 + 15) / 16);       // even split over them (<= 8 warps)
+      const int ny = (a.ncol + n_warps * 16 - 1) / (n_warps * 16);
+      // frames per lane 3 or 4 (tiles of 96 / 128 frames): whichever pads the clip's frame count less
+      const int64_t waste4 = (T_max + 127) / 128 * 128, waste3 = (T_max + 95) / 96 * 96;
+      if (a.n_fft % CT2_KC) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: kernel length must be a multiple of %d", CT2_KC);
+      if (waste3 < waste4) {
+        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<3>()));
+        dim3 grid((unsigned)((T_max + 95) / 96), ny, n_clips);
+        cqt_contract2_kernel<3><<<grid, n_warps * 32, ct2_smem_bytes<3>(), st>>>(a, n_warps);
+      } else {
+        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<4>()));
+        dim3 grid((unsigned)((T_max + 127) / 128), ny, n_clips);
+        cqt_contract2_kernel<4><<<grid, n_warps * 32, ct2_smem_bytes<4>(), st>>>(a, n_warps);
+      }
+    }
     SAGA_LAUNCH_CHECK();
   }
   return SAGA_OK;
