@@ -439,6 +439,7 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
   const int half = a.n_fft >> 1;
   const int nT = min(TF, T - t0);        // valid frames of this tile
   const int n_chunks = a.n_fft / CT2_KC;
+  const bool vec_bank = (a.ncol & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.bank) & 15) == 0);
 
   // Hankel tile ys[kk][t] = y[(t0+t)*hop + n0 + kk - n_fft/2] and bank rows gs[kk][c] of one K-chunk, copied
   // asynchronously (the level buffers carry their reflect margins: cqt_pad_kernel); the next chunk's copies are
@@ -448,11 +449,11 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
     float* gs = ys + YS;
     const int n0 = chunk * CT2_KC;
     if (a.padded) {
-      const float* yb = y + (int64_t)t0 * a.hop + n0 - half;
-      for (int i = tid; i < CT2_KC * TF; i += nthr) {
-        const int kk = i % CT2_KC, t = i / CT2_KC;
-        cp_async4(ys + kk * (TF + 1) + t, yb + (int64_t)t * a.hop + kk, t < nT);
-      }
+      // thread = (kk = lane, t = warp, warp + n_warps, ...): one pointer pair advanced by a constant step
+      const float* src = y + (int64_t)t0 * a.hop + n0 - half + (int64_t)warp * a.hop + lane;
+      float* dst = ys + lane * (TF + 1) + warp;
+      const int64_t sstep = (int64_t)n_warps * a.hop;
+      for (int t = warp; t < TF; t += n_warps, src += sstep, dst += n_warps) cp_async4(dst, src, t < nT);
     } else {
       for (int i = tid; i < CT2_KC * TF; i += nthr) {
         const int kk = i % CT2_KC, t = i / CT2_KC;
@@ -461,10 +462,23 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
         cp_async4(ys + kk * (TF + 1) + t, y + (t < nT ? s : 0), t < nT);
       }
     }
-    for (int i = tid; i < CT2_KC * ncols_cta; i += nthr) {
-      const int kk = i / ncols_cta, f = i % ncols_cta;
-      const bool ok = c0 + f < a.ncol;
-      cp_async4(gs + kk * (CT2_MAXW * 16) + f, a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0), ok);
+    if (vec_bank) {
+      // bank rows are 16-byte aligned (ncol and c0 multiples of 4): 4 columns per copy
+      const int q_per_row = ncols_cta >> 2;
+      for (int i = tid; i < CT2_KC * q_per_row; i += nthr) {
+        const int kk = i / q_per_row, f = (i % q_per_row) << 2;
+        const bool ok = c0 + f < a.ncol;          // ncol % 4 == 0: a vector is entirely inside or outside
+        const unsigned d = (unsigned)__cvta_generic_to_shared(gs + kk * (CT2_MAXW * 16) + f);
+        const float* g = a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0);
+        const int sz = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(sz) : "memory");
+      }
+    } else {
+      for (int i = tid; i < CT2_KC * ncols_cta; i += nthr) {
+        const int kk = i / ncols_cta, f = i % ncols_cta;
+        const bool ok = c0 + f < a.ncol;
+        cp_async4(gs + kk * (CT2_MAXW * 16) + f, a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0), ok);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
