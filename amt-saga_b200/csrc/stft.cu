@@ -626,27 +626,40 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
   for (int f = warp; f < nfr; f += WARPS) {
     float2* buf = bufs + f * BUF;
     const int64_t row = (int64_t)clip * a.in_clip_stride + (t_lo + f) * a.frame_pitch;
-    // rebuild conj(Z[k]),  Z = E + iO  from the half spectrum X[0..M]
+    // rebuild conj(Z[k]),  Z = E + iO  from the half spectrum X[0..M]; four bins per lane in flight (the loads
+    // of a bin pair are six independent global reads: one pair at a time left the warp waiting on DRAM latency)
+    constexpr int U = 4;
 #pragma unroll 1
-    for (int k = lane; k <= M / 2; k += 32) {
-      float2 xk, xm;
-      if (a.cplx_in) {
-        xk = a.cplx_in[row + k];
-        xm = a.cplx_in[row + M - k];
-      } else {
-        const float mk = a.mag_in[row + k], mm = a.mag_in[row + M - k];
-        const float2 pk = a.phase_in[row + k], pm = a.phase_in[row + M - k];
-        xk = make_float2(mk * pk.x, mk * pk.y);
-        xm = make_float2(mm * pm.x, mm * pm.y);
+    for (int k0 = lane; k0 <= M / 2; k0 += 32 * U) {
+      float2 xk[U], xm[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + 32 * u;
+        if (k > M / 2) continue;
+        if (a.cplx_in) {
+          xk[u] = a.cplx_in[row + k];
+          xm[u] = a.cplx_in[row + M - k];
+        } else {
+          const float mk = a.mag_in[row + k], mm = a.mag_in[row + M - k];
+          const float2 pk = a.phase_in[row + k], pm = a.phase_in[row + M - k];
+          xk[u] = make_float2(mk * pk.x, mk * pk.y);
+          xm[u] = make_float2(mm * pm.x, mm * pm.y);
+        }
       }
-      if (k == 0) { xk.y = 0.f; xm.y = 0.f; }          // irfft ignores Im of DC and Nyquist
-      const float2 E = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
-      const float2 D = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));   // W^k O
-      const float2 w = __ldg(a.twN + k);
-      const float2 O = make_float2(D.x * w.x + D.y * w.y, D.y * w.x - D.x * w.y); // D * conj(w)
-      // Z[k] = E + iO ; Z[M-k] = conj(E) + i conj(O);  store conjugates
-      buf[pidx(k)] = make_float2(E.x - O.y, -(E.y + O.x));
-      if (k != 0 && k != M / 2) buf[pidx(M - k)] = make_float2(E.x + O.y, -(O.x - E.y));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + 32 * u;
+        if (k > M / 2) continue;
+        float2 a_k = xk[u], a_m = xm[u];
+        if (k == 0) { a_k.y = 0.f; a_m.y = 0.f; }          // irfft ignores Im of DC and Nyquist
+        const float2 E = make_float2(0.5f * (a_k.x + a_m.x), 0.5f * (a_k.y - a_m.y));
+        const float2 D = make_float2(0.5f * (a_k.x - a_m.x), 0.5f * (a_k.y + a_m.y));   // W^k O
+        const float2 w = __ldg(a.twN + k);
+        const float2 O = make_float2(D.x * w.x + D.y * w.y, D.y * w.x - D.x * w.y); // D * conj(w)
+        // Z[k] = E + iO ; Z[M-k] = conj(E) + i conj(O);  store conjugates
+        buf[pidx(k)] = make_float2(E.x - O.y, -(E.y + O.x));
+        if (k != 0 && k != M / 2) buf[pidx(M - k)] = make_float2(E.x + O.y, -(O.x - E.y));
+      }
     }
     __syncwarp();
     constexpr int L1 = M / R0, L2 = L1 / R1;
@@ -659,16 +672,53 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
   // ---- gather / overlap-add in frame order, normalise, store -------------------
   const float inv_m = 1.0f / (float)M;
   float* y = a.wav_out + (int64_t)clip * a.wav_clip_stride;
-  for (int64_t p = p0 + threadIdx.x; p < p1; p += WARPS * 32) {
-    int64_t ta = (p - N + a.hop) / a.hop;               // ceil((p - N + 1)/hop)
-    if (p - N + 1 <= 0) ta = 0;
-    int64_t tb = p / a.hop;
-    if (tb > T - 1) tb = T - 1;
+  // positions relative to the first buffered frame: everything below fits 32-bit integers
+  const int q0 = (int)(p0 - t_lo * a.hop), q1 = (int)(p1 - t_lo * a.hop);
+  if (N == 4 * a.hop && (a.hop & 1) == 0) {
+    // hop = n_fft / 4 (the reference's default and the bench shape): a thread owns the sample residues r = q mod hop,
+    // keeps the four window values and buffer positions of that residue in registers and walks the tile's hop slots --
+    // 4 shared-memory loads and 8 FMAs per sample instead of re-deriving frame ranges, window addresses and
+    // digit-reversed positions per sample (2.4 k of the kernel's 6.3 k warp instructions per output frame).
+    // Contributions are still added in ascending frame order (j = 3 .. 0).
+    constexpr int J = 4;
+    const int s0 = q0 / a.hop, s1 = q1 / a.hop;          // q0, q1 are multiples of hop here (trim = 2 hop)
+    for (int r = threadIdx.x; r < a.hop; r += WARPS * 32) {
+      float wn[J];
+      int zp[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int n = r + j * a.hop;
+        wn[j] = __ldg(a.window + n);
+        zp[j] = pidx(zpos<M, R0, R1, R2>(n >> 1));
+      }
+      const bool odd = r & 1;
+      for (int sl = s0; sl < s1; ++sl) {
+        float acc = 0.f, wss = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) {
+          const int j = J - 1 - jj, f = sl - j;
+          if (f >= 0 && f < nfr) {
+            const float2 z = bufs[f * BUF + zp[j]];
+            const float xv = (odd ? -z.y : z.x) * inv_m;
+            acc += wn[j] * xv;
+            wss += wn[j] * wn[j];
+          }
+        }
+        if (wss > 1.17549435e-38f) acc /= wss;
+        y[t_lo * a.hop + (int64_t)sl * a.hop + r - trim] = acc;
+      }
+    }
+    return;
+  }
+  for (int q = q0 + threadIdx.x; q < q1; q += WARPS * 32) {
+    const int fa = (q - N + 1 <= 0) ? 0 : (q - N + a.hop) / a.hop;     // ceil((q - N + 1)/hop)
+    const int fb = min(q / a.hop, nfr - 1);
+    const int64_t p = q + t_lo * a.hop;
     float acc = 0.f, wss = 0.f;
-    for (int64_t t = ta; t <= tb; ++t) {
-      const int n = (int)(p - t * a.hop);
+    for (int f = fa; f <= fb; ++f) {
+      const int n = q - f * a.hop;
       const float wn = __ldg(a.window + n);
-      const float2 z = bufs[(int)(t - t_lo) * BUF + pidx(zpos<M, R0, R1, R2>(n >> 1))];
+      const float2 z = bufs[f * BUF + pidx(zpos<M, R0, R1, R2>(n >> 1))];
       const float xv = ((n & 1) ? -z.y : z.x) * inv_m;
       acc += wn * xv;
       wss += wn * wn;
