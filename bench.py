@@ -359,6 +359,31 @@ def run_saga(args):
         roof = {"kernel": kernels.get(dom, dom), "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": tr, "peak_source": peak_src}
 
+    # ---- the same step at the reference's own default analysis shape (main.py: N=4096, hop=1024; CQT 87 bins from A0,
+    # training.py:271), reported beside the BASELINE shape; never the headline
+    ref_shape = None
+    if world == 1 and not args.no_ref_shape:
+        try:
+            p2 = WindowFeaturePipeline(W, WIN_SAMPLES, GUESS_SAMPLES, SR, 4096, 1024, cqt_lowest="A0", cqt_bins=87,
+                                       cqt_bpo=12, device=dev)
+            offs2 = torch.div(offs, 2, rounding_mode="floor").to(torch.int32)
+            for _ in range(3):
+                p2.run(wav, guess, offs2)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n2 = max(3, min(args.steps, 30))
+            r0.record()
+            for _ in range(n2):
+                p2.run(wav, guess, offs2)
+            r1.record()
+            torch.cuda.synchronize()
+            ms2 = r0.elapsed_time(r1) / n2
+            ref_shape = {"shape": "n_fft 4096, hop 1024, 258 frames per window, CQT 87 bins from A0 (12 per octave)",
+                         "value": W / (ms2 * 1e-3), "unit": "window-features/s", "ms_per_step": ms2, "steps": n2}
+            del p2
+        except Exception as e:      # informational only
+            ref_shape = {"error": repr(e)[:200]}
+
     cpu = None
     if world == 1 and args.cpu_windows > 0:
         v = cpu_sample(args.cpu_windows, 1)
@@ -394,6 +419,7 @@ def run_saga(args):
         "roofline": roof,
         "stages": stages,
         "cpu_baseline": cpu,
+        "reference_default_shape": ref_shape,
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -412,6 +438,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cqt-impl", type=int, default=0)
     ap.add_argument("--e2e-chunks", type=int, default=12, help="window chunks for H2D/compute/D2H overlap")
+    ap.add_argument("--no-ref-shape", action="store_true", help="skip the extra pass at the reference's default n_fft/hop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
