@@ -599,6 +599,9 @@ struct IstftArgs {
   int hop, center, n_frames, FO, nbuf, tiles_per_clip;
 };
 
+// threads sharing one frame of the inverse transform: 64 for n_fft 4096 when the CTA has the 16 warps for it
+__host__ __device__ constexpr int istft_lanes(int M, int warps) { return (M == 2048 && warps == 16) ? 64 : 32; }
+
 template <int M, int R0, int R1, int R2, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(const IstftArgs a) {
   constexpr int N = 2 * M;
@@ -622,19 +625,23 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
   if (t_hi > T - 1) t_hi = T - 1;
   const int nfr = (int)(t_hi - t_lo + 1);             // <= nbuf by construction
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int f = warp; f < nfr; f += WARPS) {
+  // n_fft 4096: two warps per frame (named barrier per frame slot), so that the 8 frames whose buffers fit the SM
+  // bring 16 warps and run in one round
+  constexpr int LANES = istft_lanes(M, WARPS);
+  constexpr int GROUPS = WARPS * 32 / LANES;
+  const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  for (int f = group; f < nfr; f += GROUPS) {
     float2* buf = bufs + f * BUF;
     const int64_t row = (int64_t)clip * a.in_clip_stride + (t_lo + f) * a.frame_pitch;
     // rebuild conj(Z[k]),  Z = E + iO  from the half spectrum X[0..M]; four bins per lane in flight (the loads
     // of a bin pair are six independent global reads: one pair at a time left the warp waiting on DRAM latency)
     constexpr int U = 4;
 #pragma unroll 1
-    for (int k0 = lane; k0 <= M / 2; k0 += 32 * U) {
+    for (int k0 = lane; k0 <= M / 2; k0 += LANES * U) {
       float2 xk[U], xm[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int k = k0 + 32 * u;
+        const int k = k0 + LANES * u;
         if (k > M / 2) continue;
         if (a.cplx_in) {
           xk[u] = a.cplx_in[row + k];
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int k = k0 + 32 * u;
+        const int k = k0 + LANES * u;
         if (k > M / 2) continue;
         float2 a_k = xk[u], a_m = xm[u];
         if (k == 0) { a_k.y = 0.f; a_m.y = 0.f; }          // irfft ignores Im of DC and Nyquist
@@ -661,11 +668,11 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
         if (k != 0 && k != M / 2) buf[pidx(M - k)] = make_float2(E.x + O.y, -(O.x - E.y));
       }
     }
-    __syncwarp();
+    group_sync<LANES>(group);
     constexpr int L1 = M / R0, L2 = L1 / R1;
-    dif_pass<M, M, R0, false, false>(buf, nullptr, nullptr, a.tw0, lane);
-    dif_pass<M, L1, R1, false, (R2 == 1)>(buf, nullptr, nullptr, a.tw1, lane);
-    if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true>(buf, nullptr, nullptr, nullptr, lane);
+    dif_pass<M, M, R0, false, false, true, LANES>(buf, nullptr, nullptr, a.tw0, lane, group);
+    dif_pass<M, L1, R1, false, (R2 == 1), true, LANES>(buf, nullptr, nullptr, a.tw1, lane, group);
+    if constexpr (R2 > 1) dif_pass<M, L2, R2, false, true, true, LANES>(buf, nullptr, nullptr, nullptr, lane, group);
   }
   __syncthreads();
 
@@ -735,9 +742,13 @@ static int launch_istft(const saga_stft_plan* p, IstftArgs& a, int n_clips, cuda
   const int halo = (2 * M + p->hop - 1) / p->hop;  // frames that can overlap a chunk beyond its own FO
   int nbuf = (int)((200 * 1024) / (BUF * sizeof(float2)));
   if (M <= 1024) nbuf = std::min(nbuf, (int)((104 * 1024) / (BUF * sizeof(float2))));
+  constexpr int GROUPS = WARPS * 32 / istft_lanes(M, WARPS);
+  // multi-warp frames: every buffered frame gets its own group, one round (8 frames = 4 output hops + 4 halo frames
+  // at hop = n_fft/4 beats 11 frames run as 8 + 3)
+  if (istft_lanes(M, WARPS) > 32 && nbuf > GROUPS && GROUPS > halo) nbuf = GROUPS;
   int FO = nbuf - halo;
   if (FO < 1) return set_error(SAGA_ERR_UNSUPPORTED, "istft: hop=%d too small for n_fft=%d", p->hop, 2 * M);
-  if (FO > 2 * WARPS) FO = 2 * WARPS;
+  if (FO > 2 * GROUPS) FO = 2 * GROUPS;
   a.FO = FO;
   a.nbuf = FO + halo;
   const int64_t total = (int64_t)2 * M + (int64_t)p->hop * (a.n_frames - 1);
@@ -960,7 +971,9 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
     case 256: return launch_istft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_istft<512, 32, 16, 1, 8>(p, a, n_clips, st);
     case 1024: return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
-    case 2048: return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);
+    case 2048:
+      if (getenv("SAGA_ISTFT_ONE_WARP")) return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // A/B
+      return launch_istft<2048, 16, 16, 8, 16>(p, a, n_clips, st);
     case 4096: return launch_istft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
   }
   return set_error(SAGA_ERR_UNSUPPORTED, "istft_exec: unsupported n_fft");
