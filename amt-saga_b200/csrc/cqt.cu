@@ -418,7 +418,9 @@ template <int FPL>                      // frames per lane: CTA tile = 32 * FPL 
 __global__ void __launch_bounds__(CT2_MAXW * 32)
 cqt_contract2_kernel(const ContractArgs a, int n_warps) {
   constexpr int TF = 32 * FPL;
-  constexpr int YS = CT2_KC * (TF + 1), GS = CT2_KC * CT2_MAXW * 16, STAGE = YS + GS;   // floats per stage
+  constexpr int YS = CT2_KC * (TF + 1);                    // floats of the Hankel tile per stage
+  const int gstride = n_warps * 16;                        // bank row pitch in shared memory = columns of this CTA
+  const int STAGE = YS + CT2_KC * gstride;                 // floats per stage (sized per launch: small banks, more CTAs per SM)
   extern __shared__ __align__(16) float ct2_smem[];   // two stages: [ys | gs] [ys | gs], filled by cp.async
   const int clip = blockIdx.z;
   const int t0 = blockIdx.x * TF;
@@ -468,7 +470,7 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
       for (int i = tid; i < CT2_KC * q_per_row; i += nthr) {
         const int kk = i / q_per_row, f = (i % q_per_row) << 2;
         const bool ok = c0 + f < a.ncol;          // ncol % 4 == 0: a vector is entirely inside or outside
-        const unsigned d = (unsigned)__cvta_generic_to_shared(gs + kk * (CT2_MAXW * 16) + f);
+        const unsigned d = (unsigned)__cvta_generic_to_shared(gs + kk * gstride + f);
         const float* g = a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0);
         const int sz = ok ? 16 : 0;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(sz) : "memory");
@@ -477,7 +479,7 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
       for (int i = tid; i < CT2_KC * ncols_cta; i += nthr) {
         const int kk = i / ncols_cta, f = i % ncols_cta;
         const bool ok = c0 + f < a.ncol;
-        cp_async4(gs + kk * (CT2_MAXW * 16) + f, a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0), ok);
+        cp_async4(gs + kk * gstride + f, a.bank + (int64_t)(n0 + kk) * a.ncol + (ok ? c0 + f : 0), ok);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -494,12 +496,12 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
     __syncthreads();
     const float* ys = ct2_smem + (c & 1) * STAGE;
     const float* gs = ys + YS;
-#pragma unroll 2
+#pragma unroll 4
     for (int kk = 0; kk < CT2_KC; ++kk) {
       float v[FPL];
 #pragma unroll
       for (int j = 0; j < FPL; ++j) v[j] = ys[kk * (TF + 1) + lane + 32 * j];
-      const float4* g4 = reinterpret_cast<const float4*>(gs + kk * (CT2_MAXW * 16) + warp * 16);
+      const float4* g4 = reinterpret_cast<const float4*>(gs + kk * gstride + warp * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 g = g4[q];
@@ -538,7 +540,7 @@ cqt_contract2_kernel(const ContractArgs a, int n_warps) {
 }
 
 template <int FPL>
-static size_t ct2_smem_bytes() { return sizeof(float) * 2 * (size_t)(CT2_KC * (32 * FPL + 1) + CT2_KC * CT2_MAXW * 16); }
+static size_t ct2_smem_bytes(int n_warps) { return sizeof(float) * 2 * (size_t)(CT2_KC * (32 * FPL + 1) + CT2_KC * n_warps * 16); }
 
 // per-clip output frame count = min over octaves of 1 + len_o // hop_o (librosa __trim_stack)
 __global__ void cqt_frames_kernel(const int64_t* clip_lens, int64_t max_len, int n_clips, int early_factor,
@@ -887,13 +889,13 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
       const int64_t waste4 = (T_max + 127) / 128 * 128, waste3 = (T_max + 95) / 96 * 96;
       if (a.n_fft % CT2_KC) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: kernel length must be a multiple of %d", CT2_KC);
       if (waste3 < waste4) {
-        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<3>()));
+        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<3>(CT2_MAXW)));
         dim3 grid((unsigned)((T_max + 95) / 96), ny, n_clips);
-        cqt_contract2_kernel<3><<<grid, n_warps * 32, ct2_smem_bytes<3>(), st>>>(a, n_warps);
+        cqt_contract2_kernel<3><<<grid, n_warps * 32, ct2_smem_bytes<3>(n_warps), st>>>(a, n_warps);
       } else {
-        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<4>()));
+        SAGA_CUDA_OK(cudaFuncSetAttribute(cqt_contract2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct2_smem_bytes<4>(CT2_MAXW)));
         dim3 grid((unsigned)((T_max + 127) / 128), ny, n_clips);
-        cqt_contract2_kernel<4><<<grid, n_warps * 32, ct2_smem_bytes<4>(), st>>>(a, n_warps);
+        cqt_contract2_kernel<4><<<grid, n_warps * 32, ct2_smem_bytes<4>(n_warps), st>>>(a, n_warps);
       }
     }
     SAGA_LAUNCH_CHECK();
