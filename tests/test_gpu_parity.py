@@ -341,6 +341,8 @@ CQT_CASES = [
     (44100, 1024, "A0", 174, 24, 66150),
     (44100, 1024, "D3", 36, 24, 66150),
     (44100, 512, "C1", 84, 12, 512 * 133 + 100),    # 134 frames: the 6-frame partial tile goes to cqt_tail_kernel
+    (44100, 1024, "A0", 348, 48, 66150),            # ref_C_4 (training.py:277): 96 columns per octave, fp32 contraction
+    (44100, 1024, "C4", 348, 192, 132300),          # bins_per_tone=16 from the note (training.py:366-381): 3 column blocks
 ]
 
 
@@ -361,7 +363,8 @@ def test_cqt_matches_oracle(saga, cfg1, sr, hop, low, n_bins, bpo, n, impl):
     assert tuple(r["mag"].shape) == (1,) + ref.shape
     # fp32 path ~1e-6; 3xTF32 ~3e-6 (tensor-core accumulation); both far inside the 1e-4 bar.
     # impl=3 (single TF32 pass) measures ~1.1e-4: NOT parity-grade, opt-in only, checked loosely.
-    tol = {1: 2e-6, 2: 1e-5, 0: 1e-5, 3: 3e-4}[impl]
+    tol = {1: 2e-6 if bpo <= 48 else 5e-6,      # 8192-sample kernels at 192 per octave: longer fp32 sums
+           2: 1e-5, 0: 1e-5, 3: 3e-4}[impl]
     check_mag(r["mag"][0].cpu().numpy(), np.abs(ref), tol=tol)
     check_mag(r["C"][0].cpu().numpy(), ref, tol=tol)
 
