@@ -719,7 +719,8 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
     // the chain ran in an earlier call (SAGA_SUB_SKIP_DB) and left every window's final max in ref_out
   } else if (flat) {
     SAGA_CUDA_OK(cudaMemsetAsync(vmax, 0, sizeof(float) * n_windows, st));
-    const int fchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, guess_frames_all), (148 * 16 + n_windows - 1) / n_windows));
+    int fchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, guess_frames_all), (148 * 16 + n_windows - 1) / n_windows));
+    if (const char* e = getenv("SAGA_SUB_FLAT_CHUNKS")) fchunks = std::max(1, std::min(std::max(1, guess_frames_all), atoi(e)));   // tuning aid
     subtract_single_flat_kernel<<<(unsigned)((int64_t)n_windows * fchunks), SF_THREADS, 0, st>>>(a, vmax, fchunks);
     SAGA_LAUNCH_CHECK();
   } else if (vec) {
@@ -740,7 +741,12 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
     // 600 windows = 6.05 TB/s, profiles/microbench/db_lean_sweep_b200.txt); SAGA_DB_LEAN=0 restores the shallow kernel
     const char* lean = getenv("SAGA_DB_LEAN");
     const int lv = lean ? atoi(lean) : 4;
-    if (vec && lv > 0) chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames, (148 * 32 + n_windows - 1) / n_windows));
+    if (vec && lv > 0) {
+      // one deep batch per thread: a CTA takes as many whole rows as 256 threads x 12 vectors cover (11 rows of 1028
+      // floats -> 47 chunks of a 516-frame window; the step measures 2.908 ms at 48-64 chunks, 2.950 at 8, 2.97 at 96)
+      const int rows_per_cta = (int)std::max<int64_t>(1, (256 * 12) / std::max<int64_t>(1, frame_pitch >> 2));
+      chunks = std::max(1, (n_frames + rows_per_cta - 1) / rows_per_cta);
+    }
     if (const char* e = getenv("SAGA_DB_CHUNKS")) chunks = std::max(1, std::min(n_frames, atoi(e)));
     const int64_t blocks = (int64_t)n_windows * chunks, lblocks = blocks;
 #define SAGA_DBL(T, U) window_db_lean_kernel<T, U><<<(unsigned)lblocks, T, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins, n_frames, frame_pitch, amin, top_db, chunks)
