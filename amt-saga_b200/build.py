@@ -25,18 +25,34 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libsaga_b200.so (sm_100a). Returns the path."""
+    """Compile csrc/*.cu into libsaga_b200.so (sm_100a). Returns the path.
+    The translation units are compiled in parallel (host-only linkage between them), then linked."""
     if not force and not _stale():
         return LIB
+    import concurrent.futures
+    import tempfile
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libsaga_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-lcuda")]
+    with tempfile.TemporaryDirectory(prefix="saga_build_") as tmp:
+        def one(src):
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + \
+                ["-c", os.path.join(CSRC, src), "-o", obj]
+            return obj, subprocess.run(cmd, capture_output=True, text=True)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(one, SOURCES))
+        for obj, res in results:
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed building libsaga_b200.so")
+            if verbose:
+                sys.stderr.write(res.stderr)
+        link = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + \
+            [obj for obj, _ in results] + ["-lcuda"]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking libsaga_b200.so")
     return LIB
 
 
