@@ -6,8 +6,9 @@ arithmetic step is a call into libsaga_b200.so.  Tensors returned as
 ([..., frames, pitch], bins contiguous) -- i.e. Fortran order, the layout
 librosa.stft itself returns.
 """
+import contextlib
 import ctypes as C
-import functools
+import os
 
 import numpy as np
 import torch
@@ -20,8 +21,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t=None):
+    """The current stream OF THE TENSOR'S DEVICE (not of whichever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(None if t is None else t.device).cuda_stream)
+
+
+def _dev_index(device=None):
+    if device is None:
+        return torch.cuda.current_device()
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+@contextlib.contextmanager
+def _on(t, plan=None):
+    """Make the tensor's device current for the allocations and the launch inside, and refuse a plan whose
+    tables live on another device (kernels would read foreign pointers)."""
+    if plan is not None and getattr(plan, "device_index", None) not in (None, t.device.index):
+        raise ValueError("plan was created for cuda:%d but the data is on %s; use get_*_plan(..., device=...)"
+                         % (plan.device_index, t.device))
+    with torch.cuda.device(t.device):
+        yield
 
 
 def _require_cuda(t, name):
@@ -53,7 +73,7 @@ def storage_of(view):
 # K1 / K4 plans
 # ---------------------------------------------------------------------------
 class StftPlan:
-    def __init__(self, n_fft, hop_length, center=True, window=None):
+    def __init__(self, n_fft, hop_length, center=True, window=None, device=None):
         self.n_fft, self.hop, self.center = int(n_fft), int(hop_length), bool(center)
         self.n_bins = self.n_fft // 2 + 1
         win = None
@@ -63,8 +83,10 @@ class StftPlan:
                 raise ValueError("window must have n_fft entries")
             win = w.ctypes.data_as(C.c_void_p)
         h = C.c_void_p()
-        _lib.check(_lib.lib().saga_stft_plan_create(C.byref(h), self.n_fft, self.hop,
-                                                    int(self.center), win))
+        self.device_index = _dev_index(device)
+        with torch.cuda.device(self.device_index):      # the plan's tables are allocated on the current device
+            _lib.check(_lib.lib().saga_stft_plan_create(C.byref(h), self.n_fft, self.hop,
+                                                        int(self.center), win))
         self._h = h
 
     @property
@@ -87,14 +109,45 @@ class StftPlan:
             pass
 
 
-@functools.lru_cache(maxsize=32)
-def get_stft_plan(n_fft, hop_length, center=True):
-    return StftPlan(n_fft, hop_length, center)
+# Plan cache.  A plan owns device tables, so the key carries the DEVICE it was built on and the PROCESS that
+# built it: a worker forked by the reference's `Pool(...)` (training.py:623) must not reuse (or destroy) handles
+# that belong to its parent's CUDA context.
+_plans = {}
+_tables = {}
 
 
-@functools.lru_cache(maxsize=64)
-def get_cqt_plan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=2):
-    return CqtPlan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=filter_scale)
+def _forget_foreign(cache):
+    pid = os.getpid()
+    for k in [k for k in cache if k[0] != pid]:
+        v = cache.pop(k)
+        if hasattr(v, "_h"):
+            v._h = None          # never call *_destroy on another process's handle
+
+
+def _cached_plan(key, device, make):
+    idx = _dev_index(device)
+    k = (os.getpid(), idx) + key
+    plan = _plans.get(k)
+    if plan is None:
+        _forget_foreign(_plans)
+        plan = make(idx)
+        _plans[k] = plan
+    return plan
+
+
+def get_stft_plan(n_fft, hop_length, center=True, device=None):
+    return _cached_plan(("stft", int(n_fft), int(hop_length), bool(center)), device,
+                        lambda idx: StftPlan(n_fft, hop_length, center, device=idx))
+
+
+def get_cqt_plan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=2, device=None):
+    def make(idx):
+        with torch.cuda.device(idx):
+            plan = CqtPlan(sr, hop_length, fmin, n_bins, bins_per_octave, filter_scale=filter_scale)
+        plan.device_index = idx
+        return plan
+    return _cached_plan(("cqt", sr, int(hop_length), float(fmin), int(n_bins), int(bins_per_octave), filter_scale),
+                        device, make)
 
 
 def _clip_table(wav, lens):
@@ -107,6 +160,19 @@ def _clip_table(wav, lens):
     if wav.dim() != 2 or wav.stride(1) != 1:
         wav = wav.contiguous()
     n_clips, width = wav.shape
+    if lens is None:
+        # the offset / length tables of a dense batch depend on its geometry only: built once per
+        # (process, device, geometry) instead of three torch launches per call
+        key = (os.getpid(), wav.device.index, n_clips, wav.stride(0), width)
+        tab = _tables.get(key)
+        if tab is None:
+            _forget_foreign(_tables)
+            if len(_tables) > 256:
+                _tables.clear()
+            tab = (torch.arange(n_clips, device=wav.device, dtype=torch.int64) * wav.stride(0),
+                   torch.full((n_clips,), width, device=wav.device, dtype=torch.int64))
+            _tables[key] = tab
+        return wav, tab[0], tab[1], width
     offs = torch.arange(n_clips, device=wav.device, dtype=torch.int64) * wav.stride(0)
     if lens is None:
         max_len = width
@@ -138,9 +204,10 @@ def stft_batch(wav, plan, lens=None, want_phase=False, want_complex=False, want_
     cx = alloc((n_clips, T, P, 2), device=dev, dtype=torch.float32) if want_complex else None
     fmax = alloc((n_clips, max(T, 1)), device=dev, dtype=torch.float32) if want_max else None
     cmax = torch.zeros((n_clips,), device=dev, dtype=torch.float32) if want_max else None
-    _lib.check(_lib.lib().saga_stft_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev), n_clips,
-                                         max_len, _ptr(mag), _ptr(ph), _ptr(cx), P, T * P,
-                                         _ptr(fmax), _ptr(cmax), _stream()))
+    with _on(wav, plan):
+        _lib.check(_lib.lib().saga_stft_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev), n_clips,
+                                             max_len, _ptr(mag), _ptr(ph), _ptr(cx), P, T * P,
+                                             _ptr(fmax), _ptr(cmax), _stream(wav)))
     out = {"mag": bins_frames_view(mag, plan.n_bins), "mag_storage": mag}
     if want_phase:
         out["phase_storage"] = torch.view_as_complex(ph)
@@ -187,8 +254,9 @@ def istft_batch(plan, F=None, mag=None, phase=None, n_bins=None):
     cstride = s.stride(0) if n_clips > 1 else T * pitch
     out_len = plan.hop * (T - 1) + (0 if plan.center else plan.n_fft)
     wav = torch.empty((n_clips, max(out_len, 0)), device=s.device, dtype=torch.float32)
-    _lib.check(_lib.lib().saga_istft_exec(plan.handle, args[0], args[1], args[2], n_clips, T, pitch,
-                                          cstride, _ptr(wav), wav.stride(0), _stream()))
+    with _on(s, plan):
+        _lib.check(_lib.lib().saga_istft_exec(plan.handle, args[0], args[1], args[2], n_clips, T, pitch,
+                                              cstride, _ptr(wav), wav.stride(0), _stream(s)))
     return wav
 
 
@@ -199,7 +267,7 @@ _workspaces = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    key = (os.getpid(), device.index if device.index is not None else torch.cuda.current_device())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
@@ -226,10 +294,11 @@ def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0, fill=None):
             cx.fill_(fill)
     nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
     ws = _workspace(nbytes, dev)
-    _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev) if lens is not None else None,
-                                 n_clips, max_len,
-                                 _ptr(mag), _ptr(cx), P, T * P, _ptr(ws), ws.numel(), impl, _stream()),
-               ParameterError)
+    with _on(wav, plan):
+        _lib.check(lib.saga_cqt_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev) if lens is not None else None,
+                                     n_clips, max_len,
+                                     _ptr(mag), _ptr(cx), P, T * P, _ptr(ws), ws.numel(), impl, _stream(wav)),
+                   ParameterError)
     out = {"mag": bins_frames_view(mag, plan.n_bins), "mag_storage": mag}
     if want_complex:
         out["C"] = bins_frames_view(torch.view_as_complex(cx), plan.n_bins)
@@ -282,11 +351,12 @@ def subtract_db_batch(win, guesses, offset_frames, n_bins, overkill=None, guess_
         fm_stride = frame_max.stride(0)
     ref = torch.empty((W,), device=win.device, dtype=torch.float32)
     flags = (_lib.SUB_NORMALIZE if normalize else 0) | (_lib.SUB_RELU if relu else 0)
-    _lib.check(_lib.lib().saga_subtract_db_exec(
-        _ptr(win), None, win.stride(0) if W > 1 else T * P, _ptr(guesses), None,
-        Tg * P, _ptr(guess_frames), Tg, _ptr(offset_frames), _ptr(overkill), _ptr(guess_ref),
-        _ptr(ref_init), _ptr(frame_max), fm_stride, flags, _ptr(D), _ptr(ref), W, S, n_bins, T, P,
-        float(amin), float(top_db if top_db is not None else -1.0), _stream()))
+    with _on(win):
+        _lib.check(_lib.lib().saga_subtract_db_exec(
+            _ptr(win), None, win.stride(0) if W > 1 else T * P, _ptr(guesses), None,
+            Tg * P, _ptr(guess_frames), Tg, _ptr(offset_frames), _ptr(overkill), _ptr(guess_ref),
+            _ptr(ref_init), _ptr(frame_max), fm_stride, flags, _ptr(D), _ptr(ref), W, S, n_bins, T, P,
+            float(amin), float(top_db if top_db is not None else -1.0), _stream(win)))
     return D, ref
 
 
@@ -304,9 +374,10 @@ def amplitude_to_db_batch(mag_storage, n_bins, ref=None, amin=1e-5, top_db=80.0)
     D = torch.empty_strided(m.shape, m.stride(), device=m.device, dtype=torch.float32)
     if ref is not None:
         ref = ref.to(device=m.device, dtype=torch.float32).contiguous()
-    _lib.check(_lib.lib().saga_amplitude_to_db_exec(
-        _ptr(m), _ptr(D), _ptr(ref), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P,
-        float(amin), float(top_db if top_db is not None else -1.0), _stream()))
+    with _on(m):
+        _lib.check(_lib.lib().saga_amplitude_to_db_exec(
+            _ptr(m), _ptr(D), _ptr(ref), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P,
+            float(amin), float(top_db if top_db is not None else -1.0), _stream(m)))
     return D
 
 
@@ -327,8 +398,9 @@ def pcm16_absmax(pcm, channel_stride=1, out=None):
         return out
     if n == 0:
         return out.zero_()
-    _lib.check(_lib.lib().saga_pcm16_absmax_exec(_ptr(pcm), pcm.stride(0), channel_stride, n_clips, n,
-                                                 _ptr(out), _stream()))
+    with _on(pcm):
+        _lib.check(_lib.lib().saga_pcm16_absmax_exec(_ptr(pcm), pcm.stride(0), channel_stride, n_clips, n,
+                                                     _ptr(out), _stream(pcm)))
     return out
 
 
@@ -364,9 +436,10 @@ def pcm16_to_wave(pcm, mul=1.0, div=32768.0, channel_stride=1, out=None):
     for t in (mul_t, div_t, peak_t):
         if t is not None and t.shape != (n_clips,):
             raise ValueError("per-clip scales must be [clips]")
-    _lib.check(_lib.lib().saga_pcm16_ingest_exec(_ptr(pcm), pcm.stride(0), channel_stride, _ptr(out), out.stride(0),
-                                                 n_clips, n, _ptr(mul_t), _ptr(div_t), _ptr(peak_t),
-                                                 mul_all, div_all, _stream()))
+    with _on(pcm):
+        _lib.check(_lib.lib().saga_pcm16_ingest_exec(_ptr(pcm), pcm.stride(0), channel_stride, _ptr(out), out.stride(0),
+                                                     n_clips, n, _ptr(mul_t), _ptr(div_t), _ptr(peak_t),
+                                                     mul_all, div_all, _stream(pcm)))
     return out
 
 
@@ -394,9 +467,10 @@ def compress_bands_batch(mag_storage, n_bins, edges, inv_scale=None):
     out = torch.empty((n_clips, T, Pb), device=m.device, dtype=torch.float32)
     if inv_scale is not None:
         inv_scale = inv_scale.to(device=m.device, dtype=torch.float32).contiguous()
-    _lib.check(_lib.lib().saga_compress_bands_exec(
-        _ptr(m), _ptr(out), edges.ctypes.data_as(C.c_void_p), n_bands, n_clips, T, P,
-        m.stride(0) if n_clips > 1 else T * P, Pb, T * Pb, _ptr(inv_scale), _stream()))
+    with _on(m):
+        _lib.check(_lib.lib().saga_compress_bands_exec(
+            _ptr(m), _ptr(out), edges.ctypes.data_as(C.c_void_p), n_bands, n_clips, T, P,
+            m.stride(0) if n_clips > 1 else T * P, Pb, T * Pb, _ptr(inv_scale), _stream(m)))
     return out
 
 
@@ -436,9 +510,10 @@ def short_window_features(mag_st, phase_st, src_frames, band_min, n_rows, n_bins
         if phase_st is None or phase_st.stride(0) != mag_st.stride(0):
             raise ValueError("phase storage must match the magnitude storage")
         ph_ptr = _ptr(torch.view_as_real(phase_st))
-    _lib.check(_lib.lib().saga_short_window_exec(
-        _ptr(mag_st), ph_ptr, _ptr(src), n_cols, int(band_min), int(n_rows), int(n_bins), P, float(inv_ref),
-        _ptr(lin), _ptr(log), _ptr(pha), Po, _stream()))
+    with _on(mag_st):
+        _lib.check(_lib.lib().saga_short_window_exec(
+            _ptr(mag_st), ph_ptr, _ptr(src), n_cols, int(band_min), int(n_rows), int(n_bins), P, float(inv_ref),
+            _ptr(lin), _ptr(log), _ptr(pha), Po, _stream(mag_st)))
     view = lambda x: None if x is None else x[:, :n_rows].transpose(0, 1)
     return {"lin": view(lin), "log": view(log), "phase": view(pha)}
 
@@ -450,6 +525,7 @@ def spectral_flatness_batch(mag_storage, n_bins, amin=1e-10):
     n_clips, T, _ = m.shape
     P = m.stride(1) if T > 1 else m.shape[2]
     out = torch.empty((n_clips, T), device=m.device, dtype=torch.float32)
-    _lib.check(_lib.lib().saga_spectral_flatness_exec(
-        _ptr(m), _ptr(out), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P, float(amin), _stream()))
+    with _on(m):
+        _lib.check(_lib.lib().saga_spectral_flatness_exec(
+            _ptr(m), _ptr(out), n_clips, n_bins, T, P, m.stride(0) if n_clips > 1 else T * P, float(amin), _stream(m)))
     return out

@@ -29,9 +29,11 @@ class WindowFeaturePipeline:
                  n_fft=2048, hop=512, cqt_lowest="C1", cqt_bins=84, cqt_bpo=12, n_frames=None,
                  device=None, cqt_impl=0):
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.W, self.ns, self.ng, self.sr = n_windows, window_samples, guess_samples, sr
-        self.stft = ops.get_stft_plan(n_fft, hop, True)
-        self.cqt = ops.get_cqt_plan(sr, hop, note_to_hz(cqt_lowest), cqt_bins, cqt_bpo, 2)
+        self.stft = ops.get_stft_plan(n_fft, hop, True, device=self.dev)
+        self.cqt = ops.get_cqt_plan(sr, hop, note_to_hz(cqt_lowest), cqt_bins, cqt_bpo, 2, device=self.dev)
         self.cqt_impl = cqt_impl
         self.nb = self.stft.n_bins
         self.P = ops.frame_pitch(self.nb)
@@ -81,7 +83,16 @@ class WindowFeaturePipeline:
     def cqt_flops_per_window(self):
         return self.Tc * sum(8 * o["n_filters"] * (o["n_fft"] // 2 + 1) for o in self.cqt.octaves)
 
-    def run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None, overlap=True, parts=("stft", "cqt")):
+    def run(self, *args, **kwargs):
+        """See `_run`; executed with the pipeline's device current (plans, buffers and streams live there)."""
+        with torch.cuda.device(self.dev):
+            return self._run(*args, **kwargs)
+
+    def run_host(self, *args, **kwargs):
+        with torch.cuda.device(self.dev):
+            return self._run_host(*args, **kwargs)
+
+    def _run(self, wav, guess_wav, offset_frames, events=None, w0=0, w1=None, overlap=True, parts=("stft", "cqt")):
         """wav [W, window_samples], guess_wav [W, guess_samples] CUDA float32 contiguous,
         offset_frames [W,1] int32 CUDA.  Results land in self.mag (subtracted,
         in place), self.D, self.C, self.ref.  `events`: optional list that
@@ -98,7 +109,7 @@ class WindowFeaturePipeline:
         w1 = self.W if w1 is None else w1
         p = lambda t: C.c_void_p(t[w0:].data_ptr())
         q = lambda t: C.c_void_p(t.data_ptr())
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(main.cuda_stream)
         lib, W = self._lib, w1 - w0
         fork = overlap and events is None and self.schedule != "serial"
@@ -201,7 +212,7 @@ class WindowFeaturePipeline:
                 d_peak=torch.empty((2, self.W), device=d, dtype=torch.int32))
         return h
 
-    def run_host(self, chunks=6, pcm16=False):
+    def _run_host(self, chunks=6, pcm16=False):
         """Pinned host inputs -> device -> hot path -> features back on the host
         (CQT magnitudes + post-subtraction ref_mag; the subtracted window and its dB
         image stay resident for the next loop iteration, as in training.py:449).
@@ -218,7 +229,7 @@ class WindowFeaturePipeline:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
             self._last_compute = None
         s_in, s_cmp, s_out = self._streams
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.dev)
         start = torch.cuda.Event()
         start.record(cur)
         s_in.wait_event(start)
@@ -248,7 +259,7 @@ class WindowFeaturePipeline:
                     for k, (src, dst) in enumerate((("d_wav_pcm", "d_wav"), ("d_guess_pcm", "d_guess"))):
                         peak = ops.pcm16_absmax(h[src][a:b], out=h["d_peak"][k, a:b])
                         ops.pcm16_to_wave(h[src][a:b], mul=h["d_mul"][k, a:b], div=peak, out=h[dst][a:b])
-                self.run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
+                self._run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
                 e2 = torch.cuda.Event()
                 e2.record(s_cmp)
                 ev_cmp.append(e2)

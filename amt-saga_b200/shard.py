@@ -40,17 +40,36 @@ def gather_ragged(local, group=None):
     return torch.cat([o[:s] for o, s in zip(out, sizes)])
 
 
-def run_sharded(n_windows, compute_fn, chunk_size=600, group=None):
+def run_sharded(n_windows, compute_fn, chunk_size=600, group=None, device=None, dtype=torch.float32,
+                require_full_chunks=False):
     """Each rank runs `compute_fn(first_id, last_id) -> 1-D tensor of per-window
     results` over its block in chunks; results are gathered in window order on
-    every rank.  With torch.distributed uninitialised this is a single shard."""
+    every rank.  With torch.distributed uninitialised this is a single shard.
+
+    `device` / `dtype`: where an EMPTY shard's placeholder lives (a rank that owns no window must
+    still join the gather with a tensor of the right device and dtype).  `require_full_chunks`:
+    validate ON EVERY RANK, before any compute, that every shard is a whole number of chunks --
+    a compute_fn with preallocated buffers that raised on a ragged last chunk on some ranks only
+    would leave the others hanging in the collective."""
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
+    if require_full_chunks:
+        for r in range(world):
+            a, b = shard_range(n_windows, r, world)
+            if (b - a) % chunk_size:
+                raise ValueError("shard of rank %d has %d windows: not a multiple of chunk_size %d "
+                                 "(pad the corpus or pick a divisor)" % (r, b - a, chunk_size))
     lo, hi = shard_range(n_windows, rank, world)
     parts = [compute_fn(a, b) for a, b in chunks(lo, hi, chunk_size)]
-    local = torch.cat(parts) if parts else torch.zeros(0)
+    if parts:
+        local = torch.cat(parts)
+    else:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and \
+                world > 1 and dist.get_backend(group) == "nccl" else torch.device("cpu")
+        local = torch.zeros(0, device=device, dtype=dtype)
     return gather_ragged(local, group) if world > 1 else local
 
 

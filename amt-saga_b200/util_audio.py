@@ -57,7 +57,10 @@ def midi_to_note(midi):
 def _device(device=None):
     if not torch.cuda.is_available():
         raise RuntimeError("amt_saga_b200 needs a CUDA device: there is no CPU fallback")
-    return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if d.type != "cuda":
+        raise RuntimeError("amt_saga_b200 needs a CUDA device: there is no CPU fallback")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
 
 
 class _Spec:
@@ -148,7 +151,7 @@ class audio_complete:
         return x.detach().cpu().numpy()
 
     def _plan(self):
-        return ops.get_stft_plan(int(self.N), int(self.hl), bool(self.center))
+        return ops.get_stft_plan(int(self.N), int(self.hl), bool(self.center), device=self._dev)
 
     def _analyse(self):
         """K1 on the waveform: fills mag and ph (and the max by-product)."""
@@ -457,7 +460,7 @@ class audio_complete:
 
     def spectral_flatness(self):
         """util_audio.py:330-332 (librosa.feature.spectral_flatness, power 2, amin 1e-10)."""
-        plan = ops.get_stft_plan(int(self.N), int(self.hl), True)
+        plan = ops.get_stft_plan(int(self.N), int(self.hl), True, device=self._dev)
         r = ops.stft_batch(self._wave(), plan, want_max=False)
         flat = ops.spectral_flatness_batch(r["mag_storage"], plan.n_bins)
         return float(flat.double().mean().item())
@@ -517,7 +520,7 @@ class audio_complete:
             nbins = int((note_to_midi(highest_note) - note_to_midi(lowest_note)) * bins_per_tone)
         wav = self._wave()
         plan = ops.get_cqt_plan(self.sr, int(self.hl), note_to_hz(lowest_note), int(nbins),
-                                int(12 * bins_per_tone), 2)
+                                int(12 * bins_per_tone), 2, device=self._dev)
         plan.check_length(int(wav.numel()))
         r = ops.cqt_batch(wav, plan, want_complex=not magnitude_only)
         C = r["mag"][0] if magnitude_only else r["C"][0]

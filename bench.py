@@ -43,53 +43,64 @@ def guess_offsets(n_windows, seed=7):
 
 # ----------------------------------------------------------------------------- CPU reference arm
 _BLAS_LIMIT = None
+_CPU_INPUTS = None      # [(window wave, guess wave, onset seconds)], filled in the parent BEFORE the timer / the fork
 
 
-def _cpu_window(args):
-    """One window-feature on the CPU through the oracle (the reference's algorithm)."""
-    seed, off = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+def _cpu_class():
+    """The class that plays `util_audio.audio_complete` on the CPU arm: the reference's own class when
+    /root/reference is mounted (build container), else `AudioOracle`, which tests/test_ref_class.py proves
+    bit-identical to it on the producer loop.  librosa / resampy underneath are the numpy restatement in both."""
+    from oracle import ref_class
+    if ref_class.available():
+        return ref_class.load().audio_complete, "reference"
+    from oracle.audio_oracle import AudioOracle
+    return AudioOracle, "port"
+
+
+def cpu_prepare(n_windows, seed0=50000):
+    """Synthesise the CPU arm's inputs (same generator and seeds as the GPU arm).  NOT timed: the GPU arm
+    synthesises outside its timed region too."""
+    global _CPU_INPUTS
+    from tests.synth import piano_clip
+    rng = np.random.default_rng(7)
+    onsets = rng.uniform(0, 6.0, n_windows)
+    _CPU_INPUTS = [(piano_clip(seed0 + i, WIN_SAMPLES), piano_clip(90000 + seed0 + i, GUESS_SAMPLES, n_notes=1),
+                    float(onsets[i])) for i in range(n_windows)]
+
+
+def _cpu_window(i):
+    """One window-feature on the CPU, through the reference's class interface (util_audio.py:32):
+    STFT magnitude, CQT 84/12, one guessed-note subtraction, dB.  Returns the seconds of compute."""
     global _BLAS_LIMIT
-    if _BLAS_LIMIT is None:      # numpy is already imported: pin its BLAS / OpenMP pools to ONE thread per process,
-        try:                     # so that `cores` in the JSON line is the number of threads actually used
+    if _BLAS_LIMIT is None:      # one BLAS / OpenMP thread per process: `cores` = threads actually used
+        try:
             from threadpoolctl import threadpool_limits
             _BLAS_LIMIT = threadpool_limits(limits=1)
         except Exception:
             _BLAS_LIMIT = False
-    from oracle import cqt as ocqt, spectral as osp
-    from tests.synth import piano_clip
-    y = piano_clip(seed, WIN_SAMPLES)
-    g = piano_clip(90000 + seed, GUESS_SAMPLES, n_notes=1)
+    AC, _ = _cpu_class()
+    y, g, onset = _CPU_INPUTS[i]
+    T = WIN_SAMPLES // HOP
     t0 = time.perf_counter()
-    mag_full = np.abs(osp.stft(y, N_FFT, HOP))
-    song_ref = mag_full.max()
-    mag = mag_full[:, : WIN_SAMPLES // HOP].copy()
-    C = np.abs(ocqt.cqt(y, sr=SR, hop_length=HOP, fmin=osp.note_to_hz("C1"), n_bins=84,
-                        bins_per_octave=12, filter_scale=2))
-    gm = np.abs(osp.stft(g, N_FFT, HOP))
-    gm = gm * (song_ref / gm.max())
-    T = mag.shape[1]
-    gm = gm[:, : T - off]
-    mag[:, off:off + gm.shape[1]] -= gm
-    np.maximum(mag, 0, mag)
-    D = osp.amplitude_to_db(mag, ref=mag.max())
-    return time.perf_counter() - t0, float(C.sum() + D.sum())
+    song = AC(y, N_FFT, hop_length=HOP, sample_rate=SR)
+    song.mag                                                          # util_audio.py:147 (STFT + magphase)
+    C = song.slice_C(0, song._frames_to_seconds(song.shape[1]), song.shape[1], bins_per_tone=1,
+                     lowest_note="C1", nbins=84)                      # util_audio.py:411-434 (CQT 84/12, fs 2)
+    w = song.section(0, None, T)                                      # the 516-frame window (training.py:284)
+    w.subtract(AC(g, N_FFT, hop_length=HOP, sample_rate=SR), offset=onset)   # util_audio.py:221-259
+    D = w.D                                                           # util_audio.py:176-180
+    return time.perf_counter() - t0, float(C[0, 0] + D[0, 0])
 
 
-def cpu_sample(n_windows, procs, pool=None):
-    offs = guess_offsets(n_windows)[:, 0]
-    jobs = [(50000 + i, int(offs[i])) for i in range(n_windows)]
+def cpu_sample(n_windows, pool=None):
+    """windows/s over `n_windows` prepared windows (wall clock of the compute only; inputs are resident)."""
     t0 = time.perf_counter()
     if pool is not None:
-        pool.map(_cpu_window, jobs, chunksize=1)
-    elif procs > 1:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(procs) as p:
-            p.map(_cpu_window, jobs, chunksize=1)
+        inner = pool.map(_cpu_window, range(n_windows), chunksize=1)
     else:
-        for j in jobs:
-            _cpu_window(j)
-    return n_windows / (time.perf_counter() - t0)
+        inner = [_cpu_window(i) for i in range(n_windows)]
+    wall = time.perf_counter() - t0
+    return n_windows / wall, wall, sum(t for t, _ in inner)
 
 
 def run_reference(args):
@@ -98,31 +109,42 @@ def run_reference(args):
         return
     os.environ["OMP_NUM_THREADS"] = "1"
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    per_step = procs                       # one window per worker per step
-    _cpu_window((1, 10))                   # import / table warm-up in the parent (inherited by the forked workers)
+    per_step = procs                       # one window per worker per step: a bounded sample of the 600-window step
+    _, kind = _cpu_class()
+    cpu_prepare(per_step)                  # inputs synthesised here, before the fork and before any timer
+    _cpu_window(0)                         # import / table warm-up in the parent (inherited by the forked workers)
     # ONE pool for the whole run, like the reference's Pool(synth_worker_count) (training.py:623): worker
     # start-up is not part of a step
+    busy = 0.0
     with mp.get_context("fork").Pool(procs) as pool:
         for _ in range(max(args.warmup, 1)):
-            cpu_sample(per_step, procs, pool)
+            cpu_sample(per_step, pool)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_sample(per_step, procs, pool)
+            busy += cpu_sample(per_step, pool)[2]
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = "%d windows/step (1 per worker, %d workers) x %d steps of the same 6 s window workload" % (
-        per_step, procs, args.steps)
+    sample = ("%d of the step's 6 s windows per step (1 per worker, %d single-threaded workers = the box's usable logical "
+              "CPUs) x %d steps; inputs synthesised before the timer; %.2f s of compute per window inside a worker, "
+              "%.1f workers busy on average" % (per_step, procs, args.steps, busy / (per_step * args.steps), busy / dt))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "window-features/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "windows_per_step": per_step,
-                   "note": "reference cannot be imported here (librosa/magenta/fluidsynth absent): "
-                           "oracle port of its librosa-0.6.3 path, multiprocessing.Pool like training.py:623"},
-        "cpu_baseline": {"value": value, "unit": "window-features/s", "cores": procs, "kind": "port",
+                   "note": "the reference's audio_complete interface (util_audio.py:32) on the CPU: "
+                           + ("its own class imported from /root/reference (oracle/ref_class.py)" if kind == "reference" else
+                              "AudioOracle, bit-identical to the reference's class (tests/test_ref_class.py; /root/reference "
+                              "is not on this box)")
+                           + " over the numpy restatement of librosa 0.6.3 / resampy (not installable here), under one "
+                             "multiprocessing.Pool like training.py:623"},
+        "cpu_baseline": {"value": value, "unit": "window-features/s", "cores": procs, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "window-features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -386,10 +408,12 @@ def run_saga(args):
 
     cpu = None
     if world == 1 and args.cpu_windows > 0:
-        v = cpu_sample(args.cpu_windows, 1)
-        cpu = {"value": v, "unit": "window-features/s", "cores": 1, "kind": "port",
-               "sample": "%d of the same 6 s windows through the numpy oracle (librosa-0.6.3 restatement), 1 process"
-                         % args.cpu_windows}
+        cpu_prepare(args.cpu_windows)          # synthesis is outside the timer, as on the GPU arm
+        _cpu_window(0)
+        v, wall, _ = cpu_sample(args.cpu_windows)
+        cpu = {"value": v, "unit": "window-features/s", "cores": 1, "kind": _cpu_class()[1],
+               "sample": "%d of the step's 6 s windows through the reference's audio_complete interface on the numpy "
+                         "restatement of librosa 0.6.3, 1 process, 1 thread, inputs resident (%.1f s)" % (args.cpu_windows, wall)}
     line = {
         "metric": METRIC, "value": value, "unit": "window-features/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -434,7 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="saga", choices=["saga", "reference"])
     ap.add_argument("--windows", type=int, default=600, help="6 s windows per GPU per step (600 = 1 h)")
-    ap.add_argument("--cpu-windows", type=int, default=12, help="windows in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu-windows", type=int, default=48, help="windows in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cqt-impl", type=int, default=0)
     ap.add_argument("--e2e-chunks", type=int, default=12, help="window chunks for H2D/compute/D2H overlap")

@@ -291,14 +291,18 @@ class AudioOracle:
     @staticmethod
     def compress_bands(spectrum, bands=80, log=True):  # util_audio.py:436-466
         out = np.zeros((bands, spectrum.shape[1]))
+        # the reference averages one 1-D column slice at a time (util_audio.py:458-465); numpy's
+        # float32 summation order depends on that, so the oracle keeps the same granularity
         if log:
             ind = band_edges(spectrum.shape[0], bands)
-            for i in range(bands):
-                out[i] = np.mean(spectrum[int(ind[i]):int(ind[i + 1]), :], axis=0)
+            lo, hi = [int(v) for v in ind[:-1]], [int(v) for v in ind[1:]]
         else:
             r = spectrum.shape[0] // bands
+            lo, hi = [r * i for i in range(bands)], [r * (i + 1) for i in range(bands)]
+        for j in range(spectrum.shape[1]):
+            col = spectrum[:, j]
             for i in range(bands):
-                out[i] = np.mean(spectrum[r * i : r * (i + 1), :], axis=0)
+                out[i, j] = np.mean(col[lo[i]:hi[i]])
         return out
 
     def resize(self, start, duration, target_frame_count, attribs=("F",)):  # :469-507

@@ -438,7 +438,7 @@ def test_cqt_fused_cascade_is_bit_identical_to_level_by_level(saga, sr, hop, low
     check_mag(out["fused"][0][0][2][:, :ref.shape[1]], ref)
 
 
-def test_cqt_tensor_path_without_shared_bank():
+def test_cqt_tensor_path_without_shared_bank(saga):
     """Plans whose octave banks are not multiples of one another keep octave-major tiles and swap the
     resident bank with a bulk copy per octave; force that path (the plan reads the switch at creation)."""
     import subprocess, sys, os

@@ -40,7 +40,7 @@ def _worker(rank, world, port, n_windows, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_windows", [10, 11])
+@pytest.mark.parametrize("n_windows", [10, 11, 1])   # 1: rank 1 owns an EMPTY shard and still joins the gather
 def test_run_sharded_two_ranks_gloo(tmp_path, n_windows):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -54,3 +54,16 @@ def test_run_sharded_two_ranks_gloo(tmp_path, n_windows):
         seen += [i for a, b in d["calls"] for i in range(a, b)]
         assert all(b - a <= 4 for a, b in d["calls"])
     assert sorted(seen) == list(range(n_windows))     # no window computed twice / skipped
+
+
+def test_run_sharded_validates_chunking_on_every_rank_before_computing():
+    """A ragged last chunk must be refused before any rank computes (otherwise the ranks whose shard is
+    fine would hang in the gather while another raised)."""
+    ran = []
+    with pytest.raises(ValueError, match="not a multiple of chunk_size"):
+        shard.run_sharded(10, lambda a, b: ran.append((a, b)), chunk_size=4, require_full_chunks=True)
+    assert ran == []
+    out = shard.run_sharded(8, lambda a, b: torch.arange(a, b, dtype=torch.float32), chunk_size=4,
+                            require_full_chunks=True)
+    assert torch.equal(out, torch.arange(8, dtype=torch.float32))
+    assert shard.run_sharded(0, lambda a, b: None).numel() == 0
