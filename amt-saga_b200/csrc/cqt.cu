@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets,
                 int64_t in_stride, const int64_t* __restrict__ clip_lens, int64_t max_len, int in_shift,
                 int in_factor_total, float* __restrict__ out, int64_t out_stride,
-                const float* __restrict__ taps, int n_taps, int factor) {
+                const float* __restrict__ taps, int n_taps, int factor, int per_thread = DEC_PER_THREAD) {
   extern __shared__ float sm[];
   const int S = n_taps - 1;
   float* tp = sm;                 // n_taps
@@ -46,7 +46,7 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   for (int s = 0; s < in_shift; ++s) len = (len + 1) >> 1;                        // halvings
   const int64_t n_full = len / factor;
   const int64_t n_out = (len + factor - 1) / factor;
-  const int tile_out = DEC_THREADS * DEC_PER_THREAD;
+  const int tile_out = DEC_THREADS * per_thread;
   const int64_t o0 = (int64_t)blockIdx.x * tile_out;
   if (o0 >= n_out) return;
   const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
@@ -62,8 +62,7 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   }
   __syncthreads();
   float* y = out + (int64_t)clip * out_stride;
-#pragma unroll
-  for (int u = 0; u < DEC_PER_THREAD; ++u) {
+  for (int u = 0; u < per_thread; ++u) {
     const int lo = threadIdx.x + u * DEC_THREADS;
     const int64_t o = o0 + lo;
     if (o >= n_out) break;
@@ -80,8 +79,8 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   }
 }
 
-static size_t decimate_smem_bytes(int n_taps, int factor) {
-  const size_t tile_in = (size_t)DEC_THREADS * DEC_PER_THREAD * factor + 2 * (size_t)(n_taps - 1);
+static size_t decimate_smem_bytes(int n_taps, int factor, int per_thread = DEC_PER_THREAD) {
+  const size_t tile_in = (size_t)DEC_THREADS * per_thread * factor + 2 * (size_t)(n_taps - 1);
   return sizeof(float) * (((n_taps + 3) & ~3) + tile_in + tile_in / 32 + 1);
 }
 
@@ -777,8 +776,13 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   }
   if (!early_done) {
     const int64_t n_out = level_len(max_len, p->early_factor, 0);
-    dim3 grid((unsigned)((n_out + tile_out - 1) / tile_out), n_clips);
-    const size_t smem = decimate_smem_bytes(p->n_early_taps, p->early_factor);
+    // outputs per thread shrink with the factor so that the staged input tile (tile_out * factor + 2 * taps) fits:
+    // a 1.5-octave CQT from a low note (C_velocity, training.py:382) decimates by up to 64 first
+    int per_thread = DEC_PER_THREAD;
+    while (per_thread > 1 && decimate_smem_bytes(p->n_early_taps, p->early_factor, per_thread) > 160 * 1024) per_thread >>= 1;
+    const int tile_e = DEC_THREADS * per_thread;
+    dim3 grid((unsigned)((n_out + tile_e - 1) / tile_e), n_clips);
+    const size_t smem = decimate_smem_bytes(p->n_early_taps, p->early_factor, per_thread);
     if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
     if (smem > 48 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -788,7 +792,7 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
                                                     pitch[0], dec2_pairs(p->early_taps2));
     } else {
       decimate_kernel<<<grid, DEC_THREADS, smem, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
-                                                       pitch[0], p->d_early_taps, p->n_early_taps, p->early_factor);
+                                                       pitch[0], p->d_early_taps, p->n_early_taps, p->early_factor, per_thread);
     }
     SAGA_LAUNCH_CHECK();
   }

@@ -23,43 +23,12 @@
 
 #include "fft_radix.cuh"
 #include "saga_common.cuh"
-
-struct saga_stft_plan {
-  int n_fft, hop, center, M;
-  int n_pass;
-  int radix[3];
-  float* d_window;   // n_fft floats
-  float* d_window_half;  // 0.5 * window (forward kernel)
-  float2* d_tw[3];   // per pass: [R][L/R] inter-pass twiddles (last pass: unused)
-  float2* d_twN;     // M/2 + 1 entries exp(-2*pi*i*k/n_fft)
-  float2* d_tw_eo;   // n_fft 4096 only: [32][32] exp(-2*pi*i*rp*j/1024), first-pass twiddles of the two 1024-point halves
-  int warps;         // warps per CTA
-  int frames_per_cta;
-  int span_alloc;    // floats reserved for the staged span
-  size_t smem_bytes;
-};
+#include "stft_plan.cuh"
 
 namespace saga {
 
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
 
-struct StftArgs {
-  const float* wav;
-  const int64_t* clip_offsets;
-  const int64_t* clip_lens;
-  float* mag_out;
-  float2* phase_out;
-  float2* cplx_out;
-  float* frame_max_out;
-  float* clip_max_out;
-  const float* window;
-  const float2* tw0;
-  const float2* tw1;
-  const float2* twN;
-  const float2* tw_eo;
-  int64_t frame_pitch, out_clip_stride;
-  int hop, center, frames_per_cta, span_alloc, tiles_per_clip, max_frames;
-};
 
 // table element: read-only global path, or a plain (shared-memory) load when the CTA keeps the tables in SMEM
 template <bool GT>
@@ -807,6 +776,8 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
   const int M = p->M;
   const double PI = 3.14159265358979323846;
 
+  p->default_window = window_host ? 0 : 1;
+  p->d_ring_tables = nullptr;
   std::vector<float> win(n_fft);
   for (int n = 0; n < n_fft; ++n)
     win[n] = window_host ? window_host[n] : (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / n_fft));
@@ -871,6 +842,10 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
     saga_stft_plan_destroy(p);
     return set_error(SAGA_ERR_UNSUPPORTED, "stft_plan_create: hop=%d too large for n_fft=%d staging", hop, n_fft);
   }
+  if (int rc = saga::stft_ring_build_tables(p)) {
+    saga_stft_plan_destroy(p);
+    return rc;
+  }
   *out = p;
   return SAGA_OK;
 }
@@ -882,6 +857,7 @@ extern "C" int saga_stft_plan_destroy(saga_stft_plan* p) {
   for (int i = 0; i < 3; ++i) cudaFree(p->d_tw[i]);
   cudaFree(p->d_tw_eo);
   cudaFree(p->d_twN);
+  cudaFree(p->d_ring_tables);
   delete p;
   return SAGA_OK;
 }
@@ -933,7 +909,15 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
     case 128: return launch_stft<128, 16, 8, 1, 8>(p, a, n_clips, st);
     case 256: return launch_stft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
-    case 1024: return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
+    case 1024: {
+      // ring kernel (stft_ring.cu) for the n_fft 2048 / hop 512 / Hann shape; SAGA_STFT_RING=0 keeps the
+      // first-generation kernel (A/B twin of the parity tests), tiny batches stay on it as well
+      static const int ring_mode = [] { const char* e = getenv("SAGA_STFT_RING"); return e ? atoi(e) : -1; }();
+      const bool big = (int64_t)n_clips * T >= 64;
+      if (saga::stft_ring_supported(p) && (ring_mode > 0 || (ring_mode < 0 && big)))
+        return saga::launch_stft_ring(p, a, n_clips, T, st);
+      return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
+    }
     case 2048:
       if (getenv("SAGA_STFT_NO_EO")) return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // three-pass form (A/B)
       return launch_stft_eo4096<8>(p, a, n_clips, st);

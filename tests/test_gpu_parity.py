@@ -343,6 +343,7 @@ CQT_CASES = [
     (44100, 512, "C1", 84, 12, 512 * 133 + 100),    # 134 frames: the 6-frame partial tile goes to cqt_tail_kernel
     (44100, 1024, "A0", 348, 48, 66150),            # ref_C_4 (training.py:277): 96 columns per octave, fp32 contraction
     (44100, 1024, "C4", 348, 192, 132300),          # bins_per_tone=16 from the note (training.py:366-381): 3 column blocks
+    (44100, 1024, "F#1", 36, 24, 264192),           # C_velocity below a low note (training.py:382): early decimation by 64
 ]
 
 
