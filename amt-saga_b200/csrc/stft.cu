@@ -910,12 +910,11 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
     case 256: return launch_stft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_stft<512, 32, 16, 1, 8>(p, a, n_clips, st);
     case 1024: {
-      // ring kernel (stft_ring.cu) for the n_fft 2048 / hop 512 / Hann shape; SAGA_STFT_RING=0 keeps the
-      // first-generation kernel (A/B twin of the parity tests), tiny batches stay on it as well
-      static const int ring_mode = [] { const char* e = getenv("SAGA_STFT_RING"); return e ? atoi(e) : -1; }();
-      const bool big = (int64_t)n_clips * T >= 64;
-      if (saga::stft_ring_supported(p) && (ring_mode > 0 || (ring_mode < 0 && big)))
-        return saga::launch_stft_ring(p, a, n_clips, T, st);
+      // ring kernel (stft_ring.cu) for the n_fft 2048 / hop 512 / Hann shape, whatever the batch size (the choice must
+      // not depend on how a caller chunks its batch: the two kernels round differently); SAGA_STFT_RING=0 keeps the
+      // first-generation kernel, the A/B twin of the parity tests
+      static const int ring_mode = [] { const char* e = getenv("SAGA_STFT_RING"); return e ? atoi(e) : 1; }();
+      if (ring_mode > 0 && saga::stft_ring_supported(p)) return saga::launch_stft_ring(p, a, n_clips, T, st);
       return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
     }
     case 2048:

@@ -1,0 +1,127 @@
+"""K1 at n_fft 2048 / hop 512 has two kernels: the ring kernel (csrc/stft_ring.cu, default for batches of
+>= 64 frames) and the first-generation kernel (csrc/stft.cu).  The library picks once per process
+(SAGA_STFT_RING), so each is forced in its own subprocess and checked against the CPU oracle on the cases
+the reference's path produces: ragged batches, clips shorter than the reflect pad, an all-zero clip, clips
+whose start is not 16-byte aligned (the producer's mirrored-fill path), center=False, float64-origin audio at
+the -80 dB floor (util_audio.py:776-781 renders float64), phase / complex outputs, and a batch large enough to
+wrap the sample ring many times per CTA."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAG_TOL, DB_TOL = 1e-4, 0.01
+
+
+def run_cases():
+    """Executed inside the subprocess: returns {case: measured error} (asserts on exactness checks)."""
+    import torch
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops
+    from oracle import spectral as osp
+    from tests.synth import piano_clip
+
+    dev = torch.device("cuda")
+    out = {}
+
+    def rel(got, ref):
+        peak = float(np.abs(ref).max()) or 1.0
+        return float(np.abs(got.astype(np.complex128) - ref.astype(np.complex128)).max()) / peak
+
+    for center in (True, False):
+        rng = np.random.default_rng(3)
+        lens = [5000, 2048, 2049, 1, 300, 44100, 1023, 1025, 4095, 2048 * 3 + 7, 8192, 8193, 4096 * 5 + 1, 70000]
+        if not center:
+            lens = [x for x in lens if x >= 2048]
+        width = max(lens)
+        wav = np.zeros((len(lens), width), dtype=np.float32)
+        for i, n in enumerate(lens):
+            wav[i, :n] = rng.standard_normal(n).astype(np.float32) * (0.1 + i)
+        plan = ops.StftPlan(2048, 512, center)
+        r = ops.stft_batch(torch.as_tensor(wav, device=dev), plan, lens=lens, want_phase=True, want_complex=True)
+        worst = 0.0
+        for i, n in enumerate(lens):
+            F = osp.stft(wav[i, :n], 2048, 512, center=center)
+            T = F.shape[1]
+            assert T == plan.num_frames(n)
+            mag = r["mag"][i].cpu().numpy()
+            worst = max(worst, rel(mag[:, :T], np.abs(F)), rel(r["F"][i].cpu().numpy()[:, :T], F))
+            assert np.all(mag[:, T:] == 0), "columns past the clip's frames must stay zero"
+            assert np.all(r["mag_storage"][i, :T, 1025:].cpu().numpy() == 0), "padding bins are defined as zero"
+            fm = r["frame_max"][i, :T].cpu().numpy()
+            assert np.allclose(fm, np.abs(F).max(axis=0), rtol=1e-5, atol=1e-6 * np.abs(F).max())
+            assert abs(float(r["clip_max"][i]) - np.abs(F).max()) <= 1e-5 * np.abs(F).max()
+            ph = r["phase"][i].cpu().numpy()[:, :T]
+            big = np.abs(F) > 1e-3 * np.abs(F).max()
+            assert np.abs(ph[big] - (F / np.maximum(np.abs(F), 1e-300))[big]).max() < 2e-3
+        out["ragged_center%d" % center] = worst
+
+    # unaligned clip starts: rows of a [clips, 70001] buffer start at odd float offsets
+    n = 70001
+    base = np.stack([piano_clip(40 + i, n) for i in range(3)])
+    plan = ops.StftPlan(2048, 512, True)
+    r = ops.stft_batch(torch.as_tensor(base, device=dev), plan)
+    out["unaligned"] = max(rel(r["mag"][i].cpu().numpy(), np.abs(osp.stft(base[i], 2048, 512))) for i in range(3))
+
+    # all-zero clip: magnitude 0, phase 1+0j (magphase convention angle(0) = 0)
+    r = ops.stft_batch(torch.zeros(2, 40000, device=dev), plan, want_phase=True)
+    assert float(r["mag"].abs().max()) == 0.0
+    assert np.all(r["phase"].cpu().numpy() == 1.0 + 0.0j)
+    out["zero"] = 0.0
+
+    # float64-rendered audio (the reference's dtype) at the -80 dB floor: magnitudes and dB
+    y64 = piano_clip(11, 44100 * 3).astype(np.float64) * (1.0 + 1e-9 * np.arange(44100 * 3) % 7)
+    ref = np.abs(osp.stft(y64, 2048, 512))
+    r = ops.stft_batch(torch.as_tensor(y64, device=dev).float(), plan)
+    out["float64_mag"] = rel(r["mag"][0].cpu().numpy(), ref)
+    D = ops.amplitude_to_db_batch(r["mag_storage"], plan.n_bins)[0, :, :1025].T.cpu().numpy()
+    Dref = osp.amplitude_to_db(ref, ref=ref.max())
+    above = Dref > Dref.max() - 80.0 + 1e-3
+    out["float64_db"] = float(np.abs(D[above] - Dref[above]).max())
+
+    # many ring laps per CTA: 300 clips x 129 frames; spot-check clips against the oracle, all against a checksum
+    W, ns = 300, 65536
+    wav = np.stack([piano_clip(900 + i, ns, n_notes=3) for i in range(W)])
+    r = ops.stft_batch(torch.as_tensor(wav, device=dev), plan)
+    worst = 0.0
+    for i in (0, 1, 147, 148, 149, 298, 299):
+        worst = max(worst, rel(r["mag"][i].cpu().numpy(), np.abs(osp.stft(wav[i], 2048, 512))))
+    out["many_laps"] = worst
+    # Parseval per frame on every clip: sum_k c_k |X_k|^2 = N sum_n (w x)^2  (size-independent property)
+    mag = r["mag"].double()                                   # [W, 1025, T]
+    c = torch.full((1025,), 2.0, device=dev, dtype=torch.float64)
+    c[0] = c[-1] = 1.0
+    lhs = (mag ** 2 * c[None, :, None]).sum(dim=1)
+    w = torch.hann_window(2048, periodic=True, device=dev, dtype=torch.float64)
+    x = torch.nn.functional.pad(torch.as_tensor(wav, device=dev).double()[:, None, :], (1024, 1024), mode="reflect")[:, 0]
+    frames = x.unfold(1, 2048, 512) * w
+    rhs = 2048.0 * (frames ** 2).sum(dim=2)
+    out["parseval"] = float(((lhs - rhs).abs() / rhs.clamp_min(1e-30)).max())
+    return out
+
+
+def _run(mode):
+    code = ("import sys, json; sys.path.insert(0, %r); from tests.test_stft_ring import run_cases; "
+            "print('RESULT ' + json.dumps(run_cases()))" % ROOT)
+    env = dict(os.environ, SAGA_STFT_RING=str(mode))
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    return json.loads(p.stdout.split("RESULT ")[-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 0], ids=["ring_kernel", "first_generation_kernel"])
+def test_stft_2048_kernels_match_oracle(mode):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    res = _run(mode)
+    for k, v in res.items():
+        tol = DB_TOL if k.endswith("_db") else (1e-5 if k == "parseval" else MAG_TOL)
+        assert v <= tol, (k, v, res)
+    # fp32 FFTs: both kernels are in fact far inside the 1e-4-of-peak bar
+    assert max(res["ragged_center1"], res["ragged_center0"], res["unaligned"], res["many_laps"]) < 5e-6, res
