@@ -40,12 +40,27 @@ __global__ void __launch_bounds__(256) compress_bands_kernel(const float* __rest
 //   out_lin  = mag / ref                        (training.py:352, :361)
 //   out_log  = log10(1000 mag + 1) / max(.)     (training.py:350-351, :359-360)
 //   out_phase = (angle(ph) + 3.15) / 6.3        (training.py:362-363)
+// One CTA per window (blockIdx.x): window w reads mag + w * clip_stride, its own source frames
+// src_frames[w * n_cols ..], band_min_dev[w] / inv_ref_dev[w] when given (else the scalar arguments), and writes
+// out_* + w * out_clip_stride.
 __global__ void __launch_bounds__(256) short_window_kernel(const float* __restrict__ mag, const float2* __restrict__ ph,
                                                            const int* __restrict__ src_frames, int n_cols, int band_min,
                                                            int n_rows, int n_bins, int64_t P, float inv_ref,
                                                            float* __restrict__ out_lin, float* __restrict__ out_log,
-                                                           float* __restrict__ out_phase, int64_t out_P) {
+                                                           float* __restrict__ out_phase, int64_t out_P,
+                                                           int64_t clip_stride = 0, int64_t out_clip_stride = 0,
+                                                           const int* __restrict__ band_min_dev = nullptr,
+                                                           const float* __restrict__ inv_ref_dev = nullptr) {
   __shared__ float red[8];
+  const int w = blockIdx.x;
+  mag += (int64_t)w * clip_stride;
+  if (ph) ph += (int64_t)w * clip_stride;
+  src_frames += (int64_t)w * n_cols;
+  if (out_lin) out_lin += (int64_t)w * out_clip_stride;
+  if (out_log) out_log += (int64_t)w * out_clip_stride;
+  if (out_phase) out_phase += (int64_t)w * out_clip_stride;
+  if (band_min_dev) band_min = band_min_dev[w];
+  if (inv_ref_dev) inv_ref = inv_ref_dev[w];
   const int n = n_rows * n_cols;
   float vmax = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) {
@@ -106,9 +121,57 @@ __global__ void __launch_bounds__(256) flatness_kernel(const float* __restrict__
   if (lane == 0) out[(int64_t)clip * n_frames + t] = (float)(exp(slog / n_bins) / (slin / n_bins));
 }
 
+// Column gather of a batch of frame-major images: out[w][j][k] = in[w][src[w][j]][k] * scale[w] for k < n_bins
+// (src = -1: zeros; columns k in [n_bins, out_pitch) are written as 0).  This is `C[:, s:t]` + `_resize` +
+// `/ ref_C` of the producer loop's five slice_C calls (util_audio.py:431-434, :384-409; training.py:340-388) for a
+// whole batch of windows.  One warp per output column.
+__global__ void __launch_bounds__(256) gather_frames_kernel(const float* __restrict__ in, const int* __restrict__ src,
+                                                            const float* __restrict__ scale, float* __restrict__ out,
+                                                            int n_cols, int n_bins, int64_t P, int64_t clip_stride,
+                                                            int64_t out_P, int64_t out_clip_stride, int n_windows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t col = (int64_t)blockIdx.x * 8 + warp;
+  if (col >= (int64_t)n_windows * n_cols) return;
+  const int w = (int)(col / n_cols), j = (int)(col - (int64_t)w * n_cols);
+  const int t = src[col];
+  const float sc = scale ? scale[w] : 1.0f;
+  const float* row = in + (int64_t)w * clip_stride + (int64_t)t * P;
+  float* orow = out + (int64_t)w * out_clip_stride + (int64_t)j * out_P;
+  for (int k = lane; k < out_P; k += 32) orow[k] = (t >= 0 && k < n_bins) ? row[k] * sc : 0.f;
+}
+
 }  // namespace saga
 
 using namespace saga;
+
+extern "C" int saga_gather_frames_exec(const float* in, const int32_t* src_frames, const float* scale, float* out,
+                                       int n_windows, int n_cols, int n_bins, int64_t frame_pitch, int64_t clip_stride,
+                                       int64_t out_pitch, int64_t out_clip_stride, void* stream) {
+  if (!in || !src_frames || !out) return set_error(SAGA_ERR_INVALID, "gather_frames_exec: null argument");
+  if (n_cols < 1 || n_bins < 1 || out_pitch < n_bins || frame_pitch < n_bins)
+    return set_error(SAGA_ERR_INVALID, "gather_frames_exec: bad shape");
+  if (n_windows <= 0) return SAGA_OK;
+  const int64_t cols = (int64_t)n_windows * n_cols;
+  gather_frames_kernel<<<(unsigned)((cols + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      in, src_frames, scale, out, n_cols, n_bins, frame_pitch, clip_stride, out_pitch, out_clip_stride, n_windows);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
+extern "C" int saga_short_window_batch_exec(const float* mag, const void* phase, int64_t clip_stride, int64_t frame_pitch,
+                                            const int32_t* src_frames, int n_cols, const int32_t* band_min, int band_min_all,
+                                            int n_rows, int n_bins, const float* inv_ref, float inv_ref_all,
+                                            float* out_lin, float* out_log, float* out_phase, int64_t out_pitch,
+                                            int64_t out_clip_stride, int n_windows, void* stream) {
+  if (!mag || !src_frames) return set_error(SAGA_ERR_INVALID, "short_window_batch_exec: null argument");
+  if (n_cols < 1 || n_rows < 1 || out_pitch < n_rows) return set_error(SAGA_ERR_INVALID, "short_window_batch_exec: bad shape");
+  if (n_windows <= 0) return SAGA_OK;
+  short_window_kernel<<<n_windows, 256, 0, (cudaStream_t)stream>>>(
+      mag, (const float2*)phase, src_frames, n_cols, band_min_all, n_rows, n_bins, frame_pitch, inv_ref_all, out_lin,
+      out_log, out_phase, out_pitch, clip_stride, out_clip_stride, band_min, inv_ref);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
 
 extern "C" int saga_compress_bands_exec(const float* mag, float* out, const int32_t* band_edges_host, int n_bands,
                                         int n_clips, int n_frames, int64_t frame_pitch, int64_t clip_stride,

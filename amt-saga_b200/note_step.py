@@ -1,0 +1,174 @@
+"""Batched form of ONE iteration of the reference's per-note loop, in the reference's own order, for W
+analysis windows at once (one note per window and step):
+
+    training.py:333-336   C_timing      = _resize(compress_bands(audio_w.mag, 20), 258) / song ref_mag      K5
+    training.py:337       audio_sw      = audio_w.resize(onset, duration, 8, ['mag', 'ph'])                  K5
+    training.py:340-346   C_sw_pitch / C_sw_inst = audio_w.slice_C(...)/ref_C     (174 @ 24, 348 @ 48 per octave)   K4 + K2
+    training.py:347-363   F_sw_inst_foc(_const)(_log10), ph                                                   K5
+    training.py:365-388   C_sw_inst_foc / _foc_const (348 @ 192 per octave), C_velocity (36 @ 24)            K2
+    training.py:426       ac_note_guessed = audio_complete(render(note), N)                                   K1
+    training.py:449       audio_w.subtract(ac_note_guessed, offset=onset)                                     K3
+
+`audio_w.slice_C` reads `audio_w.wf`, which after the first subtraction is `librosa.istft(mag * ph)`
+(util_audio.py:88-106, length hop * (T - 1)): every step but the first therefore starts with K4 on the
+subtracted windows.  The first subtraction of a fresh `section` scales the guess by the SONG's ref_mag (the
+section copied it, util_audio.py:323); later ones by the window's current maximum (the `mag` setter reset it).
+
+The state (subtracted magnitudes, original phases, waveforms) stays on the device between steps; the eleven
+classifier tensors come back as `[W, bands, frames]` CUDA tensors (`batches.py` stacks them for the models).
+Host work per step is the float64 time -> frame arithmetic of util_audio.py:264 (vectorised, same operation
+order) and the `_resize` index maps.  Windows whose note needs a CQT that librosa would refuse (pass band beyond
+Nyquist) are reported in `valid` instead of raising, so one bad note does not lose the batch.
+"""
+import bisect
+
+import numpy as np
+import torch
+
+from . import ops
+from .cqt_plan import ParameterError
+from .util_audio import band_edges, midi_to_hz, note_to_midi
+
+
+class NoteStepBatch:
+    def __init__(self, n_windows, sr=44100, n_fft=4096, hop_length=None, timing_frames=258, timing_bands=20,
+                 pitch_frames=8, instrument_frames=8, pitch_bins_per_tone=2, instrument_bins_per_tone=4,
+                 instrument_bands=348, bins_velocity=36, device=None):
+        self.W, self.sr, self.N = int(n_windows), sr, int(n_fft)
+        self.hl = int(hop_length) if hop_length is not None else self.N // 4
+        self.T = int(timing_frames)
+        self.timing_bands = timing_bands
+        self.pitch_frames, self.instrument_frames = pitch_frames, instrument_frames
+        self.pitch_bpt, self.inst_bpt = pitch_bins_per_tone, instrument_bins_per_tone
+        self.instrument_bands, self.bins_velocity = instrument_bands, bins_velocity
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stft = ops.get_stft_plan(self.N, self.hl, True, device=self.dev)
+        self.nb = self.stft.n_bins
+        self._fft_freq = np.linspace(0, float(sr) / 2, int(1 + self.N // 2), endpoint=True)   # util_audio.py:67
+        self.mag = self.ph = self.wav = None
+        self.fresh = True
+
+    # ------------------------------------------------------------------ helpers (host, float64)
+    def midi_tone_to_FFT(self, tone):          # util_audio.py:278-284
+        ind = bisect.bisect_right(self._fft_freq, midi_to_hz(tone)) - 1
+        return 0 if ind == 0 else ind - 1
+
+    def _frames(self, seconds):
+        """util_audio.py:264 for every window: floor(time * T * sr / len(wf)), float64, that order."""
+        x = np.asarray(seconds, dtype=np.float64) * self.T * self.sr / self.wav.shape[1]
+        return np.floor(x).astype(np.int64)
+
+    @staticmethod
+    def _resize_map(s, t, n_src, target):
+        """Source column of every output column of `_resize(P[:, s:t], target)` for each window (numpy slice
+        clipping included); -1 = the all-zero result of an empty slice."""
+        out = np.empty((len(s), target), dtype=np.int32)
+        for i, (a, b) in enumerate(zip(s, t)):
+            a_c, b_c = min(max(int(a), 0), n_src), min(max(int(b), 0), n_src)
+            idx = ops.resize_indices(max(b_c - a_c, 0), target)
+            out[i] = np.where(idx >= 0, idx + a_c, -1)
+        return out
+
+    # ------------------------------------------------------------------ state
+    def load(self, mag_storage, phase_storage, wav, song_ref_mag, ref_C):
+        """Windows as `mid_wf.section(offset, None, timing_frames)` leaves them (training.py:284):
+        mag_storage / phase_storage: frame-major [W, T, P] (columns of the SONG's STFT), wav [W, L] the matching
+        waveform slices, song_ref_mag [W] = mid_wf.ref_mag, ref_C [W, 3] = (ref_C_1, ref_C_inst, ref_C_foc)."""
+        f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32) if not isinstance(x, torch.Tensor) else x,
+                                        device=self.dev).to(torch.float32).contiguous()
+        if mag_storage.shape[:2] != (self.W, self.T) or phase_storage.shape != mag_storage.shape:
+            raise ValueError("expected [W, T, P] magnitude and phase storage")
+        self.mag, self.ph = mag_storage.contiguous(), phase_storage.contiguous()
+        self.wav = wav.to(device=self.dev, dtype=torch.float32).contiguous()
+        self.song_ref = f32(song_ref_mag)
+        self.inv_song_ref = 1.0 / self.song_ref
+        rc = np.asarray(ref_C.cpu() if isinstance(ref_C, torch.Tensor) else ref_C, dtype=np.float64).reshape(self.W, 3)
+        self.inv_ref_C = [f32(1.0 / rc[:, i]) for i in range(3)]
+        self.stale_ref = self.song_ref.clone()     # `section` copied the song's ref_mag (util_audio.py:323)
+        self.fresh = True
+
+    # ------------------------------------------------------------------ one batched step
+    def _cqt_columns(self, wav, lowest_midi, nbins, bpt, s, t, n_cols, inv_ref):
+        plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(lowest_midi), int(nbins), int(12 * bpt), 2, device=self.dev)
+        plan.check_length(int(wav.shape[1]))
+        C = ops.cqt_batch(wav, plan)["mag_storage"]                                  # [W', Tc, Pc]
+        src = self._resize_map(s, t, C.shape[1], n_cols)                             # C[:, s:t] -> _resize
+        return ops.gather_frames_batch(C, nbins, src, inv_ref)                       # / ref_C
+
+    def step(self, onset, duration, pitch, guess_wav, guess_lens=None, subtract=True):
+        """onset / duration (seconds, relative to the window) and MIDI pitch per window (host arrays, [W]);
+        guess_wav [W, Lg]: the rendered guessed notes (device float32; `guess_lens` for ragged renders).
+        Returns the note_sample tensors (util_train_test.py:177-209) as [W, bands, frames] CUDA tensors plus
+        `valid` [W] (bool, host) and `offset_frames` [W]; then subtracts the guesses (training.py:449)."""
+        W = self.W
+        onset = np.asarray(onset, dtype=np.float64).reshape(W)
+        duration = np.asarray(duration, dtype=np.float64).reshape(W)
+        pitch = np.asarray(pitch, dtype=np.int64).reshape(W)
+        if not self.fresh:
+            # util_audio.py:88-106: wf is rebuilt from the subtracted magnitude and the original phase
+            self.wav = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb)
+        s, t = self._frames(onset), self._frames(onset + duration)
+        out = {}
+        # -- timing classifier input (training.py:333-336)
+        edges = band_edges(self.nb, self.timing_bands)
+        ct = ops.compress_bands_batch(self.mag, self.nb, edges, inv_scale=self.inv_song_ref)
+        out["C_timing"] = ct[:, :, :self.timing_bands].transpose(1, 2)              # T == timing_frames: _resize is the identity
+        # -- short window (training.py:337, :347-363)
+        sw_src = self._resize_map(s, t, self.T, self.pitch_frames)
+        b_const = self.midi_tone_to_FFT(60)
+        fc = ops.short_window_features_batch(self.mag, None, sw_src, b_const, self.instrument_bands, self.nb,
+                                             self.inv_song_ref)
+        out["F_sw_inst_foc_const"], out["F_sw_inst_foc_const_log10"] = fc["lin"], fc["log"]
+        b_note = np.array([self.midi_tone_to_FFT(int(p)) for p in pitch], dtype=np.int32)
+        fn = ops.short_window_features_batch(self.mag, self.ph, sw_src, b_note, self.instrument_bands, self.nb,
+                                             self.inv_song_ref, want_phase=True)
+        out["F_sw_inst_foc"], out["F_sw_inst_foc_log10"], out["ph"] = fn["lin"], fn["log"], fn["phase"]
+        # -- constant-Q inputs (training.py:340-346, :365-388); filter_scale 2 (util_audio.py:426)
+        a0, c8 = note_to_midi("A0"), note_to_midi("C8")
+        out["C_sw_pitch"] = self._cqt_columns(self.wav, a0, (c8 - a0) * self.pitch_bpt, self.pitch_bpt, s, t,
+                                              self.pitch_frames, self.inv_ref_C[0])
+        out["C_sw_inst"] = self._cqt_columns(self.wav, a0, (c8 - a0) * self.inst_bpt, self.inst_bpt, s, t,
+                                             self.instrument_frames, self.inv_ref_C[1])
+        out["C_sw_inst_foc_const"] = self._cqt_columns(self.wav, 60, self.instrument_bands, self.inst_bpt * 4, s, t,
+                                                       self.instrument_frames, self.inv_ref_C[2])
+        # the two note-relative transforms have one kernel bank per pitch: windows are grouped by pitch
+        valid = np.ones(W, dtype=bool)
+        foc = torch.full((W, self.instrument_bands, self.instrument_frames), float("nan"), device=self.dev)
+        vel = torch.full((W, self.bins_velocity, self.instrument_frames), float("nan"), device=self.dev)
+        for p in np.unique(pitch):
+            rows = np.nonzero(pitch == p)[0]
+            idx = torch.as_tensor(rows, device=self.dev)
+            sub = self.wav if len(rows) == W else self.wav.index_select(0, idx)
+            try:
+                f = self._cqt_columns(sub, int(p), self.instrument_bands, self.inst_bpt * 4, s[rows], t[rows],
+                                      self.instrument_frames, self.inv_ref_C[2][idx])
+                v = self._cqt_columns(sub, int(p) - 10, self.bins_velocity, 2, s[rows], t[rows],
+                                      self.instrument_frames, self.inv_ref_C[2][idx])
+            except ParameterError:          # librosa: "Filter pass-band lies beyond Nyquist" -> the loop skips the file
+                valid[rows] = False
+                continue
+            foc[idx], vel[idx] = f, v
+        out["C_sw_inst_foc"], out["C_velocity"] = foc, vel
+        off = np.maximum(s, 0).astype(np.int32)       # util_audio.py:248 with attack_compensation 0
+        out["valid"], out["offset_frames"] = valid, off
+        if subtract:
+            self.subtract(guess_wav, off, guess_lens)
+        return out
+
+    def subtract(self, guess_wav, offset_frames, guess_lens=None):
+        """training.py:426 + :449: STFT of the rendered notes (K1), then align / scale / subtract / ReLU (K3)."""
+        g = ops.stft_batch(guess_wav, self.stft, lens=guess_lens, want_max=True)
+        gm = g["mag_storage"]
+        frames = None
+        if guess_lens is not None:
+            frames = torch.as_tensor([self.stft.num_frames(int(n)) for n in np.asarray(guess_lens)], dtype=torch.int32,
+                                     device=self.dev).reshape(self.W, 1)
+        if int(np.max(offset_frames)) > self.T:
+            raise ValueError("negative dimensions are not allowed")      # numpy's error for zeros((bins, T - off - ...))
+        _, self.ref = ops.subtract_db_batch(
+            self.mag, gm.unsqueeze(1), torch.as_tensor(offset_frames, dtype=torch.int32).reshape(self.W, 1), self.nb,
+            guess_ref=g["clip_max"].reshape(self.W, 1), ref_init=self.stale_ref if self.fresh else self.ref,
+            guess_frames=frames,
+            normalize=True, relu=True, want_D=False)
+        self.stale_ref = None          # the `mag` setter dropped the copied ref_mag (util_audio.py:149-153)
+        self.fresh = False

@@ -518,6 +518,62 @@ def short_window_features(mag_st, phase_st, src_frames, band_min, n_rows, n_bins
     return {"lin": view(lin), "log": view(log), "phase": view(pha)}
 
 
+def short_window_features_batch(mag_st, phase_st, src_frames, band_min, n_rows, n_bins, inv_ref,
+                                want_lin=True, want_log=True, want_phase=False):
+    """saga_short_window_batch_exec: the short-window block of training.py:337-363 for W windows at once.
+    mag_st [W, T, P] float32 (phase_st complex64, same strides); src_frames int32 [W, n_cols] (host or device;
+    -1 = zeros); band_min: int or int32 [W]; inv_ref: float or float32 [W] device.  Returns a dict of
+    [W, n_rows, n_cols] views (lin, log, phase)."""
+    _require_cuda(mag_st, "mag")
+    W, T, _ = mag_st.shape
+    dev = mag_st.device
+    src = torch.as_tensor(np.ascontiguousarray(src_frames, dtype=np.int32), device=dev) \
+        if not isinstance(src_frames, torch.Tensor) else src_frames.to(device=dev, dtype=torch.int32).contiguous()
+    n_cols = int(src.shape[1])
+    P = mag_st.stride(1) if T > 1 else mag_st.shape[2]
+    cs = mag_st.stride(0) if W > 1 else T * P
+    Po = frame_pitch(n_rows)
+    mk = lambda on: torch.empty((W, n_cols, Po), device=dev, dtype=torch.float32) if on else None
+    lin, log, pha = mk(want_lin), mk(want_log), mk(want_phase)
+    ph_ptr = None
+    if want_phase:
+        if phase_st is None or phase_st.stride() != mag_st.stride():
+            raise ValueError("phase storage must match the magnitude storage")
+        ph_ptr = _ptr(torch.view_as_real(phase_st))
+    bm_dev, bm_all = (None, int(band_min)) if np.isscalar(band_min) else \
+        (torch.as_tensor(np.asarray(band_min, dtype=np.int32), device=dev), 0)
+    ir_dev, ir_all = (None, float(inv_ref)) if not isinstance(inv_ref, torch.Tensor) else \
+        (inv_ref.to(device=dev, dtype=torch.float32).contiguous(), 1.0)
+    with _on(mag_st):
+        _lib.check(_lib.lib().saga_short_window_batch_exec(
+            _ptr(mag_st), ph_ptr, cs, P, _ptr(src), n_cols, _ptr(bm_dev), bm_all, int(n_rows), int(n_bins),
+            _ptr(ir_dev), ir_all, _ptr(lin), _ptr(log), _ptr(pha), Po, n_cols * Po, W, _stream(mag_st)))
+    view = lambda x: None if x is None else x[:, :, :n_rows].transpose(1, 2)
+    return {"lin": view(lin), "log": view(log), "phase": view(pha)}
+
+
+def gather_frames_batch(storage, n_bins, src_frames, scale=None):
+    """saga_gather_frames_exec: out[w][:, j] = in[w][:, src[w, j]] * scale[w] (src -1 => zeros): `C[:, s:t]` +
+    `_resize` + `/ ref` of util_audio.slice_C for a batch.  storage [W, T, P] frame-major; returns the
+    [W, n_bins, n_cols] view of frame-major [W, n_cols, Pout] storage."""
+    _require_cuda(storage, "storage")
+    W, T, _ = storage.shape
+    dev = storage.device
+    src = torch.as_tensor(np.ascontiguousarray(src_frames, dtype=np.int32), device=dev) \
+        if not isinstance(src_frames, torch.Tensor) else src_frames.to(device=dev, dtype=torch.int32).contiguous()
+    n_cols = int(src.shape[1])
+    P = storage.stride(1) if T > 1 else storage.shape[2]
+    cs = storage.stride(0) if W > 1 else T * P
+    Po = frame_pitch(n_bins)
+    out = torch.empty((W, n_cols, Po), device=dev, dtype=torch.float32)
+    if scale is not None:
+        scale = scale.to(device=dev, dtype=torch.float32).contiguous()
+    with _on(storage):
+        _lib.check(_lib.lib().saga_gather_frames_exec(_ptr(storage), _ptr(src), _ptr(scale), _ptr(out), W, n_cols,
+                                                      int(n_bins), P, cs, Po, n_cols * Po, _stream(storage)))
+    return out[:, :, :n_bins].transpose(1, 2)
+
+
 def spectral_flatness_batch(mag_storage, n_bins, amin=1e-10):
     """librosa.feature.spectral_flatness(power=2) per frame: [clips, T]."""
     m = mag_storage if mag_storage.dim() == 3 else mag_storage.unsqueeze(0)

@@ -238,6 +238,24 @@ int saga_short_window_exec(const float* mag, const void* phase, const int32_t* s
                            int band_min, int n_rows, int n_bins, int64_t frame_pitch, float inv_ref,
                            float* out_lin, float* out_log, float* out_phase, int64_t out_pitch, void* stream);
 
+/* The same for a BATCH of windows (one per note of a batched step of the producer loop, training.py:337-363):
+ * window w reads mag + w*clip_stride (phase likewise, float2 units), its own n_cols source frames
+ * src_frames[w*n_cols ..] (device), rows [band_min[w], band_min[w]+n_rows) (band_min device array, or NULL =>
+ * band_min_all for every window: the fixed C4 band of training.py:289-290), scale inv_ref[w] (or inv_ref_all),
+ * and writes out_* + w*out_clip_stride.  The log10 variant is normalised by each window's own maximum. */
+int saga_short_window_batch_exec(const float* mag, const void* phase, int64_t clip_stride, int64_t frame_pitch,
+                                 const int32_t* src_frames, int n_cols, const int32_t* band_min, int band_min_all,
+                                 int n_rows, int n_bins, const float* inv_ref, float inv_ref_all,
+                                 float* out_lin, float* out_log, float* out_phase, int64_t out_pitch,
+                                 int64_t out_clip_stride, int n_windows, void* stream);
+
+/* util_audio.py:431-434 `C[:, s:t]` -> :384-409 `_resize` -> training.py:340-388 `/ ref_C` for a batch:
+ *   out[w][j][k] = in[w][src_frames[w*n_cols + j]][k] * scale[w]   (k < n_bins; src -1 => zeros; scale NULL => 1)
+ * in / out frame-major; columns k in [n_bins, out_pitch) are written as 0. */
+int saga_gather_frames_exec(const float* in, const int32_t* src_frames, const float* scale, float* out,
+                            int n_windows, int n_cols, int n_bins, int64_t frame_pitch, int64_t clip_stride,
+                            int64_t out_pitch, int64_t out_clip_stride, void* stream);
+
 /* util_audio.py:330-332 librosa.feature.spectral_flatness(power=2): flatness_out[clip*n_frames + t] */
 int saga_spectral_flatness_exec(const float* mag, float* flatness_out, int n_clips, int n_bins, int n_frames,
                                 int64_t frame_pitch, int64_t clip_stride, float amin, void* stream);

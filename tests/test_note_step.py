@@ -1,0 +1,98 @@
+"""Batched per-note step (amt_saga_b200.note_step.NoteStepBatch) against the reference's OWN class: the golden
+vectors were produced by /root/reference/util_audio.py driven through the producer loop of training.py:265-449
+(tests/golden/make_ref_class_golden.py::note_steps, three songs x two notes, N 4096 / hop 1024 / 258 frames)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.audio_oracle import AudioOracle
+from tests import ref_loop as L
+from tests.golden.make_ref_class_golden import FULL_COLS, NOTE_STEPS
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAG_TOL = 1e-4
+
+
+def test_resize_map_equals_reference_resize_on_column_indices():
+    """Host logic: the index map must pick exactly the columns `_resize(P[:, s:t], target)` returns."""
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200.note_step import NoteStepBatch
+    rng = np.random.default_rng(1)
+    P = np.arange(258, dtype=np.float64)[None, :] + 1.0       # column j holds j + 1 (0 marks "zeros")
+    s = rng.integers(0, 270, size=200)                        # onsets are >= 0: frames never negative
+    t = s + rng.integers(-2, 40, size=200)
+    t[t < 0] = 0
+    for target in (8, 258):
+        m = NoteStepBatch._resize_map(s, t, 258, target)
+        for i in range(len(s)):
+            want = AudioOracle._resize(P[:, s[i]:t[i]], target)[0]
+            got = np.where(m[i] >= 0, m[i] + 1.0, 0.0)
+            assert np.array_equal(got, want), (s[i], t[i], target)
+
+
+@pytest.mark.gpu
+def test_batched_note_step_matches_reference_class_golden():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import util_audio as ua
+    from amt_saga_b200.note_step import NoteStepBatch
+    gold = dict(np.load(os.path.join(GOLD, "ref_class_note_steps.npz")))
+    W = len(NOTE_STEPS)
+    songs, clips = zip(*[L.make_inputs(c["seed"], c["seconds"], c["notes"]) for c in NOTE_STEPS])
+    # windows exactly as `mid_wf.section(0, None, 258)` leaves them (training.py:284)
+    mags, phs, wavs = [], [], []
+    for song in songs:
+        a = ua.audio_complete(song, 4096)
+        a.mag
+        w = a.section(0, None, 258)
+        mags.append(w._mag.st), phs.append(w._ph.st), wavs.append(w._wf)
+    assert len({int(x.numel()) for x in wavs}) == 1
+    batch = NoteStepBatch(W)
+    batch.load(torch.stack(mags), torch.stack(phs), torch.stack(wavs),
+               [float(gold["w%d_song_ref_mag" % w]) for w in range(W)], np.stack([gold["w%d_ref_C" % w] for w in range(W)]))
+    names = {"C_timing": "C_timing", "C_sw_pitch": "C_sw_pitch", "C_sw_inst": "C_sw_inst", "F_sw_inst_foc": "F_foc",
+             "F_sw_inst_foc_log10": "F_foc_log10", "F_sw_inst_foc_const": "F_const",
+             "F_sw_inst_foc_const_log10": "F_const_log10", "C_sw_inst_foc": "C_foc", "C_sw_inst_foc_const": "C_foc_const",
+             "C_velocity": "C_velocity"}
+    for n in range(2):
+        notes = [c["notes"][n] for c in NOTE_STEPS]
+        lens = np.array([len(clips[w][n]) for w in range(W)])
+        g = np.zeros((W, lens.max()), dtype=np.float32)
+        for w in range(W):
+            g[w, :lens[w]] = clips[w][n]
+        out = batch.step([x[0] for x in notes], [x[1] for x in notes], [x[2] for x in notes],
+                         torch.as_tensor(g, device="cuda"), guess_lens=lens)
+        assert out["valid"].all()
+        for w in range(W):
+            key = "w%d_n%d_" % (w, n)
+            peak = float(gold["w%d_song_ref_mag" % w])
+            assert out["offset_frames"][w] == gold[key + "off_frames"]          # frame indexing: exact
+            for mine, theirs in names.items():
+                v, ref = out[mine][w].cpu().numpy(), gold[key + theirs]
+                assert v.shape == ref.shape, (mine, v.shape, ref.shape)
+                if theirs.endswith("_log10"):
+                    src = gold[key + theirs.replace("_log10", "")].astype(np.float64) * peak
+                    tol = MAG_TOL * peak * 1000 / (np.log(10) * (1000 * src + 1)) / np.log10(1000 * src.max() + 1) + 1e-6
+                    assert (np.abs(v - ref) <= tol).all(), (key, mine)
+                else:
+                    assert np.abs(v - ref).max() <= MAG_TOL * np.abs(ref).max(), (key, mine, float(np.abs(v - ref).max()))
+            # phase feature: compare phasors where the short-window magnitude is not noise
+            m, lo = gold[key + "sw_mag"], int(gold[key + "fft_bin_min"])
+            strong = np.zeros(gold[key + "ph"].shape, dtype=bool)
+            rows = min(strong.shape[0], m.shape[0] - lo)
+            strong[:rows] = m[lo:lo + rows] > 1e-3 * m.max()
+            d = np.abs(np.exp(1j * (out["ph"][w].cpu().numpy() * 6.3 - 3.15)) - np.exp(1j * (gold[key + "ph"] * 6.3 - 3.15)))
+            assert d[strong].max() <= 2e-3
+            # state after the subtraction (training.py:449)
+            mag_after = batch.mag[w, :, :2049].T.cpu().numpy()
+            ref_cols = gold[key + "mag_after__cols"]
+            assert np.abs(mag_after[:, FULL_COLS] - ref_cols).max() <= MAG_TOL * peak
+            assert np.abs(mag_after.sum(axis=0, dtype=np.float64) - gold[key + "mag_after__colsum"]).max() \
+                <= 1e-4 * gold[key + "mag_after__colsum"].max()
+            assert abs(float(batch.ref[w]) - float(gold[key + "ref_after"])) <= 2e-5 * float(gold[key + "ref_after"])
+    # after a subtraction the next step's waveform is the iSTFT of mag * ph: hop * (T - 1) samples
+    batch.step([0.5] * W, [0.5] * W, [60] * W, torch.zeros((W, 8192), device="cuda"), subtract=False)
+    assert batch.wav.shape[1] == 1024 * 257 == int(gold["w0_n1_wf_len_after"])
