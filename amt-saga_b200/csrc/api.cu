@@ -21,5 +21,5 @@ int set_error(int code, const char* fmt, ...) {
 }  // namespace saga
 
 extern "C" const char* saga_last_error_string(void) { return saga::err_buf(); }
-extern "C" int saga_abi_version(void) { return 2; }   // 2: + saga_short_window_batch_exec, saga_gather_frames_exec
+extern "C" int saga_abi_version(void) { return 2; }   // 2: + saga_short_window_batch_exec, saga_gather_frames_exec, saga_cqt_frames_exec
 extern "C" int64_t saga_launch_count(void) { return saga::g_launches.load(); }

@@ -614,6 +614,145 @@ __global__ void __launch_bounds__(256) cqt_pad_kernel(const PadArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Frame-window contraction: only `frame_count` (<= 8) consecutive CQT columns per clip, starting at
+// frame_first[clip].  The producer loop takes `C[:, s:t]` of a full-window transform and `_resize`s it to 8
+// columns (util_audio.py:431-434, :384-409; training.py:340-388): whatever t - s is, every column it keeps lies
+// in [s, s + 8), so 250 of the 258 columns of each of its five per-note CQTs are never looked at.  Here a warp
+// owns 32 filters (lane = filter, its (re, im) bank columns are one 8-byte load) and keeps the 8 frames in
+// registers: per 4 kernel samples 4 coalesced bank loads + 8 broadcast 16-byte signal loads feed 64 FFMA.  The
+// decimation cascade and the reflect margins are the ones of the full transform, so interior and edge columns
+// are the same numbers (fp32 summation order aside).  Output is COMPACT: [clip][frame_count][frame_pitch].
+// ---------------------------------------------------------------------------
+constexpr int FW_MAXF = 8;
+constexpr int FW_MAX_OCT = 12;
+constexpr int FW_MAX_KS = 32;          // K slices at most
+constexpr int FW_TARGET_CTAS = 600;    // ~4 CTAs per SM
+struct FrameWinArgs {
+  const float* sig[FW_MAX_OCT];        // level buffer of the octave + its margin: sample 0 of clip 0
+  int64_t sig_stride[FW_MAX_OCT];
+  const float* bank[FW_MAX_OCT];
+  int n_fft[FW_MAX_OCT], n_filt[FW_MAX_OCT], hop[FW_MAX_OCT], first_bin[FW_MAX_OCT];
+  int n_bins, frame_count;
+  const int32_t* frame_first;
+  const int32_t* clip_frames;
+  float* mag_out;
+  int64_t frame_pitch, out_clip_stride;
+  // split-K for small batches (a pitch group of the note-relative transforms is a few dozen clips): the kernel
+  // length is cut into `ks` slices (blockIdx.x = column block * ks + slice), the slices' sums go to `partial`
+  // [slice][clip][octave][pstride filters][8 frames][re, im] and cqt_frame_window_finish_kernel adds them in slice
+  // order (deterministic) and takes the magnitudes
+  int ks, n_clips, n_oct, pstride;
+  float* partial;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) cqt_frame_window_kernel(const FrameWinArgs a) {
+  const int oct = blockIdx.y, clip = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nf = a.n_filt[oct];
+  const int slice = blockIdx.x % a.ks, cblock = blockIdx.x / a.ks;
+  const int filt0 = (cblock * (blockDim.x >> 5) + warp) * 32;
+  if (filt0 >= nf) return;
+  const int filt = min(filt0 + lane, nf - 1);
+  const int T = a.clip_frames[clip], f0 = a.frame_first[clip];
+  const int n_fft = a.n_fft[oct], hop = a.hop[oct];
+  const float* sig = a.sig[oct] + (int64_t)clip * a.sig_stride[oct] - (n_fft >> 1);
+  const float* y[FW_MAXF];
+#pragma unroll
+  for (int f = 0; f < FW_MAXF; ++f) {
+    const int t = max(min(f0 + f, T - 1), 0);       // frames past the clip re-read the last one; zeroed on output
+    y[f] = sig + (int64_t)t * hop;
+  }
+  float acc[FW_MAXF][2];
+#pragma unroll
+  for (int f = 0; f < FW_MAXF; ++f) acc[f][0] = acc[f][1] = 0.f;
+  if (T > 0) {
+    const float2* bk = reinterpret_cast<const float2*>(a.bank[oct]) + filt;
+    float4 x[FW_MAXF], xn[FW_MAXF];
+    float2 b[4], bn[4];
+    auto load = [&](int k0, float4 (&xx)[FW_MAXF], float2 (&bb)[4]) {
+#pragma unroll
+      for (int f = 0; f < FW_MAXF; ++f) {
+        if (VEC) {
+          xx[f] = __ldg(reinterpret_cast<const float4*>(y[f] + k0));
+        } else {
+          xx[f] = make_float4(__ldg(y[f] + k0), __ldg(y[f] + k0 + 1), __ldg(y[f] + k0 + 2), __ldg(y[f] + k0 + 3));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bb[i] = __ldg(bk + (int64_t)(k0 + i) * nf);
+    };
+    const int k_lo = slice * (n_fft / a.ks), k_hi = k_lo + n_fft / a.ks;
+    load(k_lo, x, b);
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+      if (k0 + 4 < k_hi) load(k0 + 4, xn, bn);
+#pragma unroll
+      for (int f = 0; f < FW_MAXF; ++f) {
+        acc[f][0] = fmaf(x[f].x, b[0].x, acc[f][0]); acc[f][1] = fmaf(x[f].x, b[0].y, acc[f][1]);
+        acc[f][0] = fmaf(x[f].y, b[1].x, acc[f][0]); acc[f][1] = fmaf(x[f].y, b[1].y, acc[f][1]);
+        acc[f][0] = fmaf(x[f].z, b[2].x, acc[f][0]); acc[f][1] = fmaf(x[f].z, b[2].y, acc[f][1]);
+        acc[f][0] = fmaf(x[f].w, b[3].x, acc[f][0]); acc[f][1] = fmaf(x[f].w, b[3].y, acc[f][1]);
+      }
+#pragma unroll
+      for (int f = 0; f < FW_MAXF; ++f) x[f] = xn[f];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = bn[i];
+    }
+  }
+  if (a.ks > 1) {
+    if (filt0 + lane < nf) {
+      float4* dst = reinterpret_cast<float4*>(
+          a.partial + ((((int64_t)slice * a.n_clips + clip) * a.n_oct + oct) * a.pstride + filt0 + lane) * (2 * FW_MAXF));
+#pragma unroll
+      for (int f = 0; f < FW_MAXF; f += 2) dst[f >> 1] = make_float4(acc[f][0], acc[f][1], acc[f + 1][0], acc[f + 1][1]);
+    }
+    return;
+  }
+  const int bin = a.first_bin[oct] + filt0 + lane;
+  const bool ok = filt0 + lane < nf && bin >= 0 && bin < a.n_bins;
+#pragma unroll
+  for (int f = 0; f < FW_MAXF; ++f) {
+    if (f >= a.frame_count) break;
+    const int64_t row = (int64_t)clip * a.out_clip_stride + (int64_t)f * a.frame_pitch;
+    const bool live = f0 + f >= 0 && f0 + f < T;
+    if (ok) a.mag_out[row + bin] = live ? sqrtf(acc[f][0] * acc[f][0] + acc[f][1] * acc[f][1]) : 0.f;
+    if (oct == 0 && blockIdx.x == 0 && warp == 0)
+      for (int64_t k = a.n_bins + lane; k < a.frame_pitch; k += 32) a.mag_out[row + k] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) cqt_frame_window_finish_kernel(const FrameWinArgs a) {
+  const int oct = blockIdx.y, clip = blockIdx.z;
+  const int filt = blockIdx.x * 256 + threadIdx.x;
+  const int T = a.clip_frames[clip], f0 = a.frame_first[clip];
+  if (oct == 0 && blockIdx.x == 0)
+    for (int f = 0; f < a.frame_count; ++f)
+      for (int64_t k = a.n_bins + threadIdx.x; k < a.frame_pitch; k += 256)
+        a.mag_out[(int64_t)clip * a.out_clip_stride + (int64_t)f * a.frame_pitch + k] = 0.f;
+  if (filt >= a.n_filt[oct]) return;
+  const int bin = a.first_bin[oct] + filt;
+  if (bin < 0 || bin >= a.n_bins) return;
+  float acc[2 * FW_MAXF];
+#pragma unroll
+  for (int i = 0; i < 2 * FW_MAXF; ++i) acc[i] = 0.f;
+  for (int sl = 0; sl < a.ks; ++sl) {
+    const float4* src = reinterpret_cast<const float4*>(
+        a.partial + ((((int64_t)sl * a.n_clips + clip) * a.n_oct + oct) * a.pstride + filt) * (2 * FW_MAXF));
+#pragma unroll
+    for (int q = 0; q < FW_MAXF / 2; ++q) {
+      const float4 v = src[q];
+      acc[4 * q] += v.x; acc[4 * q + 1] += v.y; acc[4 * q + 2] += v.z; acc[4 * q + 3] += v.w;
+    }
+  }
+  for (int f = 0; f < a.frame_count; ++f) {
+    const bool live = f0 + f >= 0 && f0 + f < T;
+    a.mag_out[(int64_t)clip * a.out_clip_stride + (int64_t)f * a.frame_pitch + bin] =
+        live ? sqrtf(acc[2 * f] * acc[2 * f] + acc[2 * f + 1] * acc[2 * f + 1]) : 0.f;
+  }
+}
+
 constexpr int TAIL_MAX = 16;   // partial tiles up to this many frames go to cqt_tail_kernel (cqt_umma.cu), not to the MMAs
 
 }  // namespace saga
@@ -709,13 +848,18 @@ extern "C" int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* p, int n_clips,
   int64_t b = ws_header_bytes(n_clips);
   for (int l = 0; l <= p->max_level; ++l)
     b += (int64_t)n_clips * cqt_level_pitch(p, l, max_len) * 4;
+  // split-K scratch of saga_cqt_frames_exec: slices * clips * octaves <= 2 * FW_TARGET_CTAS whenever it splits
+  int max_filt = 0;
+  for (auto& o : p->oct) max_filt = std::max(max_filt, o.n_filters);
+  b += (int64_t)2 * FW_TARGET_CTAS * ((max_filt + 31) & ~31) * 2 * FW_MAXF * 4 + 256;
   return b + 256;
 }
 
-extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
-                             const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
-                             void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
-                             void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
+                         const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
+                         void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                         void* workspace, int64_t workspace_bytes, int impl, void* stream,
+                         const int32_t* frame_first, int frame_count) {
   if (!p || !wav || !clip_offsets || !C_mag_out || !workspace)
     return set_error(SAGA_ERR_INVALID, "cqt_exec: null argument");
   if (frame_pitch < p->n_bins) return set_error(SAGA_ERR_INVALID, "cqt_exec: frame_pitch < n_bins");
@@ -844,6 +988,47 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
   }
 
   if (!do_contract) return SAGA_OK;
+  // ---- frame-window contraction (saga_cqt_frames_exec): a few columns per clip, compact output -------
+  if (frame_first) {
+    if ((int)p->oct.size() > FW_MAX_OCT) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_frames_exec: too many octaves");
+    FrameWinArgs fa;
+    bool vec = true;
+    int max_filt = 0;
+    for (size_t i = 0; i < p->oct.size(); ++i) {
+      const auto& o = p->oct[i];
+      fa.sig[i] = lvl[o.level] + pad[o.level];
+      fa.sig_stride[i] = pitch[o.level];
+      fa.bank[i] = o.bank;
+      fa.n_fft[i] = o.n_fft; fa.n_filt[i] = o.n_filters; fa.hop[i] = o.hop; fa.first_bin[i] = o.first_bin;
+      if ((o.hop & 3) || (o.n_fft & 7)) vec = false;
+      if (o.n_fft & 3) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_frames_exec: kernel length must be a multiple of 4");
+      max_filt = std::max(max_filt, o.n_filters);
+    }
+    fa.n_bins = p->n_bins; fa.frame_count = frame_count;
+    fa.frame_first = frame_first; fa.clip_frames = clip_frames;
+    fa.mag_out = C_mag_out; fa.frame_pitch = frame_pitch; fa.out_clip_stride = out_clip_stride;
+    const int warps = std::min(8, (max_filt + 31) / 32);
+    const int cblocks = (max_filt + warps * 32 - 1) / (warps * 32);
+    // split-K until the launch has a few CTAs per SM (each CTA walks its K range serially, one L2 round trip per step)
+    int min_nfft = 1 << 30;
+    for (auto& o : p->oct) min_nfft = std::min(min_nfft, o.n_fft);
+    int ks = 1;
+    const int64_t ctas = (int64_t)cblocks * (int64_t)p->oct.size() * n_clips;
+    while (ks < FW_MAX_KS && ctas * ks < FW_TARGET_CTAS && min_nfft / (2 * ks) >= 64) ks *= 2;
+    fa.ks = ks; fa.n_clips = n_clips; fa.n_oct = (int)p->oct.size();
+    fa.pstride = (max_filt + 31) & ~31;
+    fa.partial = (float*)ws;           // tail of the workspace (saga_cqt_workspace_bytes reserves it)
+    dim3 grid((unsigned)(cblocks * ks), (unsigned)p->oct.size(), n_clips);
+    if (vec) cqt_frame_window_kernel<true><<<grid, warps * 32, 0, st>>>(fa);
+    else cqt_frame_window_kernel<false><<<grid, warps * 32, 0, st>>>(fa);
+    SAGA_LAUNCH_CHECK();
+    if (ks > 1) {
+      dim3 g2((unsigned)((max_filt + 255) / 256), (unsigned)p->oct.size(), n_clips);
+      cqt_frame_window_finish_kernel<<<g2, 256, 0, st>>>(fa);
+      SAGA_LAUNCH_CHECK();
+    }
+    return SAGA_OK;
+  }
   // ---- contraction -------------------------------------------------------------------
   CqtLevels lv;
   lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
@@ -905,4 +1090,24 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
     SAGA_LAUNCH_CHECK();
   }
   return SAGA_OK;
+}
+
+extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
+                             const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
+                             void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                             void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+  return cqt_exec_impl(p, wav, clip_offsets, clip_lens, n_clips, max_len, C_mag_out, C_cplx_out, frame_pitch,
+                       out_clip_stride, workspace, workspace_bytes, impl, stream, nullptr, 0);
+}
+
+extern "C" int saga_cqt_frames_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
+                                    const int64_t* clip_lens, int n_clips, int64_t max_len,
+                                    const int32_t* frame_first, int frame_count, float* C_mag_out,
+                                    int64_t frame_pitch, int64_t out_clip_stride, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  if (!frame_first) return set_error(SAGA_ERR_INVALID, "cqt_frames_exec: null frame_first");
+  if (frame_count < 1 || frame_count > FW_MAXF)
+    return set_error(SAGA_ERR_INVALID, "cqt_frames_exec: frame_count must be in 1..%d", FW_MAXF);
+  return cqt_exec_impl(p, wav, clip_offsets, clip_lens, n_clips, max_len, C_mag_out, nullptr, frame_pitch,
+                       out_clip_stride, workspace, workspace_bytes, 1, stream, frame_first, frame_count);
 }

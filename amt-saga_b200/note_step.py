@@ -47,6 +47,7 @@ class NoteStepBatch:
         self._fft_freq = np.linspace(0, float(sr) / 2, int(1 + self.N // 2), endpoint=True)   # util_audio.py:67
         self.mag = self.ph = self.wav = None
         self.fresh = True
+        self.full_cqt = False      # True: every slice_C transforms all 258 columns like the reference (A/B twin)
 
     # ------------------------------------------------------------------ helpers (host, float64)
     def midi_tone_to_FFT(self, tone):          # util_audio.py:278-284
@@ -91,9 +92,17 @@ class NoteStepBatch:
     def _cqt_columns(self, wav, lowest_midi, nbins, bpt, s, t, n_cols, inv_ref):
         plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(lowest_midi), int(nbins), int(12 * bpt), 2, device=self.dev)
         plan.check_length(int(wav.shape[1]))
+        Tc = plan.num_frames(int(wav.shape[1]))
+        src = self._resize_map(s, t, Tc, n_cols)                                     # C[:, s:t] -> _resize
+        if n_cols <= 8 and not self.full_cqt:
+            # whatever t - s is, `_resize` keeps columns of [s, s + n_cols): contract only those (K2 frame window)
+            first = np.clip(s, 0, max(Tc - 1, 0)).astype(np.int32)
+            C = ops.cqt_frames_batch(wav, plan, first, n_cols)                       # [W', n_cols, Pc]
+            rel = np.where(src >= 0, src - first[:, None], -1)
+            assert rel.max(initial=-1) < n_cols
+            return ops.gather_frames_batch(C, nbins, rel, inv_ref)                   # / ref_C
         C = ops.cqt_batch(wav, plan)["mag_storage"]                                  # [W', Tc, Pc]
-        src = self._resize_map(s, t, C.shape[1], n_cols)                             # C[:, s:t] -> _resize
-        return ops.gather_frames_batch(C, nbins, src, inv_ref)                       # / ref_C
+        return ops.gather_frames_batch(C, nbins, src, inv_ref)
 
     def step(self, onset, duration, pitch, guess_wav, guess_lens=None, subtract=True):
         """onset / duration (seconds, relative to the window) and MIDI pitch per window (host arrays, [W]);
@@ -131,23 +140,43 @@ class NoteStepBatch:
                                              self.instrument_frames, self.inv_ref_C[1])
         out["C_sw_inst_foc_const"] = self._cqt_columns(self.wav, 60, self.instrument_bands, self.inst_bpt * 4, s, t,
                                                        self.instrument_frames, self.inv_ref_C[2])
-        # the two note-relative transforms have one kernel bank per pitch: windows are grouped by pitch
+        # the two note-relative transforms have one kernel bank per pitch: windows are sorted by pitch once, every
+        # pitch group contracts its <= 8 columns straight into its slice of ONE compact buffer, and one gather
+        # (C[:, s:t] -> _resize -> / ref_C_foc) serves all windows
         valid = np.ones(W, dtype=bool)
-        foc = torch.full((W, self.instrument_bands, self.instrument_frames), float("nan"), device=self.dev)
-        vel = torch.full((W, self.bins_velocity, self.instrument_frames), float("nan"), device=self.dev)
-        for p in np.unique(pitch):
-            rows = np.nonzero(pitch == p)[0]
-            idx = torch.as_tensor(rows, device=self.dev)
-            sub = self.wav if len(rows) == W else self.wav.index_select(0, idx)
-            try:
-                f = self._cqt_columns(sub, int(p), self.instrument_bands, self.inst_bpt * 4, s[rows], t[rows],
-                                      self.instrument_frames, self.inv_ref_C[2][idx])
-                v = self._cqt_columns(sub, int(p) - 10, self.bins_velocity, 2, s[rows], t[rows],
-                                      self.instrument_frames, self.inv_ref_C[2][idx])
-            except ParameterError:          # librosa: "Filter pass-band lies beyond Nyquist" -> the loop skips the file
-                valid[rows] = False
-                continue
-            foc[idx], vel[idx] = f, v
+        order = np.argsort(pitch, kind="stable")
+        inv_order = torch.as_tensor(np.argsort(order), device=self.dev)
+        order_dev = torch.as_tensor(order, device=self.dev)
+        wav_s = self.wav.index_select(0, order_dev)
+        s_s, t_s, p_s = s[order], t[order], pitch[order]
+        nf = self.instrument_frames
+        res = []
+        for nbins, bpt, shift in ((self.instrument_bands, self.inst_bpt * 4, 0), (self.bins_velocity, 2, -10)):
+            P = ops.frame_pitch(nbins)
+            Tc = 1 + int(self.wav.shape[1]) // self.hl
+            src = self._resize_map(s_s, t_s, Tc, nf)
+            first = np.clip(s_s, 0, max(Tc - 1, 0)).astype(np.int32)
+            full = self.full_cqt
+            buf = torch.zeros((W, Tc if full else nf, P), device=self.dev, dtype=torch.float32)
+            a = 0
+            while a < W:
+                b = a + int(np.searchsorted(p_s[a:], p_s[a], side="right"))
+                try:
+                    plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(int(p_s[a]) + shift), int(nbins),
+                                            int(12 * bpt), 2, device=self.dev)
+                    plan.check_length(int(self.wav.shape[1]))
+                    if full:
+                        buf[a:b] = ops.cqt_batch(wav_s[a:b], plan)["mag_storage"]
+                    else:
+                        ops.cqt_frames_batch(wav_s[a:b], plan, first[a:b], nf, out=buf[a:b])
+                except ParameterError:      # librosa: "Filter pass-band lies beyond Nyquist" -> the loop skips the file
+                    valid[order[a:b]] = False
+                    buf[a:b] = float("nan")
+                a = b
+            rel = src if full else np.where(src >= 0, src - first[:, None], -1)
+            g = ops.gather_frames_batch(buf, nbins, rel, self.inv_ref_C[2].index_select(0, order_dev))
+            res.append(g.index_select(0, inv_order))
+        foc, vel = res
         out["C_sw_inst_foc"], out["C_velocity"] = foc, vel
         off = np.maximum(s, 0).astype(np.int32)       # util_audio.py:248 with attack_compensation 0
         out["valid"], out["offset_frames"] = valid, off

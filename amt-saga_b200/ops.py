@@ -305,6 +305,32 @@ def cqt_batch(wav, plan, lens=None, want_complex=False, impl=0, fill=None):
     return out
 
 
+def cqt_frames_batch(wav, plan, frame_first, frame_count=8, lens=None, out=None):
+    """saga_cqt_frames_exec: only columns [frame_first[c], frame_first[c] + frame_count) of each clip's CQT
+    magnitude (what slice_C + _resize keep).  Returns compact frame-major storage [clips, frame_count, P]
+    (`out`: write into this preallocated contiguous slice instead)."""
+    wav, offs, lens_dev, max_len = _clip_table(wav, lens)
+    n_clips = wav.shape[0]
+    lib = _lib.lib()
+    P = frame_pitch(plan.n_bins)
+    dev = wav.device
+    first = torch.as_tensor(np.ascontiguousarray(frame_first, dtype=np.int32), device=dev) \
+        if not isinstance(frame_first, torch.Tensor) else frame_first.to(device=dev, dtype=torch.int32).contiguous()
+    if first.shape != (n_clips,):
+        raise ValueError("frame_first must be [clips]")
+    if out is None:
+        out = torch.empty((n_clips, int(frame_count), P), device=dev, dtype=torch.float32)
+    elif out.shape != (n_clips, int(frame_count), P) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out must be contiguous float32 [clips, frame_count, %d]" % P)
+    nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
+    ws = _workspace(nbytes, dev)
+    with _on(wav, plan):
+        _lib.check(lib.saga_cqt_frames_exec(plan.handle, _ptr(wav), _ptr(offs), _ptr(lens_dev) if lens is not None else None,
+                                            n_clips, max_len, _ptr(first), int(frame_count), _ptr(out), P,
+                                            int(frame_count) * P, _ptr(ws), ws.numel(), _stream(wav)), ParameterError)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # K3
 # ---------------------------------------------------------------------------

@@ -219,6 +219,17 @@ int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* cl
                   void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
                   void* workspace, int64_t workspace_bytes, int impl, void* stream);
 
+/* Frame-window form of K2 for the producer loop's per-note calls (training.py:340-388): slice_C takes `C[:, s:t]`
+ * of a full-window transform and `_resize`s it to 8 columns (util_audio.py:431-434, :384-409), so only columns
+ * [s, s+8) are ever used.  Same cascade and reflect margins as saga_cqt_exec, but only the `frame_count` (1..8)
+ * columns starting at frame_first[c] (device int32, may point past the clip: those columns are written as 0) are
+ * contracted.  Output is COMPACT: column j of clip c at C_mag_out + c*out_clip_stride + j*frame_pitch. */
+int saga_cqt_frames_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
+                         const int64_t* clip_lens, int n_clips, int64_t max_len,
+                         const int32_t* frame_first, int frame_count, float* C_mag_out,
+                         int64_t frame_pitch, int64_t out_clip_stride, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * K5  feature gather for the classifiers (training.py:333-388)
  * ---------------------------------------------------------------------- */

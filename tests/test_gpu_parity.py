@@ -370,6 +370,36 @@ def test_cqt_matches_oracle(saga, cfg1, sr, hop, low, n_bins, bpo, n, impl):
     check_mag(r["C"][0].cpu().numpy(), ref, tol=tol)
 
 
+@pytest.mark.parametrize("sr,hop,low,n_bins,bpo,n", [c for c in CQT_CASES if c[0] == 44100 and c[1] == 1024])
+def test_cqt_frame_window_equals_columns_of_the_full_transform(saga, sr, hop, low, n_bins, bpo, n):
+    """saga_cqt_frames_exec (the per-note form: only the <= 8 columns slice_C + _resize keep) against the same
+    columns of the full transform and of the oracle, at the clip start, in the interior, across the clip end and
+    past it (zeros), on a ragged batch."""
+    ops, _ = saga
+    fmin = osp.note_to_hz(low)
+    plan = ops.CqtPlan(sr, hop, fmin, n_bins, bpo, filter_scale=2)
+    lens = [n, n - 5000, n - 1]
+    wav = np.zeros((3, n), dtype=np.float32)
+    for i, m in enumerate(lens):
+        wav[i, :m] = piano_clip(50 + i, m, sr=sr)
+    full = ops.cqt_batch(dev(wav), plan, lens=lens, impl=1)["mag"].cpu().numpy()          # [3, bins, T]
+    for first in ([0, 0, 0], [3, 11, 20], [n // hop - 2, (n - 5000) // hop - 6, n // hop + 5]):
+        got = ops.cqt_frames_batch(dev(wav), plan, np.array(first, dtype=np.int32), 8, lens=lens)
+        got = got[:, :, :n_bins].transpose(1, 2).cpu().numpy()                           # [3, bins, 8]
+        for i, m in enumerate(lens):
+            T = plan.num_frames(m)
+            ref = np.abs(ocqt.cqt(wav[i, :m], sr=sr, hop_length=hop, fmin=fmin, n_bins=n_bins, bins_per_octave=bpo,
+                                  filter_scale=2)) if first[0] == 3 else None
+            for j in range(8):
+                t = first[i] + j
+                if t >= T:
+                    assert np.all(got[i, :, j] == 0)
+                    continue
+                assert np.abs(got[i, :, j] - full[i, :, t]).max() <= 5e-6 * full[i].max()
+                if ref is not None:
+                    assert np.abs(got[i, :, j] - ref[:, t]).max() <= 1e-5 * ref.max()
+
+
 def test_cqt_ragged_batch(saga):
     ops, _ = saga
     sr, hop = 44100, 512

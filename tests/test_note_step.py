@@ -32,7 +32,8 @@ def test_resize_map_equals_reference_resize_on_column_indices():
 
 
 @pytest.mark.gpu
-def test_batched_note_step_matches_reference_class_golden():
+@pytest.mark.parametrize("full_cqt", [False, True], ids=["frame_window_cqt", "full_window_cqt"])
+def test_batched_note_step_matches_reference_class_golden(full_cqt):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -51,6 +52,7 @@ def test_batched_note_step_matches_reference_class_golden():
         mags.append(w._mag.st), phs.append(w._ph.st), wavs.append(w._wf)
     assert len({int(x.numel()) for x in wavs}) == 1
     batch = NoteStepBatch(W)
+    batch.full_cqt = full_cqt
     batch.load(torch.stack(mags), torch.stack(phs), torch.stack(wavs),
                [float(gold["w%d_song_ref_mag" % w]) for w in range(W)], np.stack([gold["w%d_ref_C" % w] for w in range(W)]))
     names = {"C_timing": "C_timing", "C_sw_pitch": "C_sw_pitch", "C_sw_inst": "C_sw_inst", "F_sw_inst_foc": "F_foc",
