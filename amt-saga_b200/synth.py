@@ -35,9 +35,12 @@ def piano_batch(clip_ids, n_samples, sr=44100, n_notes=24, seed_base=1234, devic
             for h in range(1, 9):
                 f = h * f0 * math.sqrt(1 + 1e-4 * h * h)
                 y += torch.where(f < sr / 2, env / h, torch.zeros_like(env)) * torch.sin(2 * math.pi * f * tt)
+        # noise floor: one generator state per CLIP (not per chunk), so that a clip is the same audio whichever
+        # rank or chunk it is generated in (cfg5 compares checksums across 1/2/4/8-GPU partitions)
         g = torch.Generator(device=device)
-        g.manual_seed(seed_base * 7919 + ids[0])
-        y += 1e-3 * torch.randn(y.shape, device=device, generator=g)
+        for i, cid in enumerate(ids):
+            g.manual_seed(seed_base * 7919 + cid)
+            y[i] += 1e-3 * torch.randn(n_samples, device=device, generator=g)
         y *= 0.9 / y.abs().amax(dim=1, keepdim=True).clamp_min(1e-12)
         out[c0:c0 + len(ids)] = y
     return out

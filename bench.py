@@ -207,6 +207,100 @@ class ClockSampler:
         return out
 
 
+
+# ----------------------------------------------------------------------------- extra measurements (N = 1)
+def measure_tf32_peak(torch, dev, n=8192, iters=10):
+    """the tensor fraction of a TF32 kernel is quoted against a TF32 GEMM measured the same way
+    as MEASURED_PEAKS.json's bf16 figure (torch.matmul, 8192^3, best of `iters`, CUDA events)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        c = torch.empty((n, n), device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best / 1e9
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def measure_cfg4(torch, ops, dev, hbm_peak, n_windows=4096, steps=5):
+    """BASELINE config 4: 4096 windows [1025, 516] x 16 guessed-note spectrograms [1025, 128], applied sequentially per
+    window (current-max ref at every step), ReLU, then dB -- through K3's chain kernel.  Random magnitudes of the right
+    shapes (timing; the arithmetic is bit-exact against numpy in tests/test_gpu_parity.py)."""
+    B, T, Tg, S = 1025, 516, 128, 16
+    P = ops.frame_pitch(B)
+    g = torch.Generator(device=dev).manual_seed(1)
+    win = torch.rand((n_windows, T, P), device=dev, generator=g)
+    base = win.clone()
+    gue = torch.rand((n_windows, S, Tg, P), device=dev, generator=g)
+    offs = torch.randint(0, T, (n_windows, S), device=dev, generator=g, dtype=torch.int32)
+    D = torch.empty_like(win)
+    gref = gue.amax(dim=(2, 3))
+    ms = []
+    for i in range(steps + 1):
+        win.copy_(base)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.subtract_db_batch(win, gue, offs, B, D_out=D, guess_ref=gref)
+        b.record()
+        torch.cuda.synchronize()
+        if i:
+            ms.append(a.elapsed_time(b))
+    t = sorted(ms)[len(ms) // 2]
+    alg = n_windows * 4 * B * (2 * T + S * Tg)      # read mag + read 16 guesses + write one output (SURVEY 8d)
+    del win, base, gue, D
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4: %d windows x 16 guesses, subtract chain + dB" % n_windows, "ms": t,
+            "windows_per_s": n_windows / t * 1e3, "GBps": alg / t / 1e6, "frac": alg / t / 1e6 / hbm_peak,
+            "bound": "hbm", "kernel": "subtract_chain_cluster_kernel (K3, 16 sequential steps + dB)",
+            "algorithmic_bytes": alg, "steps": steps}
+
+
+def measure_note_step(torch, ops, synth, dev, n_windows=600, steps=5):
+    """One batched iteration of the reference's per-note loop in ITS order (training.py:333-449) for 600 windows of
+    its own shape (N 4096, hop 1024, 258 frames): K4 iSTFT of the subtracted windows -> the five slice_C shapes -> K5 ->
+    guess STFT -> K3 (amt_saga_b200.note_step.NoteStepBatch; parity vs the reference's class: tests/test_note_step.py)."""
+    from amt_saga_b200.note_step import NoteStepBatch
+    L = 264168
+    wav = synth.piano_batch(range(n_windows), L, SR, seed_base=50000, device=dev)
+    plan = ops.get_stft_plan(4096, 1024, True, device=dev)
+    r = ops.stft_batch(wav, plan, want_phase=True)
+    b = NoteStepBatch(n_windows, device=dev)
+    b.load(r["mag_storage"][:, :258].contiguous(), r["phase_storage"][:, :258].contiguous(), wav, r["clip_max"],
+           np.ones((n_windows, 3)))
+    guess = synth.piano_batch(range(n_windows), 54277, SR, n_notes=1, seed_base=90000, device=dev)
+
+    def one(seed):
+        rg = np.random.default_rng(seed)
+        b.step(rg.uniform(0, 5.0, n_windows), rg.uniform(0.2, 1.2, n_windows), rg.integers(48, 72, n_windows), guess)
+    for i in range(3):          # builds (and caches) the note-relative CQT plans (one bank per pitch)
+        one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(10 + i)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    del b, wav, guess, r
+    torch.cuda.empty_cache()
+    return {"workload": "one per-note iteration of training.py:333-449 for %d windows (N 4096, hop 1024, 258 frames, 24 "
+                        "distinct pitches): iSTFT + 5 CQT shapes + K5 + guess STFT + subtract" % n_windows,
+            "ms_per_step": ms, "us_per_note": ms / n_windows * 1e3, "notes_per_s": n_windows / ms * 1e3,
+            "timing": "wall clock around the host call (includes the per-pitch host loop), synchronised",
+            "unbatched_class_ms_per_note": 2.97, "steps": steps}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_saga(args):
     import torch
@@ -343,7 +437,8 @@ def run_saga(args):
     sub_bytes = W * pipe.subtract_bytes_per_window()
     cqt_flops = W * pipe.cqt_flops_per_window()
     casc_bytes = W * 4 * pipe.ns * 2          # each level read once, written once at half the length: <= 2x the input
-    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tpeak_bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tpeak = measure_tf32_peak(torch, dev)       # the contraction runs kind::tf32: quote it against a TF32 GEMM
     stages = {
         "stft": {"ms": stage_ms.get("stft"), "bound": "hbm", "GBps": stft_bytes / stage_ms["stft"] / 1e6},
         "stft_guess": {"ms": stage_ms.get("stft_guess"), "bound": "hbm", "GBps": gst_bytes / stage_ms["stft_guess"] / 1e6},
@@ -359,7 +454,7 @@ def run_saga(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    kernels = {"stft": "stft_kernel<1024,32,32,1,10> (K1, window batch)", "stft_guess": "stft_kernel<1024,32,32,1,10> (K1, guess batch)",
+    kernels = {"stft": "stft_ring_kernel<19,20> (K1 ring kernel, window batch)", "stft_guess": "stft_ring_kernel<19,20> (K1 ring kernel, guess batch)",
                "subtract_db": "subtract_single_flat_kernel + window_db_lean_kernel<256,12> (K3)",
                "cqt_cascade": "decimate2x2_kernel x 2 + decimate2_kernel x 3 + cqt_pad_kernel (K2a)",
                "cqt_contract": "cqt_umma_kernel (tcgen05) + cqt_tail_kernel (K2b)"}
@@ -373,7 +468,7 @@ def run_saga(args):
         roof = {"kernel": "cqt_umma_kernel (tcgen05 kernel-bank contraction)", "bound": "tensor",
                 "achieved": stages[dom]["TFLOPs_algorithmic"], "peak": tpeak, "unit": "TFLOP/s",
                 "frac": stages[dom]["frac"], "traffic": tr,
-                "peak_source": "cuBLAS bf16 sustained, " + peak_src,
+                "peak_source": "TF32 torch.matmul 8192^3 measured in this run",
                 "note": "algorithmic flops = 172704/frame (SURVEY 8d); the 3xTF32 split issues 3.33x that (N=48 main + N=32 correction MMA per 24 useful columns); "
                         "an SS-mode tcgen05.mma is paced by the SMEM bytes it reads: 44-48 cycles for N<=64 (profiles/microbench)"}
     else:
@@ -405,6 +500,19 @@ def run_saga(args):
             del p2
         except Exception as e:      # informational only
             ref_shape = {"error": repr(e)[:200]}
+
+    cfg4 = note_step = None
+    if world == 1 and not args.no_extras:
+        for name, fn in (("cfg4", lambda: measure_cfg4(torch, ops, dev, hbm_peak)),
+                         ("note", lambda: measure_note_step(torch, ops, synth, dev))):
+            try:
+                res = fn()
+            except Exception as e:      # reported beside the headline, never instead of it
+                res = {"error": repr(e)[:300]}
+            if name == "cfg4":
+                cfg4 = res
+            else:
+                note_step = res
 
     cpu = None
     if world == 1 and args.cpu_windows > 0:
@@ -444,9 +552,94 @@ def run_saga(args):
         "stages": stages,
         "cpu_baseline": cpu,
         "reference_default_shape": ref_shape,
+        "cfg4": cfg4,
+        "per_note_batched": note_step,
+        "tensor_peaks": {"tf32_tflops_measured_here": tpeak, "bf16_tflops_sustained": tpeak_bf16,
+                         "how": "torch.matmul 8192^3, allow_tf32, best of 10 (CUDA events); bf16 from MEASURED_PEAKS.json"},
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+# ----------------------------------------------------------------------------- BASELINE config 5
+def run_cfg5(args):
+    """Corpus-scale sharded feature extraction: `hours` x 360 clips of 10 s (clip c = piano generator with
+    seed 1234 + c), contiguous clip ranges per rank, generated ON DEVICE in 1 h chunks (the 127 GB of input never
+    exist at once), STFT magnitude (2048 / 512) + CQT (84 bins, 12 per octave) per clip, of which only a per-clip
+    checksum is kept.  No collective on the path; one all_gather of the checksums at the end.  Prints ONE JSON line:
+    clips/s end to end (generation included) and for the feature kernels alone, and the gathered checksum, which must
+    be identical for every GPU count."""
+    import torch
+    import torch.distributed as dist
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops, shard, synth
+    from amt_saga_b200.util_audio import note_to_hz
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    clips_total = int(round(args.cfg5_hours * 360))
+    ns, chunk = 441000, 360
+    lo, hi = shard.shard_range(clips_total, rank, world)
+    sp = ops.get_stft_plan(N_FFT, HOP, True, device=dev)
+    cp = ops.get_cqt_plan(SR, HOP, note_to_hz("C1"), 84, 12, 2, device=dev)
+
+    def features(ids):
+        wav = synth.piano_batch(ids, ns, SR, seed_base=1234, device=dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        m = ops.stft_batch(wav, sp, want_max=False)["mag_storage"]
+        c = ops.cqt_batch(wav, cp)["mag_storage"]
+        b.record()
+        # per-clip checksum of the exact bit patterns (wraps in int64: order-independent, partition-independent)
+        cs = m.view(torch.int32).to(torch.int64).sum(dim=(1, 2)) + 31 * c.view(torch.int32).to(torch.int64).sum(dim=(1, 2))
+        return cs, (a, b), m.shape[1]
+
+    features(list(range(min(4, max(hi - lo, 1)))))       # warm-up: plans, allocator
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    parts, evs, frames = [], [], 0
+    for a, b in shard.chunks(lo, hi, chunk):
+        cs, ev, T = features(list(range(a, b)))
+        parts.append(cs)
+        evs.append(ev)
+        frames += (b - a) * T
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kern_ms = sum(a.elapsed_time(b) for a, b in evs)
+    local_cs = torch.cat(parts) if parts else torch.zeros(0, device=dev, dtype=torch.int64)
+    allcs = shard.gather_ragged(local_cs) if world > 1 else local_cs
+    t = torch.tensor([wall, kern_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, kern_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        assert allcs.numel() == clips_total
+        total = int(allcs.sum().item())
+        line = {"metric": "clips/s (cfg5: sharded STFT + CQT over a generated corpus)", "value": clips_total / wall,
+                "unit": "clips/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic (generated on device per shard, seeds 1234 + clip id)",
+                "config": {"workload": "cfg5: %.1f h = %d clips of 10 s at 44.1 kHz, 1 h chunks, STFT 2048/512 + CQT 84/12, "
+                                       "per-clip checksums gathered" % (args.cfg5_hours, clips_total),
+                           "partition": "contiguous clip ranges per rank, no collective on the path"},
+                "wall_s": wall, "hours_of_audio_per_s": args.cfg5_hours / wall,
+                "feature_kernels_only": {"ms": kern_ms, "clips_per_s": (hi - lo) * world / kern_ms * 1e3,
+                                         "note": "CUDA events around K1 + K2 of every chunk on the slowest rank; the rest of "
+                                                 "the wall time is the on-device audio generator"},
+                "checksum": total, "checksum_clip0": int(allcs[0].item()), "checksum_last": int(allcs[-1].item())}
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -463,9 +656,15 @@ def main():
     ap.add_argument("--cqt-impl", type=int, default=0)
     ap.add_argument("--e2e-chunks", type=int, default=12, help="window chunks for H2D/compute/D2H overlap")
     ap.add_argument("--no-ref-shape", action="store_true", help="skip the extra pass at the reference's default n_fft/hop")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 chain and batched per-note measurements")
+    ap.add_argument("--cfg5-hours", type=float, default=0.0,
+                    help="BASELINE config 5 instead of the step bench: this many hours of synthetic audio (360 clips of 10 s per "
+                         "hour), block-partitioned over the ranks, generated on device in 1 h chunks, STFT + CQT, checksum gathered")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.cfg5_hours > 0:
+        run_cfg5(args)
     else:
         run_saga(args)
 
