@@ -778,6 +778,8 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
 
   p->default_window = window_host ? 0 : 1;
   p->d_ring_tables = nullptr;
+  p->d_iring_tables = nullptr;
+  p->d_wsq = nullptr;
   std::vector<float> win(n_fft);
   for (int n = 0; n < n_fft; ++n)
     win[n] = window_host ? window_host[n] : (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / n_fft));
@@ -846,6 +848,10 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
     saga_stft_plan_destroy(p);
     return rc;
   }
+  if (int rc = saga::istft_ring_build_tables(p)) {
+    saga_stft_plan_destroy(p);
+    return rc;
+  }
   *out = p;
   return SAGA_OK;
 }
@@ -858,6 +864,8 @@ extern "C" int saga_stft_plan_destroy(saga_stft_plan* p) {
   cudaFree(p->d_tw_eo);
   cudaFree(p->d_twN);
   cudaFree(p->d_ring_tables);
+  cudaFree(p->d_iring_tables);
+  cudaFree(p->d_wsq);
   delete p;
   return SAGA_OK;
 }
@@ -953,7 +961,21 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
     case 128: return launch_istft<128, 16, 8, 1, 8>(p, a, n_clips, st);
     case 256: return launch_istft<256, 16, 16, 1, 8>(p, a, n_clips, st);
     case 512: return launch_istft<512, 32, 16, 1, 8>(p, a, n_clips, st);
-    case 1024: return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
+    case 1024: {
+      // inverse ring kernel (istft_ring.cu): every frame transformed once, in-order overlap-add; SAGA_ISTFT_RING=0 keeps
+      // the first-generation kernel (A/B twin of the parity tests)
+      static const int ring_mode = [] { const char* e = getenv("SAGA_ISTFT_RING"); return e ? atoi(e) : 1; }();
+      // the ring kernel stages whole spectrogram rows with 16-byte bulk copies and stores sample pairs
+      const uintptr_t in_bits = reinterpret_cast<uintptr_t>(cplx_in) | reinterpret_cast<uintptr_t>(mag_in) |
+                                reinterpret_cast<uintptr_t>(phase_in);
+      const bool aligned = (wav_clip_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(wav_out) & 7) == 0 &&
+                           (in_bits & 15) == 0 && (frame_pitch & 3) == 0 && frame_pitch >= p->M + 4 &&
+                           (in_clip_stride & 3) == 0;
+      if (ring_mode > 0 && aligned && saga::istft_ring_supported(p))
+        return saga::launch_istft_ring(p, cplx_in, mag_in, phase_in, n_clips, n_frames, frame_pitch, in_clip_stride,
+                                       wav_out, wav_clip_stride, st);
+      return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
+    }
     case 2048:
       if (getenv("SAGA_ISTFT_ONE_WARP")) return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // A/B
       return launch_istft<2048, 16, 16, 8, 16>(p, a, n_clips, st);

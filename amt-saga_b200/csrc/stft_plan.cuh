@@ -19,6 +19,8 @@ struct saga_stft_plan {
   size_t smem_bytes;
   int default_window;     // periodic Hann (w[n + N/2] = 1 - w[n]): the ring kernel's fused first stage relies on it
   float2* d_ring_tables;  // shared-memory image of the ring kernel's tables (stft_ring.cu), or NULL
+  float2* d_iring_tables; // the same for the inverse ring kernel (istft_ring.cu), or NULL
+  float* d_wsq;           // window^2 (inverse ring kernel, clip-edge blocks)
 };
 
 namespace saga {
@@ -45,5 +47,12 @@ struct StftArgs {
 bool stft_ring_supported(const saga_stft_plan* p);
 int stft_ring_build_tables(saga_stft_plan* p);
 int launch_stft_ring(const saga_stft_plan* p, const StftArgs& a, int n_clips, int64_t max_frames, cudaStream_t st);
+
+// istft_ring.cu
+bool istft_ring_supported(const saga_stft_plan* p);
+int istft_ring_build_tables(saga_stft_plan* p);
+int launch_istft_ring(const saga_stft_plan* p, const void* cplx_in, const float* mag_in, const void* phase_in,
+                      int n_clips, int n_frames, int64_t frame_pitch, int64_t in_clip_stride, float* wav_out,
+                      int64_t wav_clip_stride, cudaStream_t st);
 
 }  // namespace saga

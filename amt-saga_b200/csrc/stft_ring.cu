@@ -27,7 +27,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "fft_radix.cuh"
+#include "fft_packed.cuh"
 #include "saga_common.cuh"
 #include "stft_plan.cuh"
 
@@ -56,14 +56,6 @@ struct Shape {
 };
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
-// exp(-2 pi i k / 32), k = 1..7, as the two operand pairs of a two-instruction complex multiplication:
-// A = (c, -s), B = (s, c).  They travel as kernel parameters (constant bank -> uniform registers), where FMUL2 /
-// FFMA2 take them with swap / negation modifiers; literal constants would be rebuilt in general registers
-// (MOV / HFMA2 / FADD) in front of every use.
-struct Rot32 {
-  float2 A[8], B[8];
-};
-
 struct Args {
   StftArgs s;
   Rot32 w;
@@ -73,45 +65,6 @@ struct Args {
   int n_items;
 };
 
-typedef float2 f2;
-#define F2(a, b) make_float2((a), (b))
-
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, F2(-b.x, -b.y)); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-// d * (w.x + i w.y): FMUL2 (broadcast d.x) + FFMA2 (broadcast d.y, swapped / half-negated w)
-__device__ __forceinline__ f2 cmulp(f2 d, f2 w) { return fma2(F2(d.y, d.y), F2(-w.y, w.x), mul2(F2(d.x, d.x), w)); }
-
-// (neg ? -d : d) * exp(-2 pi i idx / 32), idx in [0, 16): two packed instructions on uniform-register
-// constants; the trivial angles become operand modifiers of the consuming packed add
-__device__ __forceinline__ f2 mulw(f2 d, int idx, bool neg, const Rot32& w) {
-  if (idx == 0) return neg ? F2(-d.x, -d.y) : d;
-  if (idx == 8) return neg ? F2(-d.y, d.x) : F2(d.y, -d.x);
-  const f2 dx = neg ? F2(-d.x, -d.x) : F2(d.x, d.x), dy = neg ? F2(-d.y, -d.y) : F2(d.y, d.y);
-  if (idx < 8) return fma2(dy, w.B[idx], mul2(dx, w.A[idx]));                 // dx (c, -s) + dy (s, c)
-  const f2 A = w.A[16 - idx], B = w.B[16 - idx];                             // c = -c', s = s'
-  return fma2(dy, F2(-A.y, -A.x), mul2(dx, F2(-B.y, -B.x)));                  // dx (-c', -s') + dy (s', -c')
-}
-
-// radix-2 DIF stages half = HALF0 .. 1 on 32 register-resident points; X[bitrev(i)] == v[i] afterwards
-template <int HALF0>
-__device__ __forceinline__ void fft32_tail(f2 (&v)[32], const Rot32& w) {
-#pragma unroll
-  for (int half = HALF0; half >= 1; half >>= 1) {
-#pragma unroll
-    for (int b = 0; b < 32; b += 2 * half) {
-#pragma unroll
-      for (int k = 0; k < half; ++k) {
-        const f2 a = v[b + k], c = v[b + k + half];
-        v[b + k] = add2(a, c);
-        v[b + k + half] = mulw(sub2(a, c), k * (16 / half), false, w);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -160,12 +113,6 @@ __device__ __forceinline__ void wait_issued(const uint32_t* cnt, uint32_t g) {
     __nanosleep(100);               // rare (start-up, run boundaries): do not steal issue slots from working warps
     if (++spins > (SPIN_LIMIT >> 4)) __trap();
   }
-}
-
-__device__ __forceinline__ float fast_sqrt(float x) {   // sqrt.approx: ~1 ulp, exact 0 -> 0
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
 }
 
 struct RunInfo {
@@ -513,11 +460,7 @@ static int launch_ring_shape(const saga_stft_plan* p, const StftArgs& s, int n_c
   int64_t runs = std::min(std::max(want, min_runs), std::max(max_runs, min_runs));
   Args a;
   a.s = s;
-  for (int k = 0; k < 8; ++k) {
-    const double th = 2.0 * 3.14159265358979323846 * k / 32.0;
-    a.w.A[k] = make_float2((float)std::cos(th), (float)-std::sin(th));
-    a.w.B[k] = make_float2((float)std::sin(th), (float)std::cos(th));
-  }
+  fill_rot32(a.w);
   a.tables = p->d_ring_tables;
   a.R = (int)((T + runs - 1) / runs);
   if (a.R < 4) a.R = 4;
@@ -535,10 +478,6 @@ int launch_stft_ring(const saga_stft_plan* p, const StftArgs& s, int n_clips, in
   // SAGA_STFT_RING_SHAPE=15: 15 + 1 warps at <= 128 registers (tuning aid); default 19 + 1 warps at <= 102
   static const int shape = [] { const char* e = getenv("SAGA_STFT_RING_SHAPE"); return e ? atoi(e) : 19; }();
   if (shape == 15) return launch_ring_shape<15, 24>(p, s, n_clips, max_frames, st);
-  if (shape == 1520) return launch_ring_shape<15, 20>(p, s, n_clips, max_frames, st);
-  if (shape == 1512) return launch_ring_shape<15, 12>(p, s, n_clips, max_frames, st);
-  if (shape == 1923) return launch_ring_shape<19, 23>(p, s, n_clips, max_frames, st);
-  if (shape == 1912) return launch_ring_shape<19, 12>(p, s, n_clips, max_frames, st);
   return launch_ring_shape<19, 20>(p, s, n_clips, max_frames, st);
 }
 

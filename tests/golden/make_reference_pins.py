@@ -49,6 +49,54 @@ def residual(wf, g, sub, **kw):
     return float(e.max()), float(np.sqrt((e ** 2).mean()))
 
 
+def wide_search(name):
+    """Second pass for the triples the quick grid misses: every integer frame offset, normalised or not, the
+    overkill factors the author experimented with, ReLU on / off, and the first cell's `center=False` guess STFT
+    (test_snippets.py:397-471).  Candidates are ranked on |STFT(sub)| (cheap), the best few are verified through
+    the oracle class + iSTFT against the 24-bit `_sub` file."""
+    from oracle import spectral as sp
+    wf, g, sub = load(name + "_test"), load(name + "_test_guess"), load(name + "_test_sub")
+    x, xg, xs = (wf / SCALE).astype(np.float32), (g / SCALE).astype(np.float32), (sub / SCALE).astype(np.float32)
+    mag = np.abs(sp.stft(x, N_FFT))
+    T = mag.shape[1]
+    target = np.abs(sp.stft(xs, N_FFT))[:, :T]
+    cands = []
+    for center in (True, False):
+        mg = np.abs(sp.stft(xg, N_FFT, center=center))
+        for normalize in (True, False):
+            for overkill in (1, 0.5, 2, 1.5, 3):
+                scale = (mag.max() / mg.max() if normalize else 1.0) * overkill
+                for off in range(0, T):
+                    m = mag.copy()
+                    w = min(mg.shape[1], T - off)
+                    m[:, off:off + w] -= scale * mg[:, :w]
+                    for relu in (True, False):
+                        mm = np.maximum(m, 0) if relu else m
+                        err = float(np.abs(np.abs(mm[:, :target.shape[1]]) - target).mean())
+                        cands.append((err, center, normalize, overkill, off, relu))
+    cands.sort(key=lambda c: c[0])
+    best = None
+    for err, center, normalize, overkill, off, relu in cands[:6]:
+        ac = AudioOracle(x, N_FFT)
+        if center:
+            sub_arg = AudioOracle(xg, N_FFT)
+        else:
+            sub_arg = np.abs(sp.stft(xg, N_FFT, center=False))      # raw-array subtrahend (util_audio.py:241-244)
+        s = ac.clone()
+        off_s = (off + 0.5) * len(x) / (T * 44100.0)
+        s.subtract(sub_arg, offset=off_s, normalize=normalize, relu=relu, overkill_factor=overkill)
+        w = np.asarray(s.wf, dtype=np.float64)
+        if len(w) != len(sub):
+            continue
+        e = np.abs(w * SCALE - sub)
+        r = (float(e.max()), float(np.sqrt((e ** 2).mean())),
+             dict(offset=off_s, offset_frames=off, attack_compensation=0, normalize=normalize, relu=relu,
+                  overkill_factor=overkill, guess_center=center))
+        if best is None or r[0] < best[0]:
+            best = r
+    return best
+
+
 def main():
     names = sorted(os.path.basename(p)[:-len("_test_sub.flac")] for p in glob.glob(DEMO + "*_test_sub.flac"))
     pins = {}
@@ -70,6 +118,10 @@ def main():
                     break
             if best[0] < 8:
                 break
+        if best[0] >= 8:
+            wide = wide_search(name)
+            if wide is not None and wide[0] < best[0]:
+                best = wide
         print("%-28s max %.3g LSB  rms %.3g LSB  %s" % (name, best[0], best[1], best[2]), flush=True)
         if best[0] < 8:          # 24-bit quantisation of input and output: a few LSB
             pins[name] = {"max_err_lsb24": best[0], "rms_err_lsb24": best[1], "n_fft": N_FFT,

@@ -1,4 +1,4 @@
-"""K1 at n_fft 2048 / hop 512 has two kernels: the ring kernel (csrc/stft_ring.cu, default for batches of
+"""K1 (and K4, the inverse) at n_fft 2048 / hop 512 have two kernels each: the ring kernel (csrc/stft_ring.cu, default for batches of
 >= 64 frames) and the first-generation kernel (csrc/stft.cu).  The library picks once per process
 (SAGA_STFT_RING), so each is forced in its own subprocess and checked against the CPU oracle on the cases
 the reference's path produces: ragged batches, clips shorter than the reflect pad, an all-zero clip, clips
@@ -101,13 +101,41 @@ def run_cases():
     frames = x.unfold(1, 2048, 512) * w
     rhs = 2048.0 * (frames ** 2).sum(dim=2)
     out["parseval"] = float(((lhs - rhs).abs() / rhs.clamp_min(1e-30)).max())
+
+    # ---- K4 (inverse): every frame count from 1 up (run / halo / flush logic), both input forms, both centerings
+    for center in (True, False):
+        plan = ops.StftPlan(2048, 512, center)
+        worst = 0.0
+        for n in (2048, 2048 + 512, 2048 + 2 * 512 + 9, 2048 + 3 * 512, 2048 + 7 * 512 + 1, 30000, 131072 + 77):
+            W = 3
+            wav = np.stack([piano_clip(60 + i, n, n_notes=4) for i in range(W)])
+            r = ops.stft_batch(torch.as_tensor(wav, device=dev), plan, want_phase=True, want_complex=True)
+            for kind in ("F", "magphase"):
+                y = (ops.istft_batch(plan, F=r["F_storage"]) if kind == "F" else
+                     ops.istft_batch(plan, mag=r["mag_storage"], phase=r["phase_storage"])).cpu().numpy()
+                for i in range(W):
+                    F = osp.stft(wav[i], 2048, 512, center=center)
+                    ref = osp.istft(F, hop_length=512, center=center)
+                    assert y[i].shape == ref.shape, (y[i].shape, ref.shape)
+                    ok = np.ones(len(ref), dtype=bool)
+                    if not center:      # 1 / sum w^2 is unbounded where the Hann window vanishes (first / last samples)
+                        ok = osp.window_sumsquare("hann", F.shape[1], 512, 2048)[:len(ref)] > 1e-2
+                    worst = max(worst, float(np.abs(y[i] - ref)[ok].max() / np.abs(ref).max()))
+        out["istft_center%d" % center] = worst
+    # round trip at size: istft(stft(x)) == x away from the clip edges, 64 clips x 517 frames
+    plan = ops.StftPlan(2048, 512, True)
+    wav = torch.as_tensor(np.stack([piano_clip(300 + i, 264600) for i in range(64)]), device=dev)
+    r = ops.stft_batch(wav, plan, want_complex=True)
+    y = ops.istft_batch(plan, F=r["F_storage"])
+    n = y.shape[1]
+    out["istft_roundtrip"] = float((y[:, 2048:n - 2048] - wav[:, 2048:n - 2048]).abs().max() / wav.abs().max())
     return out
 
 
 def _run(mode):
     code = ("import sys, json; sys.path.insert(0, %r); from tests.test_stft_ring import run_cases; "
             "print('RESULT ' + json.dumps(run_cases()))" % ROOT)
-    env = dict(os.environ, SAGA_STFT_RING=str(mode))
+    env = dict(os.environ, SAGA_STFT_RING=str(mode), SAGA_ISTFT_RING=str(mode))
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     return json.loads(p.stdout.split("RESULT ")[-1])
@@ -125,3 +153,4 @@ def test_stft_2048_kernels_match_oracle(mode):
         assert v <= tol, (k, v, res)
     # fp32 FFTs: both kernels are in fact far inside the 1e-4-of-peak bar
     assert max(res["ragged_center1"], res["ragged_center0"], res["unaligned"], res["many_laps"]) < 5e-6, res
+    assert max(res["istft_center1"], res["istft_center0"], res["istft_roundtrip"]) < 1e-5, res
