@@ -38,6 +38,8 @@ SIGNATURES = {
     "saga_last_error_string": (C.c_char_p, []),
     "saga_abi_version": (_I, []),
     "saga_launch_count": (_L, []),
+    "saga_set_option": (_I, [C.c_char_p, C.c_char_p]),
+    "saga_get_option": (C.c_char_p, [C.c_char_p]),
     "saga_pcm16_absmax_exec": (_I, [_P, _L, _I, _I, _L, _P, _P]),
     "saga_pcm16_ingest_exec": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _P, _P, _D, _D, _P]),
     "saga_stft_plan_create": (_I, [C.POINTER(_P), _I, _I, _I, _P]),

@@ -897,13 +897,13 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
   // ---- decimation cascade ----------------------------------------------------------
   const int tile_out = DEC_THREADS * DEC_PER_THREAD;
   // levels 1..max_level: 2:1 stages, fused two at a time (decimate2x2_kernel) when both are the 63-tap filter
-  const bool fuse = p->n_half_taps == DEC2_S + 1 && getenv("SAGA_DEC_NO_FUSE") == nullptr;
+  const bool fuse = p->n_half_taps == DEC2_S + 1 && SAGA_OPT("SAGA_DEC_NO_FUSE") == nullptr;
   // Which pairs: bit i set = the pair whose FIRST output is level i is fused.  Default: every pair (one stream, kernel
   // after kernel: cascade 0.582 -> 0.516 ms, step 3.038 -> 2.971 ms; when the CQT chain ran beside the STFT chain on a
   // second stream only the two large pairs paid -- profiles/microbench/cascade_fuse_b200.txt).  SAGA_DEC_FUSE_MASK
   // overrides (tuning aid).
   unsigned fuse_mask = ~0u;
-  if (const char* e = getenv("SAGA_DEC_FUSE_MASK")) fuse_mask = (unsigned)strtoul(e, nullptr, 0);
+  if (const char* e = SAGA_OPT("SAGA_DEC_FUSE_MASK")) fuse_mask = (unsigned)strtoul(e, nullptr, 0);
   int l = 1;
   // the early stage itself can be the first half of a fused pair (early factor 2 with the same kind of filter)
   const bool early_is_dec2 = do_cascade && p->early_factor == 2 && p->n_early_taps == DEC2_S + 1;
@@ -1048,7 +1048,7 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     a.sig = lvl[o.level] + pad[o.level];
     a.sig_offsets = nullptr;
     a.sig_stride = pitch[o.level];
-    a.padded = getenv("SAGA_CQT_CONTRACT_V1") ? 0 : 1;
+    a.padded = SAGA_OPT("SAGA_CQT_CONTRACT_V1") ? 0 : 1;
     (void)raw;
     a.clip_lens = clip_lens;
     a.max_len = max_len;
@@ -1067,7 +1067,7 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     a.frame_pitch = frame_pitch;
     a.out_clip_stride = out_clip_stride;
     a.clip_frames = clip_frames;
-    if (getenv("SAGA_CQT_CONTRACT_V1")) {          // first-generation kernel (A/B)
+    if (SAGA_OPT("SAGA_CQT_CONTRACT_V1")) {          // first-generation kernel (A/B)
       dim3 grid((unsigned)((T_max + CT_FRAMES - 1) / CT_FRAMES), (a.ncol + CT_FC - 1) / CT_FC, n_clips);
       cqt_contract_kernel<<<grid, CT_FRAMES, 0, st>>>(a);
     } else {

@@ -47,6 +47,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "cqt_plan.cuh"
@@ -806,7 +808,12 @@ struct CqtUmmaState {
   int* d_error = nullptr;
   long long* d_prof = nullptr;
   float* d_col_scale = nullptr;
-  cudaStream_t side = nullptr;   // tail kernel runs here, concurrently with the persistent kernel
+  // tail kernel runs on a side stream, concurrently with the persistent kernel: ONE side stream and event pair per
+  // CALLER stream (created on first use, reused afterwards), so two streams driving the same cached plan neither
+  // serialise on a plan-owned stream nor pay two cudaEventCreate per call
+  struct Fork { cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; };
+  mutable std::map<cudaStream_t, Fork> forks;
+  mutable std::mutex forks_mu;
   bool shared_bank = false;
   int num_sms = 0;
   int stages = 0, pps = 8;   // pipeline shape (SAGA_UMMA_CFG="stages,planes" overrides; stages 0 = as many as fit)
@@ -829,7 +836,7 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
   CqtUmmaState* st = new CqtUmmaState();
   p->umma = st;
   if ((int)p->oct.size() > UM_MAX_OCT) return;
-  if (const char* cfg = getenv("SAGA_UMMA_CFG")) {
+  if (const char* cfg = SAGA_OPT("SAGA_UMMA_CFG")) {
     int a_ = 0, b_ = 0;
     if (sscanf(cfg, "%d,%d", &a_, &b_) == 2 && a_ >= 0 && a_ <= UM_MAX_STAGES && a_ != 1 &&
         (b_ == 2 || b_ == 4 || b_ == 8)) {
@@ -884,7 +891,7 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
     const CqtOctaveDev& o0 = p->oct[0];
     const int ncol0 = 2 * o0.n_filters;
     std::vector<float> scale((size_t)p->oct.size() * UM_MAX_COLS, 0.f);
-    bool shared = p->oct.size() > 1 && getenv("SAGA_UMMA_NO_SHARED_BANK") == nullptr;
+    bool shared = p->oct.size() > 1 && SAGA_OPT("SAGA_UMMA_NO_SHARED_BANK") == nullptr;
     for (size_t i = 0; shared && i < p->oct.size(); ++i) {
       const CqtOctaveDev& o = p->oct[i];
       if (o.n_fft != o0.n_fft || o.n_filters != o0.n_filters) { shared = false; break; }
@@ -940,10 +947,6 @@ void cqt_umma_plan_init(saga_cqt_plan* p) {
     cudaGetLastError();
     return;
   }
-  if (cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking) != cudaSuccess) {
-    cudaGetLastError();
-    st->side = nullptr;
-  }
   st->supported = true;
 }
 
@@ -953,7 +956,11 @@ void cqt_umma_plan_free(saga_cqt_plan* p) {
   cudaFree(p->umma->d_error);
   cudaFree(p->umma->d_prof);
   cudaFree(p->umma->d_col_scale);
-  if (p->umma->side) cudaStreamDestroy(p->umma->side);
+  for (auto& kv : p->umma->forks) {
+    if (kv.second.ev_fork) cudaEventDestroy(kv.second.ev_fork);
+    if (kv.second.ev_join) cudaEventDestroy(kv.second.ev_join);
+    if (kv.second.side) cudaStreamDestroy(kv.second.side);
+  }
   delete p->umma;
   p->umma = nullptr;
 }
@@ -996,7 +1003,7 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   a.shared_bank = st->shared_bank ? 1 : 0;
   a.col_scale = st->d_col_scale;
   {
-    const char* dbg = getenv("SAGA_UMMA_DEBUG");
+    const char* dbg = SAGA_OPT("SAGA_UMMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
   }
   for (int i = 0; i < a.n_oct; ++i) {
@@ -1038,24 +1045,39 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
   const unsigned n_items = (unsigned)a.n_oct * (unsigned)n_clips;
   const unsigned tgrid = (n_items + UM_TAIL_WARPS - 1) / UM_TAIL_WARPS;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  const bool forked = tails && st->side && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-                      cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess;
+  cudaStream_t side = nullptr;
+  if (tails) {
+    std::lock_guard<std::mutex> lock(st->forks_mu);
+    auto it = st->forks.find(stream);
+    if (it == st->forks.end() && st->forks.size() < 64) {
+      CqtUmmaState::Fork f;
+      if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) == cudaSuccess &&
+          cudaEventCreateWithFlags(&f.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+          cudaEventCreateWithFlags(&f.ev_join, cudaEventDisableTiming) == cudaSuccess) {
+        it = st->forks.emplace(stream, f).first;
+      } else {
+        cudaGetLastError();
+        if (f.ev_fork) cudaEventDestroy(f.ev_fork);
+        if (f.side) cudaStreamDestroy(f.side);
+      }
+    }
+    if (it != st->forks.end()) { side = it->second.side; ev_fork = it->second.ev_fork; ev_join = it->second.ev_join; }
+  }
+  const bool forked = tails && side != nullptr;
   if (forked) {
     cudaEventRecord(ev_fork, stream);
-    cudaStreamWaitEvent(st->side, ev_fork, 0);
+    cudaStreamWaitEvent(side, ev_fork, 0);
   }
   cqt_umma_kernel<<<grid, UM_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
   if (tails) {
-    cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, forked ? st->side : stream>>>(a);
+    cqt_tail_kernel<<<tgrid, 32 * UM_TAIL_WARPS, 0, forked ? side : stream>>>(a);
     SAGA_LAUNCH_CHECK();
   }
   if (forked) {
-    cudaEventRecord(ev_join, st->side);
+    cudaEventRecord(ev_join, side);
     cudaStreamWaitEvent(stream, ev_join, 0);
   }
-  if (ev_fork) cudaEventDestroy(ev_fork);
-  if (ev_join) cudaEventDestroy(ev_join);
   if (a.debug & 16) {
     // profiling aid only: synchronous read-back of the per-role cycle counters, mean over CTAs
     std::vector<long long> h((size_t)grid * UM_PROF_SLOTS);

@@ -15,6 +15,11 @@ namespace saga {
 char* err_buf();
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+// run-time options (api.cu): SAGA_OPT("SAGA_X") is getenv("SAGA_X") read once at start-up, overridable through
+// saga_set_option; the id lookup happens once per call site
+int opt_id(const char* name);
+const char* opt_value(int id);
+#define SAGA_OPT(name) ([]() -> const char* { static const int id_ = saga::opt_id(name); return saga::opt_value(id_); }())
 
 #define SAGA_CUDA_OK(expr)                                                          \
   do {                                                                              \

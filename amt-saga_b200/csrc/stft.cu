@@ -835,7 +835,7 @@ extern "C" int saga_stft_plan_create(saga_stft_plan** out, int n_fft, int hop, i
   }
   if (F > groups) F = groups;   // one frame per warp (group): measured equal to two per warp on long clips (1.04 ms) and
                                 // better on short ones (128-frame guesses: 0.30 vs 0.32 ms) -- finer tiles, same overlap reuse
-  if (const char* e = getenv("SAGA_STFT_FRAMES")) F = std::max(1, std::min(F, atoi(e)));   // tuning aid
+  if (const char* e = SAGA_OPT("SAGA_STFT_FRAMES")) F = std::max(1, std::min(F, atoi(e)));   // tuning aid
   if (F < 1) F = 1;
   p->frames_per_cta = F;
   p->span_alloc = (((F - 1) * hop + n_fft) + 3) & ~3;
@@ -921,12 +921,13 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
       // ring kernel (stft_ring.cu) for the n_fft 2048 / hop 512 / Hann shape, whatever the batch size (the choice must
       // not depend on how a caller chunks its batch: the two kernels round differently); SAGA_STFT_RING=0 keeps the
       // first-generation kernel, the A/B twin of the parity tests
-      static const int ring_mode = [] { const char* e = getenv("SAGA_STFT_RING"); return e ? atoi(e) : 1; }();
+      const char* ring_opt = SAGA_OPT("SAGA_STFT_RING");
+      const int ring_mode = ring_opt ? atoi(ring_opt) : 1;
       if (ring_mode > 0 && saga::stft_ring_supported(p)) return saga::launch_stft_ring(p, a, n_clips, T, st);
       return launch_stft<1024, 32, 32, 1, 10>(p, a, n_clips, st);
     }
     case 2048:
-      if (getenv("SAGA_STFT_NO_EO")) return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // three-pass form (A/B)
+      if (SAGA_OPT("SAGA_STFT_NO_EO")) return launch_stft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // three-pass form (A/B)
       return launch_stft_eo4096<8>(p, a, n_clips, st);
     case 4096: return launch_stft<4096, 16, 16, 16, 8>(p, a, n_clips, st);
   }
@@ -964,7 +965,8 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
     case 1024: {
       // inverse ring kernel (istft_ring.cu): every frame transformed once, in-order overlap-add; SAGA_ISTFT_RING=0 keeps
       // the first-generation kernel (A/B twin of the parity tests)
-      static const int ring_mode = [] { const char* e = getenv("SAGA_ISTFT_RING"); return e ? atoi(e) : 1; }();
+      const char* ring_opt = SAGA_OPT("SAGA_ISTFT_RING");
+      const int ring_mode = ring_opt ? atoi(ring_opt) : 1;
       // the ring kernel stages whole spectrogram rows with 16-byte bulk copies and stores sample pairs
       const uintptr_t in_bits = reinterpret_cast<uintptr_t>(cplx_in) | reinterpret_cast<uintptr_t>(mag_in) |
                                 reinterpret_cast<uintptr_t>(phase_in);
@@ -977,7 +979,7 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
       return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
     }
     case 2048:
-      if (getenv("SAGA_ISTFT_ONE_WARP")) return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // A/B
+      if (SAGA_OPT("SAGA_ISTFT_ONE_WARP")) return launch_istft<2048, 16, 16, 8, 8>(p, a, n_clips, st);   // A/B
       return launch_istft<2048, 16, 16, 8, 16>(p, a, n_clips, st);
     case 4096: return launch_istft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
   }

@@ -476,7 +476,8 @@ static int launch_ring_shape(const saga_stft_plan* p, const StftArgs& s, int n_c
 
 int launch_stft_ring(const saga_stft_plan* p, const StftArgs& s, int n_clips, int64_t max_frames, cudaStream_t st) {
   // SAGA_STFT_RING_SHAPE=15: 15 + 1 warps at <= 128 registers (tuning aid); default 19 + 1 warps at <= 102
-  static const int shape = [] { const char* e = getenv("SAGA_STFT_RING_SHAPE"); return e ? atoi(e) : 19; }();
+  const char* shape_opt = SAGA_OPT("SAGA_STFT_RING_SHAPE");
+  const int shape = shape_opt ? atoi(shape_opt) : 19;
   if (shape == 15) return launch_ring_shape<15, 24>(p, s, n_clips, max_frames, st);
   return launch_ring_shape<19, 20>(p, s, n_clips, max_frames, st);
 }

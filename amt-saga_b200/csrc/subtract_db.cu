@@ -701,8 +701,8 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   if (D_out && !vmax) SAGA_CUDA_OK(cudaMallocAsync(&vmax, sizeof(float) * n_windows, st));
   a.vmax_scratch = (vmax != ref_out) ? vmax : nullptr;
   int min_steps = 2;
-  if (const char* e = getenv("SAGA_SUB_CLUSTER_MIN_STEPS")) min_steps = atoi(e);       // tuning aid
-  const bool clustered = vec && n_steps >= min_steps && n_steps >= 1 && !getenv("SAGA_SUB_NO_CLUSTER") && !skip_db && !only_db;
+  if (const char* e = SAGA_OPT("SAGA_SUB_CLUSTER_MIN_STEPS")) min_steps = atoi(e);       // tuning aid
+  const bool clustered = vec && n_steps >= min_steps && n_steps >= 1 && !SAGA_OPT("SAGA_SUB_NO_CLUSTER") && !skip_db && !only_db;
   if (clustered) {
     // >= 120 KB of dynamic shared memory per CTA keeps it alone on its SM: 37 windows in flight, L2-resident
     const size_t csmem = std::max<size_t>(sizeof(float) * ((size_t)n_frames / SUBC_CTAS + 2), 120 * 1024);
@@ -714,13 +714,13 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
   }
   // one step, ReLU, K1's by-products at hand: the flat single-step kernel (values >= 0 make the atomic max valid)
   const bool flat = vec && !only_db && n_steps == 1 && (flags & SAGA_SUB_RELU) && frame_max_in && guess_ref && vmax &&
-                    !getenv("SAGA_SUB_NO_FLAT");
+                    !SAGA_OPT("SAGA_SUB_NO_FLAT");
   if (only_db) {
     // the chain ran in an earlier call (SAGA_SUB_SKIP_DB) and left every window's final max in ref_out
   } else if (flat) {
     SAGA_CUDA_OK(cudaMemsetAsync(vmax, 0, sizeof(float) * n_windows, st));
     int fchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, guess_frames_all), (148 * 16 + n_windows - 1) / n_windows));
-    if (const char* e = getenv("SAGA_SUB_FLAT_CHUNKS")) fchunks = std::max(1, std::min(std::max(1, guess_frames_all), atoi(e)));   // tuning aid
+    if (const char* e = SAGA_OPT("SAGA_SUB_FLAT_CHUNKS")) fchunks = std::max(1, std::min(std::max(1, guess_frames_all), atoi(e)));   // tuning aid
     subtract_single_flat_kernel<<<(unsigned)((int64_t)n_windows * fchunks), SF_THREADS, 0, st>>>(a, vmax, fchunks);
     SAGA_LAUNCH_CHECK();
   } else if (vec) {
@@ -739,7 +739,7 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
     int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames, (148 * 16 + n_windows - 1) / n_windows));
     // default: 256 threads x 12 outstanding 16-byte loads, ~32 CTAs of whole row chunks per SM slot (0.54 -> 0.42 ms for
     // 600 windows = 6.05 TB/s, profiles/microbench/db_lean_sweep_b200.txt); SAGA_DB_LEAN=0 restores the shallow kernel
-    const char* lean = getenv("SAGA_DB_LEAN");
+    const char* lean = SAGA_OPT("SAGA_DB_LEAN");
     const int lv = lean ? atoi(lean) : 4;
     if (vec && lv > 0) {
       // one deep batch per thread: a CTA takes as many whole rows as 256 threads x 12 vectors cover (11 rows of 1028
@@ -747,7 +747,7 @@ extern "C" int saga_subtract_db_exec(float* win_mag, const int64_t* win_offsets,
       const int rows_per_cta = (int)std::max<int64_t>(1, (256 * 12) / std::max<int64_t>(1, frame_pitch >> 2));
       chunks = std::max(1, (n_frames + rows_per_cta - 1) / rows_per_cta);
     }
-    if (const char* e = getenv("SAGA_DB_CHUNKS")) chunks = std::max(1, std::min(n_frames, atoi(e)));
+    if (const char* e = SAGA_OPT("SAGA_DB_CHUNKS")) chunks = std::max(1, std::min(n_frames, atoi(e)));
     const int64_t blocks = (int64_t)n_windows * chunks, lblocks = blocks;
 #define SAGA_DBL(T, U) window_db_lean_kernel<T, U><<<(unsigned)lblocks, T, 0, st>>>(win_mag, win_offsets, win_stride, D_out, vmax, n_bins, n_frames, frame_pitch, amin, top_db, chunks)
     if (vec && lv == 1) SAGA_DBL(128, 12);

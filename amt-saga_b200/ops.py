@@ -473,6 +473,21 @@ def launch_count():
     return int(_lib.lib().saga_launch_count())
 
 
+@contextlib.contextmanager
+def options(**kv):
+    """Temporarily set library switches (saga_set_option), e.g. `with ops.options(SAGA_SUB_NO_CLUSTER="1"):`.
+    The previous values are restored on exit; None unsets."""
+    lib = _lib.lib()
+    old = {k: lib.saga_get_option(k.encode()) for k in kv}
+    try:
+        for k, v in kv.items():
+            _lib.check(lib.saga_set_option(k.encode(), None if v is None else str(v).encode()))
+        yield
+    finally:
+        for k, v in old.items():
+            lib.saga_set_option(k.encode(), v)
+
+
 # ---------------------------------------------------------------------------
 # K5: classifier feature gather
 # ---------------------------------------------------------------------------

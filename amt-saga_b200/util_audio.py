@@ -196,9 +196,9 @@ class audio_complete:
 
     def _mag_from_db(self):
         # librosa.db_to_amplitude(D, ref) = ref * 10**(D/20)   (util_audio.py:99-101)
-        if self._ref_mag is None:
+        if not self._ref_cached():
             self._set_ref(1.0)
-        st = self._ref_mag * torch.pow(10.0, 0.05 * self._D.st)
+        st = self._ref_device() * torch.pow(10.0, 0.05 * self._D.st)
         st[:, self._D.nb:] = 0
         self._mag = _Spec(st, self._D.nb)
         self._max_hint = None
@@ -280,30 +280,35 @@ class audio_complete:
         self._ref_mag = None if value is None else float(value)
         self._ref_dev = dev if value is not None else None
 
+    def _ref_cached(self):
+        """Would the reference's `_ref_mag` be non-None right now?  (The value may exist on the device only.)"""
+        return self._ref_mag is not None or self._ref_dev is not None
+
     def _ref_device(self):
-        """1-element CUDA tensor with ref_mag semantics: the cached value if the
-        reference would have one, else the max of the current mag."""
-        if self._ref_mag is not None:
-            if self._ref_dev is None:
+        """ref_mag as a 1-element CUDA tensor, evaluated AND CACHED exactly when the reference's getter would
+        (util_audio.py:170-174) -- but without a device-to-host read: the host float is fetched only when somebody
+        asks for `.ref_mag` itself.  `subtract` and `D` therefore never synchronise."""
+        if self._ref_dev is None:
+            if self._ref_mag is not None:
                 self._ref_dev = torch.tensor([self._ref_mag], device=self._dev, dtype=torch.float32)
-            return self._ref_dev
-        if self._max_hint is None:
-            m = self._spec_mag()
-            _, self._max_hint = ops.subtract_db_batch(m.st.unsqueeze(0), None, None, m.nb, want_D=False)
-        return self._max_hint
+            else:
+                if self._max_hint is None:
+                    m = self._spec_mag()
+                    _, self._max_hint = ops.subtract_db_batch(m.st.unsqueeze(0), None, None, m.nb, want_D=False)
+                self._ref_dev = self._max_hint
+        return self._ref_dev
 
     @property
     def ref_mag(self):
         if self._ref_mag is None:
-            dev = self._ref_device()
-            self._set_ref(dev.item(), dev)
+            self._ref_mag = float(self._ref_device().item())
         return np.float32(self._ref_mag)
 
     @property
     def D(self):
         if self._D is None:
             m = self._spec_mag()
-            self.ref_mag  # the reference evaluates (and caches) ref_mag here (util_audio.py:179)
+            # the reference evaluates (and caches) ref_mag here (util_audio.py:179)
             D = ops.amplitude_to_db_batch(m.st.unsqueeze(0), m.nb, ref=self._ref_device())
             self._D = _Spec(D[0], m.nb)
         return self._out(self._D)
@@ -371,15 +376,13 @@ class audio_complete:
             g = subtrahend._spec_mag()
             g_ref = None
             if normalize:
-                subtrahend.ref_mag          # the reference evaluates and caches it too
-                g_ref = subtrahend._ref_device()
+                g_ref = subtrahend._ref_device()     # the reference evaluates and caches subtrahend.ref_mag too
         else:
             g = _Spec.from_view(subtrahend, torch.float32, self._dev)
             g_ref = None                    # max of the array, reduced in-kernel
         ref_init = None
         if normalize:
-            self.ref_mag                    # evaluated (cached) before the update, as in :239
-            ref_init = self._ref_device()
+            ref_init = self._ref_device()   # evaluated (cached) before the update, as in :239
         off = max(self._seconds_to_frames(offset) - attack_compensation, 0)
         m = self._spec_mag()
         n_bins, T = m.shape
@@ -394,7 +397,7 @@ class audio_complete:
         _, new_max = ops.subtract_db_batch(
             m.st.unsqueeze(0), g.st.reshape(1, 1, g.T, g.st.shape[1]) if g.st.is_contiguous()
             else g.st.contiguous().reshape(1, 1, g.T, g.st.shape[1]),
-            torch.tensor([[off]], dtype=torch.int32), n_bins, overkill=ok,
+            torch.full((1, 1), off, device=self._dev, dtype=torch.int32), n_bins, overkill=ok,
             guess_ref=None if g_ref is None else g_ref.reshape(1, 1),
             ref_init=None if ref_init is None else ref_init.reshape(1),
             normalize=normalize, relu=relu, want_D=False)
@@ -522,10 +525,18 @@ class audio_complete:
         plan = ops.get_cqt_plan(self.sr, int(self.hl), note_to_hz(lowest_note), int(nbins),
                                 int(12 * bins_per_tone), 2, device=self._dev)
         plan.check_length(int(wav.numel()))
-        r = ops.cqt_batch(wav, plan, want_complex=not magnitude_only)
-        C = r["mag"][0] if magnitude_only else r["C"][0]
         t = self._seconds_to_frames(start + duration)
         s = self._seconds_to_frames(start)
+        Tc = plan.num_frames(int(wav.numel()))
+        if magnitude_only and 0 < target_frame_count <= 8 and 0 <= s < Tc:
+            # whatever t - s is, `_resize` keeps columns of [s, s + target): contract only those (K2 frame window,
+            # saga_cqt_frames_exec) instead of all T columns of the window
+            n_avail = max(min(t, Tc) - s, 0)
+            C8 = ops.cqt_frames_batch(wav.unsqueeze(0), plan, np.array([s], dtype=np.int32), target_frame_count)
+            C = C8[0, :, :plan.n_bins].transpose(0, 1)[:, :min(n_avail, target_frame_count)]
+            return self._out(self._resize(C, target_frame_count))
+        r = ops.cqt_batch(wav, plan, want_complex=not magnitude_only)
+        C = r["mag"][0] if magnitude_only else r["C"][0]
         return self._out(self._resize(C[:, s:t], target_frame_count))
 
     @staticmethod
@@ -548,7 +559,7 @@ class audio_complete:
     def resize(self, start, duration, target_frame_count, attribs=("F",)):
         """util_audio.py:469-507."""
         nac = self._new_like(None)
-        if self._ref_mag is not None:      # copied first; the F/mag setters below wipe it again,
+        if self._ref_cached():             # copied first; the F/mag setters below wipe it again,
             nac._ref_mag, nac._ref_dev = self._ref_mag, self._ref_dev   # exactly as in :489-499
         t = self._seconds_to_frames(start + duration)
         s = self._seconds_to_frames(start)

@@ -40,6 +40,11 @@ const char* saga_last_error_string(void);
 int saga_abi_version(void);
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 int64_t saga_launch_count(void);
+/* Tuning / A-B switches (DESIGN.md section 5 lists them: previous-generation kernels kept as parity twins, pipeline
+ * shapes).  Each is initialised once from the environment variable of the same name; saga_set_option changes it at
+ * run time (value NULL = unset).  Launchers read the table, never the environment. */
+int saga_set_option(const char* name, const char* value);
+const char* saga_get_option(const char* name);
 
 /* ------------------------------------------------------------------------
  * K0  PCM ingest: 16-bit PCM -> the float32 waveform audio_complete analyses.

@@ -87,3 +87,77 @@ def test_frame_arithmetic_of_the_pipeline_without_gpu():
     o._v["wf"] = np.zeros(263680, dtype=np.float32)
     for t in (0.0, 0.5, 1.999, 3.0, 5.99):
         assert seconds_to_frames(t, 516, 44100, 263680) == o._seconds_to_frames(t)
+
+
+def test_options_table_replaces_the_environment_on_the_hot_path():
+    """saga_set_option / saga_get_option: unknown names are refused, values round-trip, None unsets."""
+    from amt_saga_b200 import _lib
+    lib = _lib.lib()
+    assert lib.saga_set_option(b"SAGA_NOT_AN_OPTION", b"1") == _lib.SAGA_ERR_INVALID
+    before = lib.saga_get_option(b"SAGA_DB_CHUNKS")
+    assert lib.saga_set_option(b"SAGA_DB_CHUNKS", b"17") == 0
+    assert lib.saga_get_option(b"SAGA_DB_CHUNKS") == b"17"
+    assert lib.saga_set_option(b"SAGA_DB_CHUNKS", before) == 0
+    assert lib.saga_get_option(b"SAGA_DB_CHUNKS") == before
+
+
+def test_plan_cache_drops_handles_of_another_process():
+    """The reference forks its producers (training.py:623-630).  Plans are cached per (pid, device); entries that
+    belong to another process are dropped WITHOUT calling *_destroy on them (their handles live in the parent's
+    CUDA context)."""
+    import os
+    from amt_saga_b200 import ops
+
+    class FakePlan:
+        def __init__(self):
+            self._h = object()
+    foreign = FakePlan()
+    key = (os.getpid() + 1, 0, "stft", 2048, 512, True)
+    ops._plans[key] = foreign
+    try:
+        ops._forget_foreign(ops._plans)
+        assert key not in ops._plans and foreign._h is None
+    finally:
+        ops._plans.pop(key, None)
+
+
+@pytest.mark.gpu
+def test_forked_workers_build_their_own_plans():
+    """fork-after-import (the reference's Pool): the parent imports the package but never touches CUDA, every forked
+    worker initialises its own context lazily and builds its own plans; results agree with the oracle."""
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, multiprocessing as mp
+sys.path.insert(0, %r)
+import numpy as np
+import amt_saga_b200                      # imported BEFORE the fork, like `import util_audio` in training.py
+from amt_saga_b200 import util_audio as ua
+from tests.synth import piano_clip
+
+def work(seed):
+    import os
+    y = piano_clip(seed, 30000)
+    a = ua.audio_complete(y, 2048, hop_length=512, carrier="numpy")
+    C = a.slice_C(0, 0.5, 8, bins_per_tone=1)
+    return os.getpid(), float(a.mag.sum()), float(a.ref_mag), float(C.sum())
+
+if __name__ == "__main__":
+    with mp.get_context("fork").Pool(2) as pool:
+        res = pool.map(work, [5, 5, 6, 6])
+    from oracle.audio_oracle import AudioOracle
+    for seed, (pid, s, r, c) in zip([5, 5, 6, 6], res):
+        o = AudioOracle(piano_clip(seed, 30000), 2048, hop_length=512)
+        assert abs(s - float(o.mag.sum())) <= 1e-4 * float(o.mag.sum()), (s, float(o.mag.sum()))
+        assert abs(r - float(o.ref_mag)) <= 1e-5 * float(o.ref_mag)
+        assert abs(c - float(o.slice_C(0, 0.5, 8, bins_per_tone=1).sum())) <= 1e-3 * c
+    assert res[0][1:] == res[1][1:] and res[2][1:] == res[3][1:]
+    assert len({r[0] for r in res}) >= 1
+    print("FORK_OK", len({r[0] for r in res}))
+""" % root
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "FORK_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]

@@ -136,13 +136,9 @@ def test_stft_4096_split_kernel_against_three_pass_form(saga):
     plan = ops.StftPlan(4096, 1024, True)
     out = {}
     for mode in ("split", "three_pass"):
-        if mode == "three_pass":
-            os.environ["SAGA_STFT_NO_EO"] = "1"
-        try:
+        with ops.options(SAGA_STFT_NO_EO="1" if mode == "three_pass" else None):
             r = ops.stft_batch(dev(y), plan, want_phase=True, want_complex=True, want_max=True)
             out[mode] = {k: r[k].cpu().numpy() for k in ("mag", "phase", "F", "clip_max", "frame_max") if k in r}
-        finally:
-            os.environ.pop("SAGA_STFT_NO_EO", None)
     a, b = out["split"], out["three_pass"]
     peak = float(b["mag"].max())
     assert np.abs(a["mag"] - b["mag"]).max() <= 2e-6 * peak
@@ -248,10 +244,8 @@ def test_subtract_single_step_flat_kernel_bit_exact(saga, B, T, Tg):
     fmax = st0[:, :, :B].amax(dim=2).contiguous()
     out = {}
     for mode in ("flat", "chain", "shallow_db"):
-        env = {"chain": "SAGA_SUB_NO_FLAT", "shallow_db": "SAGA_DB_LEAN"}.get(mode)
-        if env:
-            os.environ[env] = "1" if mode == "chain" else "0"
-        try:
+        opt = {"chain": dict(SAGA_SUB_NO_FLAT="1"), "shallow_db": dict(SAGA_DB_LEAN="0")}.get(mode, {})
+        with ops.options(**opt):
             res = []
             for kw in (dict(), dict(overkill=dev(ok)), dict(guess_frames=dev(gframes), ref_init=dev(ref_init))):
                 st = st0.clone()
@@ -259,9 +253,6 @@ def test_subtract_single_step_flat_kernel_bit_exact(saga, B, T, Tg):
                 D, ref = ops.subtract_db_batch(st, g, dev(offs), B, frame_max=fmax, guess_ref=gref.reshape(W, 1), **kw)
                 res.append((st.cpu().numpy(), D[:, :, :B].cpu().numpy(), ref.cpu().numpy()))
             out[mode] = res
-        finally:
-            if env:
-                os.environ.pop(env, None)
     for mode in ("chain", "shallow_db"):
         for a, b in zip(out["flat"], out[mode]):
             for x, y in zip(a, b):
@@ -298,9 +289,7 @@ def test_subtract_cluster_kernel_equals_single_cta_kernel(saga, normalize, relu)
     fmax = win.amax(dim=2).contiguous()
     out = {}
     for mode in ("cluster", "single"):
-        if mode == "single":
-            os.environ["SAGA_SUB_NO_CLUSTER"] = "1"
-        try:
+        with ops.options(SAGA_SUB_NO_CLUSTER="1" if mode == "single" else None):
             res = []
             for kw in (dict(), dict(guess_ref=gref), dict(guess_frames=gframes, ref_init=ref_init),
                        dict(frame_max=fmax, guess_ref=gref, guess_frames=gframes)):
@@ -308,8 +297,6 @@ def test_subtract_cluster_kernel_equals_single_cta_kernel(saga, normalize, relu)
                 D, ref = ops.subtract_db_batch(st, g, offs, B, normalize=normalize, relu=relu, **kw)
                 res.append((st.cpu().numpy(), D.cpu().numpy(), ref.cpu().numpy()))
             out[mode] = res
-        finally:
-            os.environ.pop("SAGA_SUB_NO_CLUSTER", None)
     for a, b in zip(out["cluster"], out["single"]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
@@ -446,20 +433,15 @@ def test_cqt_fused_cascade_is_bit_identical_to_level_by_level(saga, sr, hop, low
         wav[i, :n] = piano_clip(60 + i, n, sr=sr)
     out = {}
     for mode in ("fused", "default", "levels"):
-        if mode == "levels":
-            os.environ["SAGA_DEC_NO_FUSE"] = "1"
-        if mode == "fused":                       # every pair, also the short deep levels the default leaves alone
-            os.environ["SAGA_DEC_FUSE_MASK"] = "0xffff"
-        try:
+        # "fused": every pair, also the short deep levels the default leaves alone
+        with ops.options(SAGA_DEC_NO_FUSE="1" if mode == "levels" else None,
+                         SAGA_DEC_FUSE_MASK="0xffff" if mode == "fused" else None):
             res = []
             for kw in (dict(lens=lens), dict()):                 # ragged and equal-length (clip_lens NULL) batches
                 for impl in (1, 0):
                     r = ops.cqt_batch(dev(wav), plan, want_complex=True, impl=impl, fill=float("nan"), **kw)
                     res.append((r["mag"].cpu().numpy(), r["C"].cpu().numpy()))
             out[mode] = res
-        finally:
-            os.environ.pop("SAGA_DEC_NO_FUSE", None)
-            os.environ.pop("SAGA_DEC_FUSE_MASK", None)
     for mode in ("fused", "default"):
         for a, b in zip(out[mode], out["levels"]):
             for x, y in zip(a, b):
