@@ -11,8 +11,9 @@ analysis windows at once (one note per window and step):
 
 `audio_w.slice_C` reads `audio_w.wf`, which after the first subtraction is `librosa.istft(mag * ph)`
 (util_audio.py:88-106, length hop * (T - 1)): every step but the first therefore starts with K4 on the
-subtracted windows.  The first subtraction of a fresh `section` scales the guess by the SONG's ref_mag (the
-section copied it, util_audio.py:323); later ones by the window's current maximum (the `mag` setter reset it).
+subtracted windows.  Every subtraction scales the guess by the window's CURRENT maximum: `section` (training.py:284)
+runs before the song's ref_mag is first evaluated (training.py:336), so it copies an empty `_ref_mag`, and the `mag`
+setter resets it after each subtraction (a stale copied value can be modelled with `load(window_ref_mag=...)`).
 
 The state (subtracted magnitudes, original phases, waveforms) stays on the device between steps; the eleven
 classifier tensors come back as `[W, bands, frames]` CUDA tensors (`batches.py` stacks them for the models).
@@ -71,10 +72,13 @@ class NoteStepBatch:
         return out
 
     # ------------------------------------------------------------------ state
-    def load(self, mag_storage, phase_storage, wav, song_ref_mag, ref_C):
+    def load(self, mag_storage, phase_storage, wav, song_ref_mag, ref_C, window_ref_mag=None):
         """Windows as `mid_wf.section(offset, None, timing_frames)` leaves them (training.py:284):
         mag_storage / phase_storage: frame-major [W, T, P] (columns of the SONG's STFT), wav [W, L] the matching
-        waveform slices, song_ref_mag [W] = mid_wf.ref_mag, ref_C [W, 3] = (ref_C_1, ref_C_inst, ref_C_foc)."""
+        waveform slices, song_ref_mag [W] = mid_wf.ref_mag (the features' normaliser, training.py:336),
+        ref_C [W, 3] = (ref_C_1, ref_C_inst, ref_C_foc).  window_ref_mag: the `_ref_mag` the section carries -- None
+        (default) when the song's had not been evaluated yet at `section` time, which is training.py's order: the
+        first subtraction then scales by the window's own maximum; pass the song's to model a stale copy."""
         f32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32) if not isinstance(x, torch.Tensor) else x,
                                         device=self.dev).to(torch.float32).contiguous()
         if mag_storage.shape[:2] != (self.W, self.T) or phase_storage.shape != mag_storage.shape:
@@ -85,7 +89,10 @@ class NoteStepBatch:
         self.inv_song_ref = 1.0 / self.song_ref
         rc = np.asarray(ref_C.cpu() if isinstance(ref_C, torch.Tensor) else ref_C, dtype=np.float64).reshape(self.W, 3)
         self.inv_ref_C = [f32(1.0 / rc[:, i]) for i in range(3)]
-        self.stale_ref = self.song_ref.clone()     # `section` copied the song's ref_mag (util_audio.py:323)
+        if window_ref_mag is None:
+            _, self.stale_ref = ops.subtract_db_batch(self.mag, None, None, self.nb, want_D=False)   # max of each window
+        else:
+            self.stale_ref = f32(window_ref_mag)   # `section` copied a cached ref_mag (util_audio.py:323)
         self.fresh = True
 
     # ------------------------------------------------------------------ one batched step

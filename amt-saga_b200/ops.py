@@ -491,7 +491,7 @@ def options(**kv):
 # ---------------------------------------------------------------------------
 # K5: classifier feature gather
 # ---------------------------------------------------------------------------
-def compress_bands_batch(mag_storage, n_bins, edges, inv_scale=None):
+def compress_bands_batch(mag_storage, n_bins, edges, inv_scale=None, out=None):
     """util_audio.compress_bands on frame-major storage [clips, T, P]: returns
     frame-major [clips, T, Pb] whose [..., :n_bands].transpose is [bands, frames]."""
     _require_cuda(mag_storage, "mag")
@@ -505,7 +505,10 @@ def compress_bands_batch(mag_storage, n_bins, edges, inv_scale=None):
     n_clips, T, _ = m.shape
     P = m.stride(1) if T > 1 else m.shape[2]
     Pb = frame_pitch(n_bands)
-    out = torch.empty((n_clips, T, Pb), device=m.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((n_clips, T, Pb), device=m.device, dtype=torch.float32)
+    elif out.shape != (n_clips, T, Pb) or not out.is_contiguous():
+        raise ValueError("out must be contiguous [clips, T, %d]" % Pb)
     if inv_scale is not None:
         inv_scale = inv_scale.to(device=m.device, dtype=torch.float32).contiguous()
     with _on(m):
@@ -593,7 +596,7 @@ def short_window_features_batch(mag_st, phase_st, src_frames, band_min, n_rows, 
     return {"lin": view(lin), "log": view(log), "phase": view(pha)}
 
 
-def gather_frames_batch(storage, n_bins, src_frames, scale=None):
+def gather_frames_batch(storage, n_bins, src_frames, scale=None, out=None):
     """saga_gather_frames_exec: out[w][:, j] = in[w][:, src[w, j]] * scale[w] (src -1 => zeros): `C[:, s:t]` +
     `_resize` + `/ ref` of util_audio.slice_C for a batch.  storage [W, T, P] frame-major; returns the
     [W, n_bins, n_cols] view of frame-major [W, n_cols, Pout] storage."""
@@ -606,7 +609,10 @@ def gather_frames_batch(storage, n_bins, src_frames, scale=None):
     P = storage.stride(1) if T > 1 else storage.shape[2]
     cs = storage.stride(0) if W > 1 else T * P
     Po = frame_pitch(n_bins)
-    out = torch.empty((W, n_cols, Po), device=dev, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((W, n_cols, Po), device=dev, dtype=torch.float32)
+    elif out.shape != (W, n_cols, Po) or not out.is_contiguous():
+        raise ValueError("out must be contiguous [W, n_cols, %d]" % Po)
     if scale is not None:
         scale = scale.to(device=dev, dtype=torch.float32).contiguous()
     with _on(storage):

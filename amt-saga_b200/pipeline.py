@@ -6,6 +6,9 @@ Per window (reference flow, training.py:265-449 restricted to the hot path):
     K2  constant-Q magnitudes of the window audio   (util_audio.py:424-429)
     K1  STFT magnitude of the rendered guessed note (util_audio.py:237)
     K3  align / scale / subtract / ReLU, then dB    (util_audio.py:238-259, :179)
+        The guess is scaled by the WINDOW's own maximum: `section` (training.py:284) runs before anything has
+        evaluated the song's `ref_mag` (first use: training.py:336), so the window's `_ref_mag` is None and its first
+        `subtract` takes `max(window mag)` over the window's 516 columns (K3 reduces K1's per-frame maxima).
 
 The window is the first `n_frames` STFT columns of its clip, which is what
 `section(..., duration_in_frames=timing_frames)` (training.py:284) keeps.
@@ -149,7 +152,7 @@ class WindowFeaturePipeline:
         def subtract(phase):
             _lib.check(lib.saga_subtract_db_exec(
                 p(self.mag), None, self.T_clip * self.P, p(self.gmag), None, self.Tg * self.P, None, self.Tg,
-                p(offset_frames), None, p(self.gmax), p(self.clip_max), p(self.frame_max), self.T_clip,
+                p(offset_frames), None, p(self.gmax), None, p(self.frame_max), self.T_clip,
                 _lib.SUB_NORMALIZE | _lib.SUB_RELU | phase, p(self.D), p(self.ref), W, 1, self.nb, self.T, self.P,
                 1e-5, 80.0, st))
 
@@ -212,7 +215,7 @@ class WindowFeaturePipeline:
                 d_peak=torch.empty((2, self.W), device=d, dtype=torch.int32))
         return h
 
-    def _run_host(self, chunks=6, pcm16=False):
+    def _run_host(self, chunks=6, pcm16=False, returns="cqt"):
         """Pinned host inputs -> device -> hot path -> features back on the host
         (CQT magnitudes + post-subtraction ref_mag; the subtracted window and its dB
         image stay resident for the next loop iteration, as in training.py:449).
@@ -225,6 +228,11 @@ class WindowFeaturePipeline:
         util_audio.py:894 / :964) plus the per-clip float64 factor; K0 rebuilds the reference's float
         waveform `pcm * mul / max|pcm|` (util_audio.py:781) on the device, which halves the PCIe bytes."""
         h = self.host_pcm_buffers() if pcm16 else self.host_buffers()
+        feats = returns == "features"
+        if feats:
+            self.feature_buffers()
+        elif returns != "cqt":
+            raise ValueError("returns must be 'cqt' or 'features'")
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
             self._last_compute = None
@@ -260,23 +268,67 @@ class WindowFeaturePipeline:
                         peak = ops.pcm16_absmax(h[src][a:b], out=h["d_peak"][k, a:b])
                         ops.pcm16_to_wave(h[src][a:b], mul=h["d_mul"][k, a:b], div=peak, out=h[dst][a:b])
                 self._run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
+                if feats:
+                    self._reduce_features(h, a, b)
                 e2 = torch.cuda.Event()
                 e2.record(s_cmp)
                 ev_cmp.append(e2)
         with torch.cuda.stream(s_out):
             for (a, b), e in zip(bounds, ev_cmp):
                 s_out.wait_event(e)
-                h["C"][a:b].copy_(self.C[a:b], non_blocking=True)
+                if feats:
+                    for k in ("D8", "C8", "timing"):
+                        h[k][a:b].copy_(h["d_" + k][a:b], non_blocking=True)
+                else:
+                    h["C"][a:b].copy_(self.C[a:b], non_blocking=True)
                 h["ref"][a:b].copy_(self.ref[a:b], non_blocking=True)
         done = torch.cuda.Event()
         done.record(s_out)
         cur.wait_event(done)
         cur.wait_event(ev_in[-1])
 
+    # ---- reduced, classifier-ready outputs of the e2e path (K5 on the device) ----------------------
+    FEATURE_COLS = 8          # pitch_frames / instrument_frames of the reference (util_train_test.py:41-59)
+    TIMING_BANDS = 20         # timing_bands
+
+    def feature_buffers(self):
+        """Device + pinned host buffers of `run_host(returns="features")`: per window
+        D8 [8, P]   the dB image's 8 columns from the guessed note's onset frame (util_audio.py:176-180 -> :469-507),
+        C8 [8, Pc]  the same columns of the constant-Q magnitudes (util_audio.py:431-434),
+        timing [T, 20] compress_bands of the subtracted magnitude / song ref_mag (training.py:333-336),
+        ref [1]     post-subtraction ref_mag."""
+        h = self.host_buffers()
+        if "D8" not in h:
+            pin, d, n = dict(pin_memory=True), self.dev, self.FEATURE_COLS
+            Pb = ops.frame_pitch(self.TIMING_BANDS)
+            shapes = dict(D8=(self.W, n, self.P), C8=(self.W, n, self.Pc), timing=(self.W, self.T, Pb))
+            for k, shp in shapes.items():
+                h["d_" + k] = torch.empty(shp, device=d, dtype=torch.float32)
+                h[k] = torch.empty(shp, dtype=torch.float32, **pin)
+            h["cols"] = torch.arange(n, device=d, dtype=torch.int32).reshape(1, n)
+            from .util_audio import band_edges
+            h["edges"] = band_edges(self.nb, self.TIMING_BANDS)
+            h["inv_song"] = torch.empty((self.W,), device=d, dtype=torch.float32)
+        return h
+
+    def _reduce_features(self, h, a, b):
+        """K5 on windows [a, b): what the classifiers consume instead of the full CQT / dB images."""
+        src = h["d_offs"][a:b] + h["cols"]                               # onset frame + 0..7   (index bookkeeping)
+        src_d = torch.where(src < self.T, src, torch.full_like(src, -1))
+        src_c = torch.where(src < self.Tc, src, torch.full_like(src, -1))
+        ops.gather_frames_batch(self.D[a:b, :self.T], self.nb, src_d, out=h["d_D8"][a:b])
+        ops.gather_frames_batch(self.C[a:b], self.cqt.n_bins, src_c, out=h["d_C8"][a:b])
+        torch.reciprocal(self.clip_max[a:b], out=h["inv_song"][a:b])
+        ops.compress_bands_batch(self.mag[a:b, :self.T], self.nb, h["edges"], inv_scale=h["inv_song"][a:b],
+                                 out=h["d_timing"][a:b])
+
     def h2d_bytes(self, pcm16=False):
         if pcm16:
             return self.W * (2 * (self.ns + self.ng) + 4 + 16)
         return 4 * self.W * (self.ns + self.ng + 1)
 
-    def d2h_bytes(self):
+    def d2h_bytes(self, returns="cqt"):
+        if returns == "features":
+            n = self.FEATURE_COLS
+            return 4 * self.W * (n * self.P + n * self.Pc + self.T * ops.frame_pitch(self.TIMING_BANDS) + 1)
         return 4 * self.W * (self.Tc * self.Pc + 1)

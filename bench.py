@@ -377,13 +377,14 @@ def run_saga(args):
     h["wav"].copy_(wav); h["guess"].copy_(guess); h["offs"].copy_(offs)
     torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    RET = "features"      # D2H = what the classifiers consume (K5 on the device), not the raw CQT image
     for _ in range(2):
-        pipe.run_host(args.e2e_chunks)
+        pipe.run_host(args.e2e_chunks, returns=RET)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
-        pipe.run_host(args.e2e_chunks)
+        pipe.run_host(args.e2e_chunks, returns=RET)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -399,13 +400,13 @@ def run_saga(args):
     hp["mul"].copy_((vel / 128.0) ** 4)
     torch.cuda.synchronize()
     for _ in range(2):
-        pipe.run_host(args.e2e_chunks, pcm16=True)
+        pipe.run_host(args.e2e_chunks, pcm16=True, returns=RET)
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ops.launch_count()
     g0.record()
     for _ in range(e2e_steps):
-        pipe.run_host(args.e2e_chunks, pcm16=True)
+        pipe.run_host(args.e2e_chunks, pcm16=True, returns=RET)
     g1.record()
     barrier()
     ms_pcm = g0.elapsed_time(g1)
@@ -535,12 +536,14 @@ def run_saga(args):
                               "the kernels (sum %.3f ms)" % (pipe.schedule, sum(stage_ms.values())),
                    "cqt_impl": args.cqt_impl},
         "e2e": {"value": e2e_value, "unit": "window-features/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
-                "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": e2e_steps,
+                "d2h_bytes_per_step": pipe.d2h_bytes(RET), "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps,
-                "returns": "CQT magnitudes + post-subtraction ref_mag per window",
+                "returns": "per window, reduced on the device by K5: the log-dB image's 8 columns from the guessed note's "
+                           "onset [8 x 1025], the CQT's same 8 columns [8 x 84], compress_bands(subtracted mag)/ref [516 x 20], "
+                           "post-subtraction ref_mag (the shapes the classifiers take, util_train_test.py:39-59)",
                 "overlap": "%d window chunks on 3 streams (H2D | kernels | D2H)" % args.e2e_chunks},
         "e2e_pcm16": {"value": world * W / (ms_pcm / e2e_steps * 1e-3), "unit": "window-features/s",
-                      "h2d_bytes_per_step": pipe.h2d_bytes(pcm16=True), "d2h_bytes_per_step": pipe.d2h_bytes(),
+                      "h2d_bytes_per_step": pipe.h2d_bytes(pcm16=True), "d2h_bytes_per_step": pipe.d2h_bytes(RET),
                       "steps": e2e_steps, "ms_per_step": ms_pcm / e2e_steps, "launches_per_step": int(pcm_launches),
                       "note": "same call with int16 PCM + per-clip float64 factor in pinned host memory (the form in which "
                               "fluidsynth / soundfile deliver audio, util_audio.py:894/:964); K0 (pcm16_absmax + pcm16_ingest "

@@ -74,7 +74,6 @@ def run_loop(AC, song, notes, clips, params=Params, foc_bpt_scale=4, slide_after
     mid_wf = AC(song, p.N)                                                 # :265
     r["flatness"] = np.float64(host(mid_wf.spectral_flatness()))           # :266
     mid_wf.mag                                                             # :269
-    r["song_ref_mag"] = np.float64(host(mid_wf.ref_mag))
     dur = mid_wf._frames_to_seconds(mid_wf.shape[1])
     r["song_dur"] = np.float64(dur)
     T = mid_wf.shape[1]
@@ -89,7 +88,10 @@ def run_loop(AC, song, notes, clips, params=Params, foc_bpt_scale=4, slide_after
     fft_bin_min_const = mid_wf.midi_tone_to_FFT(60)                        # :289
     fft_bin_max_const = fft_bin_min_const + p.instrument_bands
     r["fft_bin_min_const"] = np.int64(fft_bin_min_const)
+    # the song's ref_mag is first evaluated HERE (training.py:336), after `section` copied a still-empty `_ref_mag`:
+    # the window's first subtraction therefore scales by the window's own maximum, not by the song's
     song_ref = host(mid_wf.ref_mag)
+    r["song_ref_mag"] = np.float64(song_ref)
 
     for i, (onset, duration, pitch) in enumerate(notes):
         k = "n%d_" % i

@@ -556,7 +556,7 @@ def test_window_pipeline_matches_oracle(saga):
         full = np.abs(osp.stft(wav[w], n_fft, hop))
         mag = full[:, :516].copy()
         g = np.abs(osp.stft(gue[w], n_fft, hop))
-        g *= full.max() / g.max()
+        g *= mag.max() / g.max()          # the window's own maximum (training.py:284 precedes the song's ref_mag, :336)
         g = g[:, :516 - offs[w, 0]]
         mag[:, offs[w, 0]:offs[w, 0] + g.shape[1]] -= g
         np.maximum(mag, 0, mag)
@@ -749,3 +749,33 @@ def test_feature_gather_matches_oracle_sequence(saga):
             exp = AudioOracle._resize(P, target)[0]
             got = np.where(idx >= 0, P[0][np.clip(idx, 0, max(t - 1, 0))] if t else 0.0, 0.0)
             assert np.array_equal(got, exp)
+
+
+def test_run_host_feature_return_matches_the_full_images(saga):
+    """run_host(returns="features"): the reduced outputs the e2e path ships (K5 on the device) are exactly the
+    columns / band means of the full dB, CQT and magnitude images the resident pass leaves on the device."""
+    from amt_saga_b200.pipeline import WindowFeaturePipeline
+    from amt_saga_b200.util_audio import band_edges
+    W, ns, ng = 5, 44100, 16384
+    pipe = WindowFeaturePipeline(W, ns, ng)
+    wav = np.stack([piano_clip(710 + i, ns, n_notes=5) for i in range(W)])
+    gue = np.stack([piano_clip(810 + i, ng, n_notes=1) for i in range(W)])
+    offs = np.array([[0], [3], [40], [80], [85]], dtype=np.int32)
+    h = pipe.host_buffers()
+    h["wav"].copy_(torch.as_tensor(wav)); h["guess"].copy_(torch.as_tensor(gue)); h["offs"].copy_(torch.as_tensor(offs))
+    pipe.run_host(2, returns="features")
+    torch.cuda.synchronize()
+    D, C, mag = pipe.D.cpu().numpy(), pipe.C.cpu().numpy(), pipe.mag.cpu().numpy()
+    edges = band_edges(pipe.nb, 20)
+    for w in range(W):
+        for j in range(8):
+            t = offs[w, 0] + j
+            want_d = D[w, t, :pipe.nb] if t < pipe.T else np.zeros(pipe.nb, np.float32)
+            want_c = C[w, t, :84] if t < pipe.Tc else np.zeros(84, np.float32)
+            assert np.array_equal(h["D8"][w, j, :pipe.nb].numpy(), want_d)
+            assert np.array_equal(h["C8"][w, j, :84].numpy(), want_c)
+        inv = np.float32(1.0) / pipe.clip_max[w].cpu().numpy()
+        for b in range(20):
+            want = mag[w, :pipe.T, edges[b]:edges[b + 1]].mean(axis=1) * inv
+            assert np.allclose(h["timing"][w, :, b].numpy(), want, rtol=2e-6, atol=1e-9)
+        assert h["ref"][w] == pipe.ref[w].cpu()
