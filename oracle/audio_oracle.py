@@ -2,12 +2,13 @@
 `audio_complete` container (/root/reference/util_audio.py:32-527) on top of
 the numpy restatements in oracle.spectral / oracle.cqt.
 
-The reference class cannot be imported here (matplotlib, magenta, librosa,
-soundfile missing; `np.int` gone from numpy 2.x), so this module re-expresses
-its behaviour: lazy fields with the reference's invalidation rules, the
-generative-subtractive `subtract`, the float64 time<->frame maps, the window
-slide helpers and the CQT slice.  Pinned on the reference's own FLAC outputs for the
-STFT/subtract/iSTFT chain; CQT and dB unpinned (see oracle/__init__.py).
+This module re-expresses the class's behaviour (lazy fields with the reference's
+invalidation rules, the generative-subtractive `subtract`, the float64 time<->frame
+maps, the window slide helpers, the CQT slice) so that it can travel to the GPU box,
+where /root/reference does not exist.  It is asserted BIT-IDENTICAL to the reference's
+own class (imported unmodified by oracle/ref_class.py) over the producer loop in
+tests/test_ref_class.py.  The librosa layer underneath: see oracle/__init__.py
+(CQT and dB unpinned against reference outputs).
 
 Each method cites the reference lines it follows.
 """
