@@ -776,6 +776,7 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
   p->d_levels = p->d_hops = nullptr;
   p->max_level = 0;
   p->umma = nullptr;
+  p->stream_tc = nullptr;
   auto fail = [&](int rc) { saga_cqt_plan_destroy(p); return rc; };
   if (d->early_factor > 1) {
     if (cudaMalloc(&p->d_early_taps, sizeof(float) * d->n_early_taps) != cudaSuccess)
@@ -816,6 +817,7 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(set_error(SAGA_ERR_CUDA, "cqt_plan_create: %s", cudaGetErrorString(e)));
   cqt_umma_plan_init(p);  // tensor-core side tables (no-op when the plan does not fit that path)
+  cqt_stream_plan_init(p);  // streamed-bank tensor path: packed banks per (octave, column group)
   *out = p;
   return SAGA_OK;
 }
@@ -823,6 +825,7 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
 extern "C" int saga_cqt_plan_destroy(saga_cqt_plan* p) {
   if (!p) return SAGA_OK;
   cqt_umma_plan_free(p);
+  cqt_stream_plan_free(p);
   cudaFree(p->d_early_taps);
   cudaFree(p->d_half_taps);
   cudaFree(p->d_levels);
@@ -989,6 +992,15 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
 
   if (!do_contract) return SAGA_OK;
   // ---- frame-window contraction (saga_cqt_frames_exec): a few columns per clip, compact output -------
+  // SAGA_CQT_STREAM=0 keeps the fp32 CUDA-core kernels (A/B twin of the streamed tensor-core contraction)
+  const bool stream_on = cqt_stream_supported(p) && !(SAGA_OPT("SAGA_CQT_STREAM") && atoi(SAGA_OPT("SAGA_CQT_STREAM")) == 0);
+  if (frame_first && stream_on) {
+    CqtLevels lv;
+    lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
+    lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.pad = pad.data(); lv.clip_frames = clip_frames;
+    return cqt_stream_exec(p, lv, n_clips, T_max, frame_first, frame_count, C_mag_out, nullptr, frame_pitch,
+                           out_clip_stride, st);
+  }
   if (frame_first) {
     if ((int)p->oct.size() > FW_MAX_OCT) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_frames_exec: too many octaves");
     FrameWinArgs fa;
@@ -1037,7 +1049,12 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     int rc = cqt_umma_exec(p, lv, n_clips, max_len, T_max, C_mag_out, (float2*)C_cplx_out, frame_pitch,
                            out_clip_stride, impl == 3 ? 1 : 3, TAIL_MAX, st);
     if (rc == SAGA_OK) return SAGA_OK;
-    if (rc != SAGA_ERR_UNSUPPORTED || impl >= 2) return rc;
+    if (rc != SAGA_ERR_UNSUPPORTED) return rc;
+    // the bank does not fit the resident kernel (24 / 48 / 192 bins per octave): stream it
+    if (impl != 3 && stream_on)
+      return cqt_stream_exec(p, lv, n_clips, T_max, nullptr, 0, C_mag_out, (float2*)C_cplx_out, frame_pitch,
+                             out_clip_stride, st);
+    if (impl >= 2) return rc;
   }
   bool first = true;
   for (auto& o : p->oct) {

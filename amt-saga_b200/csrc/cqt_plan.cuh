@@ -12,7 +12,8 @@ struct CqtOctaveDev {
   std::vector<float> bank_host;   // same, host copy (tensor-path operand packing)
 };
 
-struct CqtUmmaState;  // opaque to cqt.cu
+struct CqtUmmaState;    // opaque to cqt.cu
+struct CqtStreamState;  // opaque to cqt.cu (cqt_umma_stream.cu)
 
 struct saga_cqt_plan {
   int n_bins, hop, early_factor;
@@ -26,6 +27,7 @@ struct saga_cqt_plan {
   int max_level;
   std::vector<CqtOctaveDev> oct;
   CqtUmmaState* umma;
+  CqtStreamState* stream_tc;
 };
 
 namespace saga {
@@ -52,5 +54,14 @@ int cqt_umma_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int6
                   int64_t T_max, float* mag_out, float2* cplx_out, int64_t frame_pitch,
                   int64_t out_clip_stride, int n_split, int tail_max, cudaStream_t st);
 bool cqt_umma_supported(const saga_cqt_plan* p);
+
+// gathered rows x streamed bank (cqt_umma_stream.cu): whole transforms whose bank does not fit the resident kernel,
+// and frame windows (frame_first != NULL: rows = frames [first, first + 8) of every clip, compact output)
+void cqt_stream_plan_init(saga_cqt_plan* p);
+void cqt_stream_plan_free(saga_cqt_plan* p);
+bool cqt_stream_supported(const saga_cqt_plan* p);
+int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t T_max,
+                    const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
+                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t st);
 
 }  // namespace saga

@@ -1,0 +1,572 @@
+// K2 contraction on the tensor cores, second form: GATHERED ROWS x STREAMED BANK (tcgen05 kind::tf32, sm_100a).
+//
+//   C[(clip, t), :] = sum_n y_o[clip][t*hop - n_fft/2 + n] * G_o[n, :]
+//
+// cqt_umma.cu keeps an octave's whole bank resident in shared memory, which only the 12-bins-per-octave
+// transform fits (n_fft * 4 * ncol * 4 B <= ~150 KB).  The producer loop's own shapes -- 24, 48 and 192 bins per
+// octave, kernels of 1024 / 2048 / 8192 samples, 48 / 96 / 384 real columns per octave (training.py:340-388) --
+// have banks of 0.4 / 1.5 / 25 MB.  Here the bank is streamed: the K loop runs in stages of 32 samples and a
+// stage is
+//     A_hi, A_lo : 128 rows x 32 samples, row r = 32 contiguous samples of ONE frame, gathered from the padded
+//                  level signal by cp.async (16 B pieces straight into the K-major SWIZZLE_NONE core-matrix
+//                  layout: plane g = samples 4g..4g+3 of every row, 16 B per row)
+//     B          : the bank's 32 rows x n_main columns for this stage, ONE bulk copy from the pre-packed
+//                  [n_fft/4][n_main][4] image (TF32 hi | lo side by side along N)
+// and costs 4 K-slices x (main MMA N = n_main, correction MMA N = n_lo) issued by one thread: 3xTF32 split as in
+// cqt_umma.cu (hi*hi + hi*lo + lo*hi in fp32 TMEM).  TMEM holds 1, 2 or 4 partial accumulators per buffer (long
+// kernels: see cqt_stream_plan_init) and two buffers when the 512 columns allow it.
+// A "row" is any frame of any clip, so the same kernel serves
+//   * whole transforms  : rows = every frame of every clip, 128 consecutive (clip, frame) pairs per tile --
+//                         clips of 258 frames pack densely, there are no partial tiles and no tail kernel;
+//   * frame windows     : rows = frames [first[clip], first[clip] + 8) of every clip (saga_cqt_frames_exec: the
+//                         producer loop keeps 8 columns of each per-note transform), 16 clips per tile.
+// Column groups of <= 128 real columns (64 filters) are separate work items, ordered (octave, group)-major so
+// that all CTAs stream the same bank slab out of L2 at the same time.
+//
+// Warp roles of the persistent CTA (one per SM): 0-3 epilogue (TMEM lanes 32w..32w+31), 4 MMA issuer, 5 bank
+// loader (bulk copies), 6-13 row loaders (cp.async, completion by mbarrier arrive), 14-21 converters (lo plane).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "cqt_plan.cuh"
+#include "saga_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace saga {
+
+constexpr int US_TILE_M = 128;
+constexpr int US_KC = 32;                                  // samples per stage
+constexpr int US_PLANES = US_KC / 4;
+constexpr int US_W_MMA = 4, US_W_BANK = 5, US_W_LOAD0 = 6, US_W_CONV0 = 14;
+constexpr int US_LOAD_WARPS = 8, US_CONV_WARPS = 8;
+constexpr int US_THREADS = 32 * (US_W_CONV0 + US_CONV_WARPS);
+constexpr int US_MAX_STAGES = 6;
+constexpr int US_MAX_GROUPS = 64;                          // (octave, column group) pairs per launch
+constexpr int US_GROUP_COLS = 128;                         // real columns per group (64 filters)
+// plane pitch = 128 rows + one 16-byte pad: the row loaders write 8 planes x 4 rows per warp instruction, and a
+// pitch that is a multiple of 128 B would put the 8 planes of a row on the same banks
+constexpr uint32_t US_PLANE_BYTES = US_TILE_M * 16 + 16;
+constexpr uint32_t US_A_BYTES = (US_PLANES * US_PLANE_BYTES + 127u) & ~127u;   // one of hi / lo per stage
+constexpr uint32_t US_SMEM_LIMIT = 232448 - 1024;
+
+struct UsGroup {
+  const float* sig;       // padded level signal of the octave, element 0 = sample -n_fft/2 of clip 0
+  int64_t sig_stride;     // floats per clip
+  const float* b_pack;    // [n_fft/4][n_main][4]: rows [0,ncol) TF32 hi, [ncol,2ncol) lo, rest 0
+  int hop, n_fft, ncol, first_bin;   // first_bin of THIS column group
+  int n_main, n_lo;
+};
+
+struct UsArgs {
+  UsGroup grp[US_MAX_GROUPS];
+  int n_groups, n_clips, n_bins;
+  int rows_per_clip;            // whole transform: T_max; frame window: 8
+  int frame_count;              // frame window: rows j < frame_count are stored
+  const int32_t* frame_first;   // NULL = whole transform
+  const int32_t* clip_frames;
+  uint32_t m_tiles, total_items, total_rows;
+  float* mag_out;
+  float2* cplx_out;
+  int64_t frame_pitch, out_clip_stride;
+  uint32_t b_stage_bytes;       // bank region per stage (largest group)
+  uint32_t tmem_cols, acc_stride, part_stride;
+  int stages;
+  int parts, bufs;              // partial accumulators per buffer (stage st adds into partial st % parts), buffers
+  int debug;                    // SAGA_UMMA_DEBUG (timing bisection only): 1 no MMAs, 2 no row copies, 8 no bank copies, 32 no lo conversion
+  int* error_flag;
+};
+
+// (clip, frame) of row R; `store` = the row has an output slot, `live` = its frame exists
+struct UsRow {
+  int clip, j, t;
+  bool store, live;
+};
+__device__ __forceinline__ UsRow us_row(const UsArgs& a, uint32_t R) {
+  UsRow r;
+  if (R >= a.total_rows) {
+    r.clip = a.n_clips - 1; r.j = 0; r.t = 0; r.store = false; r.live = false;
+    return r;
+  }
+  r.clip = (int)(R / (uint32_t)a.rows_per_clip);
+  r.j = (int)(R - (uint32_t)r.clip * (uint32_t)a.rows_per_clip);
+  const int T = a.clip_frames[r.clip];
+  if (a.frame_first) {
+    r.t = a.frame_first[r.clip] + r.j;
+    r.store = r.j < a.frame_count;
+    r.live = r.t >= 0 && r.t < T;
+  } else {
+    r.t = r.j;
+    r.live = r.store = r.t < T;
+  }
+  return r;
+}
+
+// One stage = 4 K-slices: per slice the main MMA (A_hi x [B_hi | B_lo], N = n_main, into columns [0, n_main) of
+// the partial accumulator) and the correction MMA (A_lo x B_hi, N = n_lo).  The correction goes to the hi*lo
+// columns [ncol, ncol + n_lo) -- NOT on top of the main columns as in cqt_umma.cu: every MMA is one truncating add
+// per accumulator element, and the large main sums should see as few of them as possible.
+__device__ __forceinline__ void us_mma_stage(uint32_t d_main, uint32_t d_lo, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                             uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate, uint32_t da,
+                                             uint32_t db) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, p, t;\n\t"
+      ".reg .b64 ah, al, bb, dda, ddb;\n\t"
+      "elect.sync _|e, 0xFFFFFFFF;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 ah, %2;\n\t"
+      "mov.b64 al, %3;\n\t"
+      "mov.b64 bb, %4;\n\t"
+      "cvt.u64.u32 dda, %8;\n\t"
+      "cvt.u64.u32 ddb, %9;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "}\n" ::"r"(d_main),
+      "r"(d_lo), "l"(a_hi), "l"(a_lo), "l"(b), "r"(idesc_main), "r"(idesc_lo), "r"(accumulate), "r"(da), "r"(db)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __grid_constant__ UsArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t S = (uint32_t)a.stages;
+  const uint32_t stage_bytes = 2u * US_A_BYTES + a.b_stage_bytes;       // [A_hi | A_lo | B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S * stage_bytes);
+  uint64_t* raw = bars;                            // [S] hi planes landed (cp.async completion)
+  uint64_t* full = bars + US_MAX_STAGES;           // [S] lo planes written and the bank slab landed
+  uint64_t* empty = bars + 2 * US_MAX_STAGES;      // [S] the stage's MMAs retired
+  uint64_t* tfull = bars + 3 * US_MAX_STAGES;      // [2]
+  uint64_t* tempty = bars + 3 * US_MAX_STAGES + 2; // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 3 * US_MAX_STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(&raw[s], 32 * US_LOAD_WARPS);
+      mbar_init(&full[s], US_CONV_WARPS + 1);      // converter warps + the bank loader's expect_tx arrive
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+  const uint32_t G = gridDim.x;
+
+  if (warp < 4) {
+    // =========================== epilogue ===========================
+    const int ew = warp;
+    uint32_t it_acc = 0;
+    for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
+      const uint32_t g = item / a.m_tiles, tile = item - g * a.m_tiles;
+      const UsGroup& gr = a.grp[g];
+      const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
+      const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
+      mbar_wait(&tfull[acc], acc_ph, a.error_flag);
+      tc_fence_after();
+      const int64_t row = (int64_t)r.clip * a.out_clip_stride + (int64_t)(a.frame_first ? r.j : r.t) * a.frame_pitch;
+      const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
+      const bool vec_ok = ((a.frame_pitch | a.out_clip_stride | (int64_t)gr.first_bin) & 3) == 0 && !a.cplx_out &&
+                          (reinterpret_cast<uintptr_t>(a.mag_out) & 15) == 0;
+      for (int c0 = 0; c0 < gr.ncol; c0 += 8) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hi[i] = lo[i] = 0.f;
+        for (int pt = 0; pt < a.parts; ++pt) {
+          uint32_t v[8], u[8];
+          tmem_ld8(tbase + (uint32_t)pt * a.part_stride + (uint32_t)c0, v);
+          tmem_ld8(tbase + (uint32_t)pt * a.part_stride + (uint32_t)(gr.ncol + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            hi[i] += __uint_as_float(v[i]);
+            lo[i] += __uint_as_float(u[i]);
+          }
+        }
+        if (r.store) {
+          float sum[8], m[4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum[i] = hi[i] + lo[i];      // the correction columns are ~2^-11 of the main ones
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            m[i] = r.live ? sqrtf(sum[2 * i] * sum[2 * i] + sum[2 * i + 1] * sum[2 * i + 1]) : 0.f;
+          const int bin0 = gr.first_bin + (c0 >> 1);
+          if (vec_ok && bin0 >= 0 && bin0 + 4 <= a.n_bins) {
+            *reinterpret_cast<float4*>(a.mag_out + row + bin0) = make_float4(m[0], m[1], m[2], m[3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int bin = bin0 + i;
+              if (bin >= 0 && bin < a.n_bins) {
+                a.mag_out[row + bin] = m[i];
+                if (a.cplx_out) a.cplx_out[row + bin] = r.live ? make_float2(sum[2 * i], sum[2 * i + 1]) : make_float2(0.f, 0.f);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  } else if (warp == US_W_MMA) {
+    // =========================== MMA issuer ===========================
+    uint32_t k = 0, it_acc = 0;
+    for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
+      const uint32_t g = item / a.m_tiles;
+      const UsGroup& gr = a.grp[g];
+      // instruction descriptors: D = f32, A = B = tf32, K-major both, M = 128
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(US_TILE_M >> 4) << 24);
+      const uint32_t idesc_main = idesc_base | ((uint32_t)(gr.n_main >> 3) << 17);
+      const uint32_t idesc_lo = idesc_base | ((uint32_t)(gr.n_lo >> 3) << 17);
+      const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
+      mbar_wait_warp(&tempty[acc], acc_ph ^ 1, a.error_flag);
+      tc_fence_after();
+      const uint32_t d_tmem0 = tmem_base + acc * a.acc_stride;
+      const uint32_t bchunk16 = (uint32_t)gr.n_main;           // K-chunk pitch of the slab in 16-byte units
+      const int n_st = gr.n_fft / US_KC;
+      // The tensor core adds into the fp32 accumulator with truncation: the error grows with the number of
+      // accumulation steps (measured ~6.6e-9 of peak per kernel sample).  Long kernels therefore alternate between
+      // `parts` partial accumulators, which the epilogue adds in fp32.
+      for (int st = 0; st < n_st; ++st, ++k) {
+        const uint32_t s = k % S;
+        const uint32_t d_tmem = d_tmem0 + (uint32_t)(st & (a.parts - 1)) * a.part_stride;
+        const uint32_t accum = st >= a.parts ? 1u : 0u;
+        mbar_wait_warp(&full[s], (k / S) & 1, a.error_flag);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem_raw + s * stage_bytes);
+        const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
+        const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
+        const uint64_t db = smem_desc(base + 2u * US_A_BYTES, bchunk16 * 16u, 128);
+        // 4 K-slices of 8 samples: planes (0,1), (2,3), (4,5), (6,7) against bank chunks (0,1), ...
+        if (!(a.debug & 1))
+          us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
+                       2u * (US_PLANE_BYTES >> 4), 2u * bchunk16);
+        tc_commit(&empty[s]);
+        if (st == n_st - 1) tc_commit(&tfull[acc]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == US_W_BANK) {
+    // =========================== bank loader ===========================
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
+        const uint32_t g = item / a.m_tiles;
+        const UsGroup& gr = a.grp[g];
+        const uint32_t bytes = (uint32_t)gr.n_main * (US_PLANES * 16u);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(gr.b_pack);
+        const int n_st = gr.n_fft / US_KC;
+        for (int st = 0; st < n_st; ++st, ++k) {
+          const uint32_t s = k % S;
+          mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
+          if (a.debug & 8) { mbar_arrive(&full[s]); continue; }
+          mbar_arrive_expect_tx(&full[s], bytes);
+          bulk_g2s(smem_u32(smem_raw + s * stage_bytes + 2u * US_A_BYTES), src + (size_t)st * bytes, bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp < US_W_CONV0) {
+    // =========================== row loaders ===========================
+    const int ltid = threadIdx.x - 32 * US_W_LOAD0;
+    // a warp instruction copies 4 rows x 128 contiguous bytes (lane = plane + 8 * row): 4 cache lines per request
+    // instead of 32, and 4 shared-memory wavefronts thanks to the padded plane pitch
+    const int plane = ltid & 7, row0 = ltid >> 3;
+    uint32_t k = 0;
+    for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
+      const uint32_t g = item / a.m_tiles, tile = item - g * a.m_tiles;
+      const UsGroup& gr = a.grp[g];
+      const float* src[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(row0 + 32 * i));
+        const int T = a.clip_frames[r.clip];
+        const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
+        src[i] = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane;
+      }
+      const uint32_t dst_off = (uint32_t)plane * US_PLANE_BYTES + (uint32_t)row0 * 16u;
+      const int n_st = gr.n_fft / US_KC;
+      for (int st = 0; st < n_st; ++st, ++k) {
+        const uint32_t s = k % S;
+        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
+        const uint32_t dst = smem_u32(smem_raw + s * stage_bytes) + dst_off;
+        if (!(a.debug & 2)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * (32u * 16u)), "l"(src[i] + st * US_KC)
+                         : "memory");
+        }
+        cp_async_arrive_noinc(&raw[s]);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // =========================== converters ===========================
+    const int ctid = threadIdx.x - 32 * US_W_CONV0;
+    constexpr int CT = 32 * US_CONV_WARPS;
+    constexpr int PER = US_PLANES * US_TILE_M / CT;                  // 4 float4 per thread and stage
+    int cidx[PER];                                                   // float4 index of (plane, row) in the padded planes
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = ctid + i * CT;
+      cidx[i] = (e >> 7) * (int)(US_PLANE_BYTES / 16) + (e & 127);
+    }
+    uint32_t k = 0;
+    for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
+      const uint32_t g = item / a.m_tiles;
+      const int n_st = a.grp[g].n_fft / US_KC;
+      for (int st = 0; st < n_st; ++st, ++k) {
+        const uint32_t s = k % S;
+        mbar_wait(&raw[s], (k / S) & 1, a.error_flag);
+        const float4* dh = reinterpret_cast<const float4*>(smem_raw + s * stage_bytes);
+        float4* dl = reinterpret_cast<float4*>(smem_raw + s * stage_bytes + US_A_BYTES);
+        float4 x[PER];
+        if (a.debug & 32) { __syncwarp(); if (lane == 0) mbar_arrive(&full[s]); continue; }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) x[i] = dh[cidx[i]];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          // kind::tf32 reads the top 19 bits of an operand: the raw fp32 samples ARE the hi operand, and
+          // lo = x - trunc13(x) is exact in fp32 (cqt_umma.cu)
+          float4 l;
+          l.x = x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u);
+          l.y = x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u);
+          l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u);
+          l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u);
+          dl[cidx[i]] = l;
+        }
+        fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+  }
+}
+
+// columns [n_bins, pitch) of every output row are defined as zero
+__global__ void cqt_stream_zero_cols_kernel(float* mag, float2* cplx, const int32_t* clip_frames, int fixed_rows,
+                                            int n_bins, int64_t pitch, int64_t clip_stride) {
+  const int clip = blockIdx.y;
+  const int rows = fixed_rows > 0 ? fixed_rows : clip_frames[clip];
+  for (int t = blockIdx.x * blockDim.y + threadIdx.y; t < rows; t += gridDim.x * blockDim.y)
+    for (int64_t k = n_bins + threadIdx.x; k < pitch; k += blockDim.x) {
+      mag[clip * clip_stride + t * pitch + k] = 0.f;
+      if (cplx) cplx[clip * clip_stride + t * pitch + k] = make_float2(0.f, 0.f);
+    }
+}
+
+struct StreamPack {
+  float* d_pack = nullptr;
+  int oct = 0, col0 = 0, ncol = 0, n_main = 0, n_lo = 0;
+};
+
+}  // namespace saga
+
+struct CqtStreamState {
+  std::vector<saga::StreamPack> packs;   // (octave, column group), octave-major
+  bool supported = false;
+  uint32_t b_stage_bytes = 0, tmem_cols = 0, acc_stride = 0, part_stride = 0;
+  size_t smem_bytes = 0;
+  int stages = 0, num_sms = 0, parts = 1, bufs = 2;
+  int* d_error = nullptr;
+};
+
+namespace saga {
+
+static float us_tf32_rna_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0x1000u;
+  u &= ~0x1FFFu;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+void cqt_stream_plan_init(saga_cqt_plan* p) {
+  CqtStreamState* st = new CqtStreamState();
+  p->stream_tc = st;
+  int n_main_max = 0, n_fft_max = 0;
+  size_t n_groups = 0;
+  for (auto& o : p->oct) n_fft_max = std::max(n_fft_max, o.n_fft);
+  // The tensor core adds into its fp32 accumulator with truncation: measured ~4.5e-9 of peak per kernel sample and
+  // accumulator.  Long kernels alternate between `parts` partial accumulators (added in fp32 by the epilogue) to stay
+  // below ~7e-6 where the 512 TMEM columns allow it.  A 128-column group needs 256 columns per partial ([hi*hi | hi*lo]),
+  // so 8192-sample kernels (192 bins per octave) get two partials: 1.7e-5 of peak against the fp32 kernel.  Groups
+  // of 64 columns with four partials measured 9.5e-6 but 23.3 instead of 13.9 ms per 600 windows (every row is
+  // gathered twice as often), so the wide groups stay.
+  int parts = 1;
+  while (parts < 4 && 4.5e-9 * n_fft_max / parts > 7e-6) parts *= 2;
+  const int group_cols = US_GROUP_COLS;
+  for (auto& o : p->oct) {
+    const int ncol = 2 * o.n_filters;
+    if (ncol % 8) return;                                   // the epilogue reads 8 columns (4 filters) at a time
+    if (o.hop < 4 || (o.hop % 4) != 0 || (o.n_fft % US_KC) != 0 || o.n_fft / US_KC < 4) return;
+    n_groups += (size_t)(ncol + group_cols - 1) / group_cols;
+  }
+  if (n_groups == 0 || n_groups > (size_t)US_MAX_GROUPS) return;
+  for (size_t oi = 0; oi < p->oct.size(); ++oi) {
+    const CqtOctaveDev& o = p->oct[oi];
+    const int ncol_o = 2 * o.n_filters;
+    for (int c0 = 0; c0 < ncol_o; c0 += group_cols) {
+      StreamPack pk;
+      pk.oct = (int)oi;
+      pk.col0 = c0;
+      pk.ncol = std::min(group_cols, ncol_o - c0);
+      pk.n_main = (2 * pk.ncol + 15) & ~15;                 // [B_hi | B_lo]; M = 128 needs N % 16 == 0
+      pk.n_lo = (pk.ncol + 15) & ~15;
+      n_main_max = std::max(n_main_max, pk.n_main);
+      const size_t n = (size_t)o.n_fft * pk.n_main;
+      std::vector<float> pack(n, 0.f);
+      for (int k = 0; k < o.n_fft; ++k) {
+        const size_t chunk = (size_t)(k / 4) * pk.n_main;
+        for (int c = 0; c < pk.ncol; ++c) {
+          const float b = o.bank_host[(size_t)k * ncol_o + c0 + c];
+          const float h = us_tf32_rna_host(b);
+          pack[(chunk + c) * 4 + (k % 4)] = h;
+          pack[(chunk + pk.ncol + c) * 4 + (k % 4)] = us_tf32_rna_host(b - h);
+        }
+      }
+      if (cudaMalloc(&pk.d_pack, n * 4) != cudaSuccess) { cudaGetLastError(); return; }
+      cudaMemcpy(pk.d_pack, pack.data(), n * 4, cudaMemcpyHostToDevice);
+      st->packs.push_back(pk);
+    }
+  }
+  st->b_stage_bytes = (uint32_t)n_main_max * (US_PLANES * 16u);
+  const uint32_t stage = 2u * US_A_BYTES + st->b_stage_bytes;
+  int fit = (int)((US_SMEM_LIMIT - 512u) / stage);
+  fit = std::min(fit, US_MAX_STAGES);
+  if (fit < 2) return;
+  st->stages = fit;
+  st->smem_bytes = (size_t)fit * stage + 512;
+  // accumulator layout: `parts` partial accumulators per buffer, two buffers when 512 TMEM columns allow it
+  const uint32_t w = ((uint32_t)n_main_max + 31u) & ~31u;
+  while (parts > 1 && (uint32_t)parts * w > 512) parts /= 2;
+  if (w > 512) return;
+  st->parts = parts;
+  st->bufs = (2u * parts * w <= 512) ? 2 : 1;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(st->bufs * parts) * w) cols <<= 1;
+  st->tmem_cols = cols;
+  st->part_stride = w;
+  st->acc_stride = parts * w;
+  if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemset(st->d_error, 0, sizeof(int));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  // the attribute is per function, plans differ in their needs: ask for the maximum once
+  if (cudaFuncSetAttribute(cqt_umma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)US_SMEM_LIMIT) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  st->supported = true;
+}
+
+void cqt_stream_plan_free(saga_cqt_plan* p) {
+  if (!p->stream_tc) return;
+  for (auto& pk : p->stream_tc->packs) cudaFree(pk.d_pack);
+  cudaFree(p->stream_tc->d_error);
+  delete p->stream_tc;
+  p->stream_tc = nullptr;
+}
+
+bool cqt_stream_supported(const saga_cqt_plan* p) { return p->stream_tc && p->stream_tc->supported; }
+
+int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t T_max,
+                    const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
+                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t stream) {
+  const CqtStreamState* st = p->stream_tc;
+  if (!st || !st->supported) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: plan does not fit the streamed tcgen05 path");
+  UsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n_groups = (int)st->packs.size();
+  a.n_clips = n_clips;
+  a.n_bins = p->n_bins;
+  a.rows_per_clip = frame_first ? 8 : (int)T_max;
+  a.frame_count = frame_count;
+  a.frame_first = frame_first;
+  a.clip_frames = lv.clip_frames;
+  const int64_t rows = (int64_t)n_clips * a.rows_per_clip;
+  const int64_t m_tiles = (rows + US_TILE_M - 1) / US_TILE_M;
+  if (rows <= 0) return SAGA_OK;
+  if (rows >= ((int64_t)1 << 31) || m_tiles * a.n_groups >= ((int64_t)1 << 31))
+    return set_error(SAGA_ERR_UNSUPPORTED, "cqt: batch too large for one launch");
+  a.total_rows = (uint32_t)rows;
+  a.m_tiles = (uint32_t)m_tiles;
+  a.total_items = (uint32_t)(m_tiles * a.n_groups);
+  a.mag_out = mag_out;
+  a.cplx_out = cplx_out;
+  a.frame_pitch = frame_pitch;
+  a.out_clip_stride = out_clip_stride;
+  a.b_stage_bytes = st->b_stage_bytes;
+  a.tmem_cols = st->tmem_cols;
+  a.acc_stride = st->acc_stride;
+  a.part_stride = st->part_stride;
+  a.parts = st->parts;
+  a.bufs = st->bufs;
+  a.stages = st->stages;
+  a.error_flag = st->d_error;
+  {
+    const char* dbg = SAGA_OPT("SAGA_UMMA_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
+  for (int i = 0; i < a.n_groups; ++i) {
+    const StreamPack& pk = st->packs[i];
+    const CqtOctaveDev& o = p->oct[pk.oct];
+    UsGroup& g = a.grp[i];
+    g.sig = lv.lvl[o.level] + (lv.pad[o.level] - o.n_fft / 2);
+    g.sig_stride = lv.pitch[o.level];
+    g.b_pack = pk.d_pack;
+    g.hop = o.hop;
+    g.n_fft = o.n_fft;
+    g.ncol = pk.ncol;
+    g.first_bin = o.first_bin + pk.col0 / 2;
+    g.n_main = pk.n_main;
+    g.n_lo = pk.n_lo;
+  }
+  if (frame_pitch > p->n_bins) {
+    dim3 grid(frame_first ? 1 : 8, n_clips), block(32, 8);
+    cqt_stream_zero_cols_kernel<<<grid, block, 0, stream>>>(mag_out, cplx_out, lv.clip_frames, frame_first ? frame_count : 0,
+                                                            p->n_bins, frame_pitch, out_clip_stride);
+    SAGA_LAUNCH_CHECK();
+  }
+  const int grid = (int)std::min<int64_t>(a.total_items, st->num_sms > 0 ? st->num_sms : 148);
+  cqt_umma_stream_kernel<<<grid, US_THREADS, st->smem_bytes, stream>>>(a);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
+}  // namespace saga
