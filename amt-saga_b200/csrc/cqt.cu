@@ -994,13 +994,6 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
   // ---- frame-window contraction (saga_cqt_frames_exec): a few columns per clip, compact output -------
   // SAGA_CQT_STREAM=0 keeps the fp32 CUDA-core kernels (A/B twin of the streamed tensor-core contraction)
   const bool stream_on = cqt_stream_supported(p) && !(SAGA_OPT("SAGA_CQT_STREAM") && atoi(SAGA_OPT("SAGA_CQT_STREAM")) == 0);
-  if (frame_first && stream_on) {
-    CqtLevels lv;
-    lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
-    lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.pad = pad.data(); lv.clip_frames = clip_frames;
-    return cqt_stream_exec(p, lv, n_clips, T_max, frame_first, frame_count, C_mag_out, nullptr, frame_pitch,
-                           out_clip_stride, st);
-  }
   if (frame_first) {
     if ((int)p->oct.size() > FW_MAX_OCT) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_frames_exec: too many octaves");
     FrameWinArgs fa;
@@ -1019,6 +1012,27 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     fa.n_bins = p->n_bins; fa.frame_count = frame_count;
     fa.frame_first = frame_first; fa.clip_frames = clip_frames;
     fa.mag_out = C_mag_out; fa.frame_pitch = frame_pitch; fa.out_clip_stride = out_clip_stride;
+    fa.n_clips = n_clips; fa.n_oct = (int)p->oct.size();
+    fa.pstride = (max_filt + 31) & ~31;
+    fa.partial = (float*)ws;           // tail of the workspace (saga_cqt_workspace_bytes reserves it)
+    if (stream_on) {
+      // tensor cores (cqt_umma_stream.cu); small batches are split along K into the same scratch layout and finished
+      // by the same kernel as the fp32 form
+      CqtLevels lv;
+      lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
+      lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.pad = pad.data(); lv.clip_frames = clip_frames;
+      int max_slices = 1;
+      while (2 * max_slices <= FW_MAX_KS && (int64_t)2 * max_slices * n_clips * fa.n_oct <= 2 * FW_TARGET_CTAS) max_slices *= 2;
+      int ks = 1;
+      const int rc = cqt_stream_exec(p, lv, n_clips, T_max, frame_first, frame_count, C_mag_out, nullptr, frame_pitch,
+                                     out_clip_stride, st, max_slices, fa.partial, fa.pstride, &ks);
+      if (rc != SAGA_OK || ks == 1) return rc;
+      fa.ks = ks;
+      dim3 g2((unsigned)((max_filt + 255) / 256), (unsigned)p->oct.size(), n_clips);
+      cqt_frame_window_finish_kernel<<<g2, 256, 0, st>>>(fa);
+      SAGA_LAUNCH_CHECK();
+      return SAGA_OK;
+    }
     const int warps = std::min(8, (max_filt + 31) / 32);
     const int cblocks = (max_filt + warps * 32 - 1) / (warps * 32);
     // split-K until the launch has a few CTAs per SM (each CTA walks its K range serially, one L2 round trip per step)
@@ -1027,9 +1041,7 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     int ks = 1;
     const int64_t ctas = (int64_t)cblocks * (int64_t)p->oct.size() * n_clips;
     while (ks < FW_MAX_KS && ctas * ks < FW_TARGET_CTAS && min_nfft / (2 * ks) >= 64) ks *= 2;
-    fa.ks = ks; fa.n_clips = n_clips; fa.n_oct = (int)p->oct.size();
-    fa.pstride = (max_filt + 31) & ~31;
-    fa.partial = (float*)ws;           // tail of the workspace (saga_cqt_workspace_bytes reserves it)
+    fa.ks = ks;
     dim3 grid((unsigned)(cblocks * ks), (unsigned)p->oct.size(), n_clips);
     if (vec) cqt_frame_window_kernel<true><<<grid, warps * 32, 0, st>>>(fa);
     else cqt_frame_window_kernel<false><<<grid, warps * 32, 0, st>>>(fa);

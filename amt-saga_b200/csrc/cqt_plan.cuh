@@ -62,6 +62,7 @@ void cqt_stream_plan_free(saga_cqt_plan* p);
 bool cqt_stream_supported(const saga_cqt_plan* p);
 int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t T_max,
                     const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
-                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t st);
+                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t st, int max_slices = 1,
+                    float* partial = nullptr, int pstride = 0, int* slices_out = nullptr);
 
 }  // namespace saga

@@ -58,6 +58,7 @@ struct UsGroup {
   const float* b_pack;    // [n_fft/4][n_main][4]: rows [0,ncol) TF32 hi, [ncol,2ncol) lo, rest 0
   int hop, n_fft, ncol, first_bin;   // first_bin of THIS column group
   int n_main, n_lo;
+  int oct, filt0;         // octave index and first filter of the group within it (split-K partial sums)
 };
 
 struct UsArgs {
@@ -75,6 +76,12 @@ struct UsArgs {
   uint32_t tmem_cols, acc_stride, part_stride;
   int stages;
   int parts, bufs;              // partial accumulators per buffer (stage st adds into partial st % parts), buffers
+  // split-K (frame windows of small batches: a pitch group of the note-relative transforms is a few dozen clips, a
+  // handful of tiles, and one CTA walking an 8192-sample kernel alone takes 220 us): the kernel length is cut into `ks`
+  // slices, item = (group * ks + slice) * m_tiles + tile, and the slices' complex sums go to `partial`
+  // [slice][clip][octave][pstride filters][8 frames][re, im] for cqt_frame_window_finish_kernel (cqt.cu)
+  int ks, n_oct, pstride;
+  float* partial;
   int debug;                    // SAGA_UMMA_DEBUG (timing bisection only): 1 no MMAs, 2 no row copies, 8 no bank copies, 32 no lo conversion
   int* error_flag;
 };
@@ -183,7 +190,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     const int ew = warp;
     uint32_t it_acc = 0;
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
-      const uint32_t g = item / a.m_tiles, tile = item - g * a.m_tiles;
+      const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
+      const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
       const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
       const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
@@ -208,7 +216,14 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
             lo[i] += __uint_as_float(u[i]);
           }
         }
-        if (r.store) {
+        if (a.ks > 1) {
+          if (r.store) {
+            float2* dst = reinterpret_cast<float2*>(
+                a.partial + ((((int64_t)slice * a.n_clips + r.clip) * a.n_oct + gr.oct) * a.pstride + gr.filt0 + (c0 >> 1)) * 16) + r.j;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[8 * i] = make_float2(hi[2 * i] + lo[2 * i], hi[2 * i + 1] + lo[2 * i + 1]);
+          }
+        } else if (r.store) {
           float sum[8], m[4];
 #pragma unroll
           for (int i = 0; i < 8; ++i) sum[i] = hi[i] + lo[i];      // the correction columns are ~2^-11 of the main ones
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     // =========================== MMA issuer ===========================
     uint32_t k = 0, it_acc = 0;
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
-      const uint32_t g = item / a.m_tiles;
+      const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
       // instruction descriptors: D = f32, A = B = tf32, K-major both, M = 128
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(US_TILE_M >> 4) << 24);
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       tc_fence_after();
       const uint32_t d_tmem0 = tmem_base + acc * a.acc_stride;
       const uint32_t bchunk16 = (uint32_t)gr.n_main;           // K-chunk pitch of the slab in 16-byte units
-      const int n_st = gr.n_fft / US_KC;
+      const int n_st = gr.n_fft / US_KC / a.ks;
       // The tensor core adds into the fp32 accumulator with truncation: the error grows with the number of
       // accumulation steps (measured ~6.6e-9 of peak per kernel sample).  Long kernels therefore alternate between
       // `parts` partial accumulators, which the epilogue adds in fp32.
@@ -277,11 +292,12 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     if (lane == 0) {
       uint32_t k = 0;
       for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-        const uint32_t g = item / a.m_tiles;
+        const uint32_t gs = item / a.m_tiles;
+        const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
         const UsGroup& gr = a.grp[g];
         const uint32_t bytes = (uint32_t)gr.n_main * (US_PLANES * 16u);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(gr.b_pack);
-        const int n_st = gr.n_fft / US_KC;
+        const int n_st = gr.n_fft / US_KC / a.ks;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(gr.b_pack) + (size_t)slice * n_st * bytes;
         for (int st = 0; st < n_st; ++st, ++k) {
           const uint32_t s = k % S;
           mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
@@ -299,18 +315,19 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     const int plane = ltid & 7, row0 = ltid >> 3;
     uint32_t k = 0;
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-      const uint32_t g = item / a.m_tiles, tile = item - g * a.m_tiles;
+      const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
+      const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
+      const int n_st = gr.n_fft / US_KC / a.ks;
       const float* src[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(row0 + 32 * i));
         const int T = a.clip_frames[r.clip];
         const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
-        src[i] = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane;
+        src[i] = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane + (int)slice * n_st * US_KC;
       }
       const uint32_t dst_off = (uint32_t)plane * US_PLANE_BYTES + (uint32_t)row0 * 16u;
-      const int n_st = gr.n_fft / US_KC;
       for (int st = 0; st < n_st; ++st, ++k) {
         const uint32_t s = k % S;
         mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
@@ -338,8 +355,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     }
     uint32_t k = 0;
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-      const uint32_t g = item / a.m_tiles;
-      const int n_st = a.grp[g].n_fft / US_KC;
+      const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
+      const int n_st = a.grp[g].n_fft / US_KC / a.ks;
       for (int st = 0; st < n_st; ++st, ++k) {
         const uint32_t s = k % S;
         mbar_wait(&raw[s], (k / S) & 1, a.error_flag);
@@ -507,7 +524,8 @@ bool cqt_stream_supported(const saga_cqt_plan* p) { return p->stream_tc && p->st
 
 int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, int64_t T_max,
                     const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
-                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t stream) {
+                    int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t stream, int max_slices,
+                    float* partial, int pstride, int* slices_out) {
   const CqtStreamState* st = p->stream_tc;
   if (!st || !st->supported) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: plan does not fit the streamed tcgen05 path");
   UsArgs a;
@@ -524,9 +542,21 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   if (rows <= 0) return SAGA_OK;
   if (rows >= ((int64_t)1 << 31) || m_tiles * a.n_groups >= ((int64_t)1 << 31))
     return set_error(SAGA_ERR_UNSUPPORTED, "cqt: batch too large for one launch");
+  // split-K (frame windows only, the caller provides the scratch and runs the finish kernel): until the launch
+  // covers most of the SMs, with at least 8 stages (and every partial accumulator used) per slice
+  int ks = 1, min_st = 1 << 30;
+  for (auto& o : p->oct) min_st = std::min(min_st, o.n_fft / US_KC);
+  const int n_sm = st->num_sms > 0 ? st->num_sms : 148;
+  if (frame_first && partial)
+    while (2 * ks <= max_slices && m_tiles * a.n_groups * ks < n_sm && min_st / (2 * ks) >= 8 && min_st % (2 * ks) == 0) ks *= 2;
+  if (slices_out) *slices_out = ks;
+  a.ks = ks;
+  a.n_oct = (int)p->oct.size();
+  a.pstride = pstride;
+  a.partial = partial;
   a.total_rows = (uint32_t)rows;
   a.m_tiles = (uint32_t)m_tiles;
-  a.total_items = (uint32_t)(m_tiles * a.n_groups);
+  a.total_items = (uint32_t)(m_tiles * a.n_groups * ks);
   a.mag_out = mag_out;
   a.cplx_out = cplx_out;
   a.frame_pitch = frame_pitch;
@@ -556,14 +586,16 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     g.first_bin = o.first_bin + pk.col0 / 2;
     g.n_main = pk.n_main;
     g.n_lo = pk.n_lo;
+    g.oct = pk.oct;
+    g.filt0 = pk.col0 / 2;
   }
-  if (frame_pitch > p->n_bins) {
+  if (frame_pitch > p->n_bins && ks == 1) {      // (the split-K finish kernel writes the padding itself)
     dim3 grid(frame_first ? 1 : 8, n_clips), block(32, 8);
     cqt_stream_zero_cols_kernel<<<grid, block, 0, stream>>>(mag_out, cplx_out, lv.clip_frames, frame_first ? frame_count : 0,
                                                             p->n_bins, frame_pitch, out_clip_stride);
     SAGA_LAUNCH_CHECK();
   }
-  const int grid = (int)std::min<int64_t>(a.total_items, st->num_sms > 0 ? st->num_sms : 148);
+  const int grid = (int)std::min<int64_t>(a.total_items, n_sm);
   cqt_umma_stream_kernel<<<grid, US_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
   return SAGA_OK;

@@ -48,6 +48,7 @@ class NoteStepBatch:
         self._fft_freq = np.linspace(0, float(sr) / 2, int(1 + self.N // 2), endpoint=True)   # util_audio.py:67
         self.mag = self.ph = self.wav = None
         self.fresh = True
+        self._tone_fft = None
         self.full_cqt = False      # True: every slice_C transforms all 258 columns like the reference (A/B twin)
 
     # ------------------------------------------------------------------ helpers (host, float64)
@@ -60,15 +61,39 @@ class NoteStepBatch:
         x = np.asarray(seconds, dtype=np.float64) * self.T * self.sr / self.wav.shape[1]
         return np.floor(x).astype(np.int64)
 
-    @staticmethod
-    def _resize_map(s, t, n_src, target):
+    _resize_tables = {}
+
+    @classmethod
+    def _resize_map(cls, s, t, n_src, target):
         """Source column of every output column of `_resize(P[:, s:t], target)` for each window (numpy slice
-        clipping included); -1 = the all-zero result of an empty slice."""
-        out = np.empty((len(s), target), dtype=np.int32)
-        for i, (a, b) in enumerate(zip(s, t)):
-            a_c, b_c = min(max(int(a), 0), n_src), min(max(int(b), 0), n_src)
-            idx = ops.resize_indices(max(b_c - a_c, 0), target)
-            out[i] = np.where(idx >= 0, idx + a_c, -1)
+        clipping included); -1 = the all-zero result of an empty slice.  `_resize` of a slice of n columns only
+        depends on n up to `target` (n >= target keeps the first `target` columns): one table row per n."""
+        tbl = cls._resize_tables.get(target)
+        if tbl is None:
+            tbl = np.stack([ops.resize_indices(n, target) for n in range(target + 1)]).astype(np.int32)
+            cls._resize_tables[target] = tbl
+        a_c = np.clip(np.asarray(s, dtype=np.int64), 0, n_src)
+        b_c = np.clip(np.asarray(t, dtype=np.int64), 0, n_src)
+        idx = tbl[np.minimum(np.maximum(b_c - a_c, 0), target)]
+        return np.where(idx >= 0, idx + a_c[:, None], -1).astype(np.int32)
+
+    def _upload(self, host):
+        """All of a step's small index tables in ONE pinned staging buffer and one asynchronous copy (a pageable
+        torch.as_tensor per table is a blocking copy behind everything queued on the stream: 62 of them made the
+        step host-bound).  Returns {name: int32 device view}."""
+        sizes = [(k, v.shape, int(v.size)) for k, v in host.items()]
+        total = sum(n for _, _, n in sizes)
+        stage = torch.empty(total, dtype=torch.int32, pin_memory=True)
+        flat = stage.numpy()
+        o = 0
+        for (k, _, n) in sizes:
+            flat[o:o + n] = np.asarray(host[k], dtype=np.int32).reshape(-1)
+            o += n
+        dbuf = stage.to(self.dev, non_blocking=True)
+        out, o = {}, 0
+        for (k, shape, n) in sizes:
+            out[k] = dbuf[o:o + n].view(shape)
+            o += n
         return out
 
     # ------------------------------------------------------------------ state
@@ -96,20 +121,31 @@ class NoteStepBatch:
         self.fresh = True
 
     # ------------------------------------------------------------------ one batched step
-    def _cqt_columns(self, wav, lowest_midi, nbins, bpt, s, t, n_cols, inv_ref):
+    def _cqt_prepare(self, L, lowest_midi, nbins, bpt, s, t, n_cols):
+        """Host side of one slice_C shape: the plan, the first column each window needs and the `_resize` map
+        relative to it (frame-window form) or absolute (full transform)."""
         plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(lowest_midi), int(nbins), int(12 * bpt), 2, device=self.dev)
-        plan.check_length(int(wav.shape[1]))
-        Tc = plan.num_frames(int(wav.shape[1]))
+        plan.check_length(int(L))
+        Tc = plan.num_frames(int(L))
         src = self._resize_map(s, t, Tc, n_cols)                                     # C[:, s:t] -> _resize
-        if n_cols <= 8 and not self.full_cqt:
-            # whatever t - s is, `_resize` keeps columns of [s, s + n_cols): contract only those (K2 frame window)
-            first = np.clip(s, 0, max(Tc - 1, 0)).astype(np.int32)
-            C = ops.cqt_frames_batch(wav, plan, first, n_cols)                       # [W', n_cols, Pc]
-            rel = np.where(src >= 0, src - first[:, None], -1)
-            assert rel.max(initial=-1) < n_cols
-            return ops.gather_frames_batch(C, nbins, rel, inv_ref)                   # / ref_C
-        C = ops.cqt_batch(wav, plan)["mag_storage"]                                  # [W', Tc, Pc]
-        return ops.gather_frames_batch(C, nbins, src, inv_ref)
+        windowed = n_cols <= 8 and not self.full_cqt
+        # whatever t - s is, `_resize` keeps columns of [s, s + n_cols): contract only those (K2 frame window)
+        first = np.clip(s, 0, max(Tc - 1, 0)).astype(np.int32)
+        rel = np.where(src >= 0, src - first[:, None], -1).astype(np.int32) if windowed else src
+        assert not windowed or rel.max(initial=-1) < n_cols
+        return plan, windowed, first, rel
+
+    def _cqt_run(self, wav, plan, windowed, first_dev, rel_dev, n_cols, nbins, inv_ref):
+        if windowed:
+            C = ops.cqt_frames_batch(wav, plan, first_dev, n_cols)                   # [W', n_cols, Pc]
+        else:
+            C = ops.cqt_batch(wav, plan)["mag_storage"]                              # [W', Tc, Pc]
+        return ops.gather_frames_batch(C, nbins, rel_dev, inv_ref)                   # / ref_C
+
+    def _cqt_columns(self, wav, lowest_midi, nbins, bpt, s, t, n_cols, inv_ref):
+        plan, windowed, first, rel = self._cqt_prepare(wav.shape[1], lowest_midi, nbins, bpt, s, t, n_cols)
+        d = self._upload({"first": first, "rel": rel})
+        return self._cqt_run(wav, plan, windowed, d["first"], d["rel"], n_cols, nbins, inv_ref)
 
     def step(self, onset, duration, pitch, guess_wav, guess_lens=None, subtract=True):
         """onset / duration (seconds, relative to the window) and MIDI pitch per window (host arrays, [W]);
@@ -125,45 +161,61 @@ class NoteStepBatch:
             self.wav = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb)
         s, t = self._frames(onset), self._frames(onset + duration)
         out = {}
-        # -- timing classifier input (training.py:333-336)
-        edges = band_edges(self.nb, self.timing_bands)
-        ct = ops.compress_bands_batch(self.mag, self.nb, edges, inv_scale=self.inv_song_ref)
-        out["C_timing"] = ct[:, :, :self.timing_bands].transpose(1, 2)              # T == timing_frames: _resize is the identity
-        # -- short window (training.py:337, :347-363)
-        sw_src = self._resize_map(s, t, self.T, self.pitch_frames)
-        b_const = self.midi_tone_to_FFT(60)
-        fc = ops.short_window_features_batch(self.mag, None, sw_src, b_const, self.instrument_bands, self.nb,
-                                             self.inv_song_ref)
-        out["F_sw_inst_foc_const"], out["F_sw_inst_foc_const_log10"] = fc["lin"], fc["log"]
-        b_note = np.array([self.midi_tone_to_FFT(int(p)) for p in pitch], dtype=np.int32)
-        fn = ops.short_window_features_batch(self.mag, self.ph, sw_src, b_note, self.instrument_bands, self.nb,
-                                             self.inv_song_ref, want_phase=True)
-        out["F_sw_inst_foc"], out["F_sw_inst_foc_log10"], out["ph"] = fn["lin"], fn["log"], fn["phase"]
-        # -- constant-Q inputs (training.py:340-346, :365-388); filter_scale 2 (util_audio.py:426)
+        L = int(self.wav.shape[1])
         a0, c8 = note_to_midi("A0"), note_to_midi("C8")
-        out["C_sw_pitch"] = self._cqt_columns(self.wav, a0, (c8 - a0) * self.pitch_bpt, self.pitch_bpt, s, t,
-                                              self.pitch_frames, self.inv_ref_C[0])
-        out["C_sw_inst"] = self._cqt_columns(self.wav, a0, (c8 - a0) * self.inst_bpt, self.inst_bpt, s, t,
-                                             self.instrument_frames, self.inv_ref_C[1])
-        out["C_sw_inst_foc_const"] = self._cqt_columns(self.wav, 60, self.instrument_bands, self.inst_bpt * 4, s, t,
-                                                       self.instrument_frames, self.inv_ref_C[2])
+        nf = self.instrument_frames
+        # ---- host: every index table of the step, then ONE upload ------------------------------------------
+        if self._tone_fft is None:
+            self._tone_fft = np.array([self.midi_tone_to_FFT(p) for p in range(128)], dtype=np.int32)
+        host = {"sw_src": self._resize_map(s, t, self.T, self.pitch_frames),
+                "b_note": self._tone_fft[np.clip(pitch, 0, 127)]}
+        const_shapes = (("C_sw_pitch", a0, (c8 - a0) * self.pitch_bpt, self.pitch_bpt, self.pitch_frames, 0),
+                        ("C_sw_inst", a0, (c8 - a0) * self.inst_bpt, self.inst_bpt, nf, 1),
+                        ("C_sw_inst_foc_const", 60, self.instrument_bands, self.inst_bpt * 4, nf, 2))
+        const_plans = {}
+        for name, low, nbins, bpt, n_cols, _ in const_shapes:
+            plan, windowed, first, rel = self._cqt_prepare(L, low, nbins, bpt, s, t, n_cols)
+            const_plans[name] = (plan, windowed)
+            host["first_" + name], host["rel_" + name] = first, rel
         # the two note-relative transforms have one kernel bank per pitch: windows are sorted by pitch once, every
         # pitch group contracts its <= 8 columns straight into its slice of ONE compact buffer, and one gather
         # (C[:, s:t] -> _resize -> / ref_C_foc) serves all windows
         valid = np.ones(W, dtype=bool)
         order = np.argsort(pitch, kind="stable")
-        inv_order = torch.as_tensor(np.argsort(order), device=self.dev)
-        order_dev = torch.as_tensor(order, device=self.dev)
-        wav_s = self.wav.index_select(0, order_dev)
+        host["order"], host["inv_order"] = order, np.argsort(order)
         s_s, t_s, p_s = s[order], t[order], pitch[order]
-        nf = self.instrument_frames
+        Tc = 1 + L // self.hl
+        src_s = self._resize_map(s_s, t_s, Tc, nf)
+        first_s = np.clip(s_s, 0, max(Tc - 1, 0)).astype(np.int32)
+        full = self.full_cqt
+        host["first_s"] = first_s
+        host["rel_s"] = src_s if full else np.where(src_s >= 0, src_s - first_s[:, None], -1)
+        off = np.maximum(s, 0).astype(np.int32)       # util_audio.py:248 with attack_compensation 0
+        host["off"] = off
+        d = self._upload(host)
+        # ---- device ---------------------------------------------------------------------------------------------
+        # -- timing classifier input (training.py:333-336)
+        edges = band_edges(self.nb, self.timing_bands)
+        ct = ops.compress_bands_batch(self.mag, self.nb, edges, inv_scale=self.inv_song_ref)
+        out["C_timing"] = ct[:, :, :self.timing_bands].transpose(1, 2)              # T == timing_frames: _resize is the identity
+        # -- short window (training.py:337, :347-363)
+        b_const = self.midi_tone_to_FFT(60)
+        fc = ops.short_window_features_batch(self.mag, None, d["sw_src"], b_const, self.instrument_bands, self.nb,
+                                             self.inv_song_ref)
+        out["F_sw_inst_foc_const"], out["F_sw_inst_foc_const_log10"] = fc["lin"], fc["log"]
+        fn = ops.short_window_features_batch(self.mag, self.ph, d["sw_src"], d["b_note"], self.instrument_bands, self.nb,
+                                             self.inv_song_ref, want_phase=True)
+        out["F_sw_inst_foc"], out["F_sw_inst_foc_log10"], out["ph"] = fn["lin"], fn["log"], fn["phase"]
+        # -- constant-Q inputs (training.py:340-346, :365-388); filter_scale 2 (util_audio.py:426)
+        for name, low, nbins, bpt, n_cols, ref_i in const_shapes:
+            plan, windowed = const_plans[name]
+            out[name] = self._cqt_run(self.wav, plan, windowed, d["first_" + name], d["rel_" + name], n_cols, nbins,
+                                      self.inv_ref_C[ref_i])
+        wav_s = self.wav.index_select(0, d["order"])
+        inv_ref_s = self.inv_ref_C[2].index_select(0, d["order"])
         res = []
         for nbins, bpt, shift in ((self.instrument_bands, self.inst_bpt * 4, 0), (self.bins_velocity, 2, -10)):
             P = ops.frame_pitch(nbins)
-            Tc = 1 + int(self.wav.shape[1]) // self.hl
-            src = self._resize_map(s_s, t_s, Tc, nf)
-            first = np.clip(s_s, 0, max(Tc - 1, 0)).astype(np.int32)
-            full = self.full_cqt
             buf = torch.zeros((W, Tc if full else nf, P), device=self.dev, dtype=torch.float32)
             a = 0
             while a < W:
@@ -171,27 +223,25 @@ class NoteStepBatch:
                 try:
                     plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(int(p_s[a]) + shift), int(nbins),
                                             int(12 * bpt), 2, device=self.dev)
-                    plan.check_length(int(self.wav.shape[1]))
+                    plan.check_length(L)
                     if full:
                         buf[a:b] = ops.cqt_batch(wav_s[a:b], plan)["mag_storage"]
                     else:
-                        ops.cqt_frames_batch(wav_s[a:b], plan, first[a:b], nf, out=buf[a:b])
+                        ops.cqt_frames_batch(wav_s[a:b], plan, d["first_s"][a:b], nf, out=buf[a:b])
                 except ParameterError:      # librosa: "Filter pass-band lies beyond Nyquist" -> the loop skips the file
                     valid[order[a:b]] = False
                     buf[a:b] = float("nan")
                 a = b
-            rel = src if full else np.where(src >= 0, src - first[:, None], -1)
-            g = ops.gather_frames_batch(buf, nbins, rel, self.inv_ref_C[2].index_select(0, order_dev))
-            res.append(g.index_select(0, inv_order))
+            g = ops.gather_frames_batch(buf, nbins, d["rel_s"], inv_ref_s)
+            res.append(g.index_select(0, d["inv_order"]))
         foc, vel = res
         out["C_sw_inst_foc"], out["C_velocity"] = foc, vel
-        off = np.maximum(s, 0).astype(np.int32)       # util_audio.py:248 with attack_compensation 0
         out["valid"], out["offset_frames"] = valid, off
         if subtract:
-            self.subtract(guess_wav, off, guess_lens)
+            self.subtract(guess_wav, off, guess_lens, offset_dev=d["off"])
         return out
 
-    def subtract(self, guess_wav, offset_frames, guess_lens=None):
+    def subtract(self, guess_wav, offset_frames, guess_lens=None, offset_dev=None):
         """training.py:426 + :449: STFT of the rendered notes (K1), then align / scale / subtract / ReLU (K3)."""
         g = ops.stft_batch(guess_wav, self.stft, lens=guess_lens, want_max=True)
         gm = g["mag_storage"]
@@ -202,7 +252,8 @@ class NoteStepBatch:
         if int(np.max(offset_frames)) > self.T:
             raise ValueError("negative dimensions are not allowed")      # numpy's error for zeros((bins, T - off - ...))
         _, self.ref = ops.subtract_db_batch(
-            self.mag, gm.unsqueeze(1), torch.as_tensor(offset_frames, dtype=torch.int32).reshape(self.W, 1), self.nb,
+            self.mag, gm.unsqueeze(1),
+            (offset_dev if offset_dev is not None else torch.as_tensor(offset_frames, dtype=torch.int32)).reshape(self.W, 1), self.nb,
             guess_ref=g["clip_max"].reshape(self.W, 1), ref_init=self.stale_ref if self.fresh else self.ref,
             guess_frames=frames,
             normalize=True, relu=True, want_D=False)

@@ -584,8 +584,11 @@ def short_window_features_batch(mag_st, phase_st, src_frames, band_min, n_rows, 
         if phase_st is None or phase_st.stride() != mag_st.stride():
             raise ValueError("phase storage must match the magnitude storage")
         ph_ptr = _ptr(torch.view_as_real(phase_st))
-    bm_dev, bm_all = (None, int(band_min)) if np.isscalar(band_min) else \
-        (torch.as_tensor(np.asarray(band_min, dtype=np.int32), device=dev), 0)
+    if isinstance(band_min, torch.Tensor):
+        bm_dev, bm_all = band_min.to(device=dev, dtype=torch.int32).contiguous(), 0
+    else:
+        bm_dev, bm_all = (None, int(band_min)) if np.isscalar(band_min) else \
+            (torch.as_tensor(np.asarray(band_min, dtype=np.int32), device=dev), 0)
     ir_dev, ir_all = (None, float(inv_ref)) if not isinstance(inv_ref, torch.Tensor) else \
         (inv_ref.to(device=dev, dtype=torch.float32).contiguous(), 1.0)
     with _on(mag_st):
