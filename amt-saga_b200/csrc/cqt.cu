@@ -79,6 +79,62 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
   }
 }
 
+// Large early factors (a CQT that starts at a low note decimates by up to 64 first: C_velocity, training.py:382):
+// the filter has 32 * factor taps, and the kernel above spends three shared-memory loads per multiply-add on it
+// (112 us per pitch group of the per-note step).  Polyphase form: with j = q * factor + r,
+//     y[o] = sum_r sum_{q=-16}^{15} g[q][r] * x[(o + q) * factor + r],     g[q][r] = h[|q * factor + r|]
+// i.e. `factor` independent 32-tap convolutions of the stride-1 sequences x_r.  A lane owns one phase r (adjacent lanes
+// = adjacent samples: every load is a coalesced 128-byte row, straight from global memory) and a run of R outputs,
+// holds the 32 taps of its phase in registers and slides over R + 31 samples: 0.28 loads per multiply-add.  The
+// phases are then summed across the lanes by shuffles.  factor < 32: 32 / factor runs per warp.
+constexpr int DECP_Q = 16;      // taps per side and phase (kaiser_fast: 16 zero crossings)
+constexpr int DECP_R = 8;       // outputs per lane
+constexpr int DECP_WARPS = 8;
+__global__ void __launch_bounds__(32 * DECP_WARPS, 2)
+decimate_phase_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
+                      const int64_t* __restrict__ clip_lens, int64_t max_len, float* __restrict__ out,
+                      int64_t out_stride, const float* __restrict__ g, int factor) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int clip = blockIdx.y;
+  const int64_t len = clip_lens ? clip_lens[clip] : max_len;
+  const int64_t n_full = len / factor, n_out = (len + factor - 1) / factor;
+  const int fl = min(factor, 32);                    // lanes that share a run of outputs
+  const int runs = 32 / fl;                          // runs per warp
+  const int r0 = lane % fl, u = lane / fl;
+  const int64_t o_warp = ((int64_t)blockIdx.x * DECP_WARPS + warp) * runs * DECP_R;
+  if (o_warp >= n_out) return;
+  const int64_t o0 = o_warp + (int64_t)u * DECP_R;
+  const float* x = in + (in_offsets ? in_offsets[clip] : (int64_t)clip * in_stride);
+  float acc[DECP_R];
+#pragma unroll
+  for (int i = 0; i < DECP_R; ++i) acc[i] = 0.f;
+  for (int r = r0; r < factor; r += 32) {
+    float tap[2 * DECP_Q];
+#pragma unroll
+    for (int t = 0; t < 2 * DECP_Q; ++t) tap[t] = __ldg(g + t * factor + r);
+    float xw[DECP_R + 2 * DECP_Q - 1];
+    const int s0 = ((int)o0 - DECP_Q) * factor + r, n = (int)len;     // clips are far shorter than 2^31 samples
+#pragma unroll
+    for (int w = 0; w < DECP_R + 2 * DECP_Q - 1; ++w) {
+      const int s = s0 + w * factor;
+      xw[w] = ((unsigned)s < (unsigned)n) ? __ldg(x + s) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < DECP_R; ++i)
+#pragma unroll
+      for (int t = 0; t < 2 * DECP_Q; ++t) acc[i] = fmaf(tap[t], xw[i + t], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < DECP_R; ++i)
+    for (int d = fl >> 1; d > 0; d >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], d);
+  // after the butterfly every lane of the run holds every sum: lane r0 stores outputs r0, r0 + fl, ...
+#pragma unroll
+  for (int i = 0; i < DECP_R; ++i) {
+    const int64_t o = o0 + i;
+    if ((i & (fl - 1)) == r0 && o < n_out) out[(int64_t)clip * out_stride + o] = o < n_full ? acc[i] : 0.f;
+  }
+}
+
 static size_t decimate_smem_bytes(int n_taps, int factor, int per_thread = DEC_PER_THREAD) {
   const size_t tile_in = (size_t)DEC_THREADS * per_thread * factor + 2 * (size_t)(n_taps - 1);
   return sizeof(float) * (((n_taps + 3) & ~3) + tile_in + tile_in / 32 + 1);
@@ -783,6 +839,18 @@ extern "C" int saga_cqt_plan_create(saga_cqt_plan** out, const saga_cqt_desc* d)
       return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
     cudaMemcpy(p->d_early_taps, d->early_taps_host, sizeof(float) * d->n_early_taps, cudaMemcpyHostToDevice);
     for (int i = 0; i < 32 && i < d->n_early_taps; ++i) p->early_taps2[i] = d->early_taps_host[i];
+    const int F = d->early_factor;
+    if (F >= 4 && (F & (F - 1)) == 0 && d->n_early_taps == DECP_Q * F) {
+      std::vector<float> g((size_t)2 * DECP_Q * F, 0.f);
+      for (int q = -DECP_Q; q < DECP_Q; ++q)
+        for (int r = 0; r < F; ++r) {
+          const int j = std::abs(q * F + r);
+          if (j < d->n_early_taps) g[(size_t)(q + DECP_Q) * F + r] = d->early_taps_host[j];
+        }
+      if (cudaMalloc(&p->d_early_phase, sizeof(float) * g.size()) != cudaSuccess)
+        return fail(set_error(SAGA_ERR_NOMEM, "cqt_plan_create: cudaMalloc"));
+      cudaMemcpy(p->d_early_phase, g.data(), sizeof(float) * g.size(), cudaMemcpyHostToDevice);
+    }
   }
   std::vector<int> levels, hops;
   for (int o = 0; o < d->n_octaves; ++o) {
@@ -827,6 +895,7 @@ extern "C" int saga_cqt_plan_destroy(saga_cqt_plan* p) {
   cqt_umma_plan_free(p);
   cqt_stream_plan_free(p);
   cudaFree(p->d_early_taps);
+  cudaFree(p->d_early_phase);
   cudaFree(p->d_half_taps);
   cudaFree(p->d_levels);
   cudaFree(p->d_hops);
@@ -933,7 +1002,12 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
     if (smem > 200 * 1024) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: early factor too large");
     if (smem > 48 * 1024)
       SAGA_CUDA_OK(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (early_is_dec2) {
+    if (p->d_early_phase && !SAGA_OPT("SAGA_DEC_NO_PHASE")) {
+      const int per_cta = DECP_WARPS * DECP_R * (32 / std::min(p->early_factor, 32));
+      dim3 gp((unsigned)((n_out + per_cta - 1) / per_cta), n_clips);
+      decimate_phase_kernel<<<gp, 32 * DECP_WARPS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, lvl[0] + pad[0],
+                                                            pitch[0], p->d_early_phase, p->early_factor);
+    } else if (early_is_dec2) {
       dim3 g2((unsigned)((n_out + DEC2_TILE - 1) / DEC2_TILE), n_clips);
       decimate2_kernel<<<g2, DEC2_THREADS, 0, st>>>(wav, clip_offsets, 0, clip_lens, max_len, 0, 1, lvl[0] + pad[0],
                                                     pitch[0], dec2_pairs(p->early_taps2));

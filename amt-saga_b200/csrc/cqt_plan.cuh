@@ -19,6 +19,7 @@ struct saga_cqt_plan {
   int n_bins, hop, early_factor;
   int n_early_taps, n_half_taps;
   float* d_early_taps;
+  float* d_early_phase = nullptr;   // polyphase image of the early filter [32][early_factor] (decimate_phase_kernel), or NULL
   float* d_half_taps;
   float early_taps2[32] = {0};   // host copies of the 32-tap (63-point symmetric) 2:1 decimators,
   float half_taps2[32] = {0};    // passed to the kernel by value
