@@ -8,8 +8,8 @@
 // have banks of 0.4 / 1.5 / 25 MB.  Here the bank is streamed: the K loop runs in stages of 32 samples and a
 // stage is
 //     A_hi, A_lo : 128 rows x 32 samples, row r = 32 contiguous samples of ONE frame, gathered from the padded
-//                  level signal by cp.async (16 B pieces straight into the K-major SWIZZLE_NONE core-matrix
-//                  layout: plane g = samples 4g..4g+3 of every row, 16 B per row)
+//                  level signal (16 B pieces into the K-major SWIZZLE_NONE core-matrix layout: plane g = samples
+//                  4g..4g+3 of every row, 16 B per row)
 //     B          : the bank's 32 rows x n_main columns for this stage, ONE bulk copy from the pre-packed
 //                  [n_fft/4][n_main][4] image (TF32 hi | lo side by side along N)
 // and costs 4 K-slices x (main MMA N = n_main, correction MMA N = n_lo) issued by one thread: 3xTF32 split as in
@@ -24,7 +24,12 @@
 // that all CTAs stream the same bank slab out of L2 at the same time.
 //
 // Warp roles of the persistent CTA (one per SM): 0-3 epilogue (TMEM lanes 32w..32w+31), 4 MMA issuer, 5 bank
-// loader (bulk copies), 6-13 row loaders (cp.async, completion by mbarrier arrive), 14-21 converters (lo plane).
+// loader (bulk copies), 6-21 row loaders in four groups that take the stages in turn: global -> registers (the group's
+// next stage, loaded while the other groups' stages run, so the L2 round trip is not on the shared-memory ring's
+// critical path) -> hi and lo planes in shared memory, ONE mbarrier arrive per warp.  (The first
+// version copied rows with cp.async and split them in separate converter warps: 256 per-thread barrier arrivals and
+// an extra hand-over per stage cost more than the copies -- the barrier skeleton alone ran at 540 cycles per stage.)
+// Every wait is polled by lane 0 only; the other lanes park at __syncwarp.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,9 +45,11 @@ namespace saga {
 constexpr int US_TILE_M = 128;
 constexpr int US_KC = 32;                                  // samples per stage
 constexpr int US_PLANES = US_KC / 4;
-constexpr int US_W_MMA = 4, US_W_BANK = 5, US_W_LOAD0 = 6, US_W_CONV0 = 14;
-constexpr int US_LOAD_WARPS = 8, US_CONV_WARPS = 8;
-constexpr int US_THREADS = 32 * (US_W_CONV0 + US_CONV_WARPS);
+constexpr int US_W_MMA = 4, US_W_BANK = 5, US_W_LOAD0 = 6;
+constexpr int US_LOAD_WARPS = 16;
+constexpr int US_THREADS = 32 * (US_W_LOAD0 + US_LOAD_WARPS);
+constexpr int US_MAX_LOAD_GROUPS = 4;                      // stage q is filled by loader group q % groups
+constexpr int US_MAX_RPT = US_PLANES * US_TILE_M / (32 * US_LOAD_WARPS / US_MAX_LOAD_GROUPS);   // 8 pieces per thread
 constexpr int US_MAX_STAGES = 6;
 constexpr int US_MAX_GROUPS = 64;                          // (octave, column group) pairs per launch
 constexpr int US_GROUP_COLS = 128;                         // real columns per group (64 filters)
@@ -75,6 +82,7 @@ struct UsArgs {
   uint32_t b_stage_bytes;       // bank region per stage (largest group)
   uint32_t tmem_cols, acc_stride, part_stride;
   int stages;
+  int load_groups;              // 4, or 2 when the ring has fewer than 4 stages (see the row loaders)
   int parts, bufs;              // partial accumulators per buffer (stage st adds into partial st % parts), buffers
   // split-K (frame windows of small batches: a pitch group of the note-relative transforms is a few dozen clips, a
   // handful of tiles, and one CTA walking an 8192-sample kernel alone takes 220 us): the kernel length is cut into `ks`
@@ -84,6 +92,7 @@ struct UsArgs {
   float* partial;
   int debug;                    // SAGA_UMMA_DEBUG (timing bisection only): 1 no MMAs, 2 no row copies, 8 no bank copies, 32 no lo conversion
   int* error_flag;
+  long long* prof;              // debug & 16: per-CTA cycle counters [grid][8]
 };
 
 // (clip, frame) of row R; `store` = the row has an output slot, `live` = its frame exists
@@ -146,13 +155,41 @@ __device__ __forceinline__ void us_mma_stage(uint32_t d_main, uint32_t d_lo, uin
       : "memory");
 }
 
+// lane 0 polls, the others wait at the warp barrier and then observe the completed phase themselves (one try_wait
+// that succeeds: acquire for every lane) -- 700 threads polling shared memory slow the barriers down for everybody
+__device__ __forceinline__ bool us_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// test_wait (non-blocking) in a spin loop, NOT try_wait: a thread that try_wait suspends is woken late
+// (measured here: ~1900 cycles per hand-over with try_wait, two hand-overs per stage)
+__device__ __forceinline__ void us_wait(uint64_t* bar, uint32_t parity, int lane, int* error_flag) {
+  if (lane == 0) {
+    uint32_t spins = 0;
+    while (!us_test_wait(bar, parity)) {
+      if (++spins > UM_SPIN_LIMIT) {
+        if (error_flag) atomicExch(error_flag, 1);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  while (!us_test_wait(bar, parity)) {}
+}
+
 __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __grid_constant__ UsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t S = (uint32_t)a.stages;
   const uint32_t stage_bytes = 2u * US_A_BYTES + a.b_stage_bytes;       // [A_hi | A_lo | B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S * stage_bytes);
-  uint64_t* raw = bars;                            // [S] hi planes landed (cp.async completion)
-  uint64_t* full = bars + US_MAX_STAGES;           // [S] lo planes written and the bank slab landed
+  uint64_t* full = bars + US_MAX_STAGES;           // [S] hi / lo planes written and the bank slab landed
   uint64_t* empty = bars + 2 * US_MAX_STAGES;      // [S] the stage's MMAs retired
   uint64_t* tfull = bars + 3 * US_MAX_STAGES;      // [2]
   uint64_t* tempty = bars + 3 * US_MAX_STAGES + 2; // [2]
@@ -163,8 +200,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < S; ++s) {
-      mbar_init(&raw[s], 32 * US_LOAD_WARPS);
-      mbar_init(&full[s], US_CONV_WARPS + 1);      // converter warps + the bank loader's expect_tx arrive
+      mbar_init(&full[s], US_LOAD_WARPS / a.load_groups + 1);      // the stage's row-loader warps + the bank loader's expect_tx arrive
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -195,7 +231,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       const UsGroup& gr = a.grp[g];
       const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
       const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
-      mbar_wait(&tfull[acc], acc_ph, a.error_flag);
+      us_wait(&tfull[acc], acc_ph, lane, a.error_flag);
       tc_fence_after();
       const int64_t row = (int64_t)r.clip * a.out_clip_stride + (int64_t)(a.frame_first ? r.j : r.t) * a.frame_pitch;
       const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
@@ -252,6 +288,10 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
   } else if (warp == US_W_MMA) {
     // =========================== MMA issuer ===========================
     uint32_t k = 0, it_acc = 0;
+    const bool prof_on = (a.debug & 16) != 0;
+    long long pr_wait = 0, pr_issue = 0, pr_commit = 0, pr_acc = 0, pt = prof_on ? clock64() : 0;
+    const long long pt_start = pt;
+#define US_PROF(var) do { if (prof_on) { const long long n_ = clock64(); var += n_ - pt; pt = n_; } } while (0)
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
       const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
@@ -260,8 +300,10 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       const uint32_t idesc_main = idesc_base | ((uint32_t)(gr.n_main >> 3) << 17);
       const uint32_t idesc_lo = idesc_base | ((uint32_t)(gr.n_lo >> 3) << 17);
       const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
-      mbar_wait_warp(&tempty[acc], acc_ph ^ 1, a.error_flag);
+      US_PROF(pr_issue);
+      us_wait(&tempty[acc], acc_ph ^ 1, lane, a.error_flag);
       tc_fence_after();
+      US_PROF(pr_acc);
       const uint32_t d_tmem0 = tmem_base + acc * a.acc_stride;
       const uint32_t bchunk16 = (uint32_t)gr.n_main;           // K-chunk pitch of the slab in 16-byte units
       const int n_st = gr.n_fft / US_KC / a.ks;
@@ -272,8 +314,9 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         const uint32_t s = k % S;
         const uint32_t d_tmem = d_tmem0 + (uint32_t)(st & (a.parts - 1)) * a.part_stride;
         const uint32_t accum = st >= a.parts ? 1u : 0u;
-        mbar_wait_warp(&full[s], (k / S) & 1, a.error_flag);
+        us_wait(&full[s], (k / S) & 1, lane, a.error_flag);
         tc_fence_after();
+        US_PROF(pr_wait);
         const uint32_t base = smem_u32(smem_raw + s * stage_bytes);
         const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
         const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
@@ -282,10 +325,16 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         if (!(a.debug & 1))
           us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
                        2u * (US_PLANE_BYTES >> 4), 2u * bchunk16);
+        US_PROF(pr_issue);
         tc_commit(&empty[s]);
         if (st == n_st - 1) tc_commit(&tfull[acc]);
         __syncwarp();
+        US_PROF(pr_commit);
       }
+    }
+    if (prof_on && lane == 0) {
+      long long* o = a.prof + (size_t)blockIdx.x * 8;
+      o[0] = pr_wait; o[1] = pr_issue; o[2] = pr_commit; o[3] = pr_acc; o[4] = clock64() - pt_start; o[5] = k;
     }
   } else if (warp == US_W_BANK) {
     // =========================== bank loader ===========================
@@ -300,87 +349,82 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         const uint8_t* src = reinterpret_cast<const uint8_t*>(gr.b_pack) + (size_t)slice * n_st * bytes;
         for (int st = 0; st < n_st; ++st, ++k) {
           const uint32_t s = k % S;
-          mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
+          while (!us_test_wait(&empty[s], ((k / S) & 1) ^ 1)) {}
           if (a.debug & 8) { mbar_arrive(&full[s]); continue; }
           mbar_arrive_expect_tx(&full[s], bytes);
           bulk_g2s(smem_u32(smem_raw + s * stage_bytes + 2u * US_A_BYTES), src + (size_t)st * bytes, bytes, &full[s]);
         }
       }
     }
-  } else if (warp < US_W_CONV0) {
+  } else {
     // =========================== row loaders ===========================
-    const int ltid = threadIdx.x - 32 * US_W_LOAD0;
-    // a warp instruction copies 4 rows x 128 contiguous bytes (lane = plane + 8 * row): 4 cache lines per request
-    // instead of 32, and 4 shared-memory wavefronts thanks to the padded plane pitch
-    const int plane = ltid & 7, row0 = ltid >> 3;
-    uint32_t k = 0;
+    // `load_groups` groups of warps; group q fills stages q, q + groups, ... of every item (the stage count is a
+    // multiple of 4): the generic -> async proxy fence that has to follow the shared-memory stores costs ~1000 cycles,
+    // and a warp that fenced every stage capped the pipeline at one stage per fence (measured: 1100 cycles per stage
+    // with every copy and MMA switched off).  groups <= ring stages, or a group could wait for a slot two uses ahead
+    // and be fooled by the barrier's phase parity.  lane = plane + 8 * row: a warp instruction reads 4 rows x 128
+    // contiguous bytes (4 cache lines) and writes 4 shared-memory wavefronts (padded plane pitch); a thread owns plane
+    // (t & 7) of `rpt` rows and keeps its NEXT stage in registers, loaded while the other groups' stages run.
+    const int NG = a.load_groups, wpg = US_LOAD_WARPS / NG, rpt = 2 * NG, rstep = 64 / NG;
+    const int lw = warp - US_W_LOAD0;
+    const int grp = lw / wpg, t = (lw - grp * wpg) * 32 + lane;
+    const int plane = t & 7, row0 = t >> 3;
+    const uint32_t dst_off = (uint32_t)plane * US_PLANE_BYTES + (uint32_t)row0 * 16u;
+    uint32_t k0 = 0;                                   // ring index of the item's first stage
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
       const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
       const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
       const int n_st = gr.n_fft / US_KC / a.ks;
-      const float* src[4];
+      const float4* src[US_MAX_RPT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(row0 + 32 * i));
+      for (int i = 0; i < US_MAX_RPT; ++i) {
+        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(row0 + rstep * (i < rpt ? i : 0)));
         const int T = a.clip_frames[r.clip];
         const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
-        src[i] = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane + (int)slice * n_st * US_KC;
+        src[i] = reinterpret_cast<const float4*>(gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane +
+                                                 (int)slice * n_st * US_KC);
       }
-      const uint32_t dst_off = (uint32_t)plane * US_PLANE_BYTES + (uint32_t)row0 * 16u;
-      for (int st = 0; st < n_st; ++st, ++k) {
+      float4 x[US_MAX_RPT];
+      const bool copy = !(a.debug & 2);
+#pragma unroll
+      for (int i = 0; i < US_MAX_RPT; ++i)
+        x[i] = (copy && i < rpt) ? __ldcg(src[i] + grp * (US_KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int st = grp; st < n_st; st += NG) {
+        const uint32_t k = k0 + (uint32_t)st;
         const uint32_t s = k % S;
-        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, a.error_flag);
-        const uint32_t dst = smem_u32(smem_raw + s * stage_bytes) + dst_off;
-        if (!(a.debug & 2)) {
+        long long lt0 = (a.debug & 16) ? clock64() : 0;
+        us_wait(&empty[s], ((k / S) & 1) ^ 1, lane, a.error_flag);
+        if ((a.debug & 16) && lw == 0 && lane == 0) a.prof[(size_t)blockIdx.x * 8 + 6] += clock64() - lt0;
+        lt0 = (a.debug & 16) ? clock64() : 0;
+        float4* dh = reinterpret_cast<float4*>(smem_raw + s * stage_bytes + dst_off);
+        float4* dl = reinterpret_cast<float4*>(smem_raw + s * stage_bytes + US_A_BYTES + dst_off);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * (32u * 16u)), "l"(src[i] + st * US_KC)
-                         : "memory");
-        }
-        cp_async_arrive_noinc(&raw[s]);
-      }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else {
-    // =========================== converters ===========================
-    const int ctid = threadIdx.x - 32 * US_W_CONV0;
-    constexpr int CT = 32 * US_CONV_WARPS;
-    constexpr int PER = US_PLANES * US_TILE_M / CT;                  // 4 float4 per thread and stage
-    int cidx[PER];                                                   // float4 index of (plane, row) in the padded planes
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int e = ctid + i * CT;
-      cidx[i] = (e >> 7) * (int)(US_PLANE_BYTES / 16) + (e & 127);
-    }
-    uint32_t k = 0;
-    for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-      const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
-      const int n_st = a.grp[g].n_fft / US_KC / a.ks;
-      for (int st = 0; st < n_st; ++st, ++k) {
-        const uint32_t s = k % S;
-        mbar_wait(&raw[s], (k / S) & 1, a.error_flag);
-        const float4* dh = reinterpret_cast<const float4*>(smem_raw + s * stage_bytes);
-        float4* dl = reinterpret_cast<float4*>(smem_raw + s * stage_bytes + US_A_BYTES);
-        float4 x[PER];
-        if (a.debug & 32) { __syncwarp(); if (lane == 0) mbar_arrive(&full[s]); continue; }
-#pragma unroll
-        for (int i = 0; i < PER; ++i) x[i] = dh[cidx[i]];
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
+        for (int i = 0; i < US_MAX_RPT; ++i) {
+          if (i >= rpt) break;
           // kind::tf32 reads the top 19 bits of an operand: the raw fp32 samples ARE the hi operand, and
           // lo = x - trunc13(x) is exact in fp32 (cqt_umma.cu)
+          const float4 v = x[i];
           float4 l;
-          l.x = x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u);
-          l.y = x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u);
-          l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u);
-          l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u);
-          dl[cidx[i]] = l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          dh[i * rstep] = v;                      // rows row0 + rstep * i
+          dl[i * rstep] = (a.debug & 32) ? v : l;
         }
         fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+        if ((a.debug & 16) && lw == 0 && lane == 0) a.prof[(size_t)blockIdx.x * 8 + 7] += clock64() - lt0;
+        // this group's next stage: in flight while the other groups' stages are consumed
+        if (st + NG < n_st && copy) {
+#pragma unroll
+          for (int i = 0; i < US_MAX_RPT; ++i)
+            if (i < rpt) x[i] = __ldcg(src[i] + (st + NG) * (US_KC / 4));
+        }
       }
+      k0 += (uint32_t)n_st;
     }
   }
 
@@ -417,6 +461,7 @@ struct CqtStreamState {
   size_t smem_bytes = 0;
   int stages = 0, num_sms = 0, parts = 1, bufs = 2;
   int* d_error = nullptr;
+  long long* d_prof = nullptr;
 };
 
 namespace saga {
@@ -501,6 +546,8 @@ void cqt_stream_plan_init(saga_cqt_plan* p) {
   st->acc_stride = parts * w;
   if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return; }
   cudaMemset(st->d_error, 0, sizeof(int));
+  if (cudaMalloc(&st->d_prof, sizeof(long long) * 256 * 8) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemset(st->d_prof, 0, sizeof(long long) * 256 * 8);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -516,6 +563,7 @@ void cqt_stream_plan_free(saga_cqt_plan* p) {
   if (!p->stream_tc) return;
   for (auto& pk : p->stream_tc->packs) cudaFree(pk.d_pack);
   cudaFree(p->stream_tc->d_error);
+  cudaFree(p->stream_tc->d_prof);
   delete p->stream_tc;
   p->stream_tc = nullptr;
 }
@@ -568,7 +616,9 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   a.parts = st->parts;
   a.bufs = st->bufs;
   a.stages = st->stages;
+  a.load_groups = st->stages >= 4 ? 4 : 2;
   a.error_flag = st->d_error;
+  a.prof = st->d_prof;
   {
     const char* dbg = SAGA_OPT("SAGA_UMMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
@@ -596,8 +646,23 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     SAGA_LAUNCH_CHECK();
   }
   const int grid = (int)std::min<int64_t>(a.total_items, n_sm);
+  if (a.debug & 16) cudaMemsetAsync(st->d_prof, 0, sizeof(long long) * 256 * 8, stream);
   cqt_umma_stream_kernel<<<grid, US_THREADS, st->smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
+  if (a.debug & 16) {
+    // profiling aid only: synchronous read-back of the MMA issuer's cycle split, mean over CTAs
+    std::vector<long long> h((size_t)grid * 8);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), st->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    static const char* names[8] = {"mma.wait_full", "mma.issue", "mma.commit", "mma.wait_tempty", "mma.total", "stages",
+                                   "load0.wait_empty", "load0.store_fence_arrive"};
+    fprintf(stderr, "us_prof stages/ring=%d groups=%d parts=%d bufs=%d items=%u\n", a.stages, a.load_groups, a.parts, a.bufs, a.total_items);
+    for (int sidx = 0; sidx < 8; ++sidx) {
+      double sum = 0;
+      for (int c = 0; c < grid; ++c) sum += (double)h[(size_t)c * 8 + sidx];
+      fprintf(stderr, "us_prof %-26s %12.0f per CTA\n", names[sidx], sum / grid);
+    }
+  }
   return SAGA_OK;
 }
 

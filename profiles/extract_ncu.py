@@ -20,7 +20,9 @@ KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
         "launch__block_size", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct"]
+        "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct",
+        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_read.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__inst_executed_pipe_tensor.sum"]
 STALL = re.compile(r"smsp__average_warps?_issue_stalled_(\w+)_per_issue_active\.ratio$|"
                    r"smsp__average_warp_latency_issue_stalled_(\w+)\.ratio$")
 
