@@ -208,9 +208,11 @@ int64_t saga_cqt_workspace_bytes(const saga_cqt_plan* plan, int n_clips, int64_t
  * the per-item length look-ups).
  * C_mag_out: |C| frame-major: (clip c, frame t, bin k) at c*out_clip_stride + t*frame_pitch + k
  * C_cplx_out: optional float2 complex CQT, same indexing in float2 units
- * impl: 0 = default (tcgen05 tensor-core path, 3xTF32 split = fp32-grade accuracy, when the
- *       plan fits it, else the fp32 CUDA-core path), 1 = force the fp32 CUDA-core path
- *       (validation), 2 = force the tensor path (SAGA_ERR_UNSUPPORTED if it does not fit),
+ * impl: 0 = default: tcgen05 tensor cores with a 3xTF32 split (fp32-grade accuracy) -- the resident-bank kernel
+ *       when the octave banks fit shared memory (12 bins per octave), else the streamed-bank kernel (24 / 48 / 192
+ *       bins per octave: 1e-5 of peak, 2e-5 for 8192-sample kernels), else the fp32 CUDA-core path;
+ *       1 = force the fp32 CUDA-core path (validation; option SAGA_CQT_STREAM=0 does the same for the streamed
+ *       kernel only), 2 = force a tensor path (SAGA_ERR_UNSUPPORTED if neither fits),
  *       3 = tensor path with a single TF32 pass (measured 1.1e-4 of peak: NOT parity-grade)
  *       | SAGA_CQT_SKIP_CONTRACT: run only the decimation cascade (fills the workspace)
  *       | SAGA_CQT_SKIP_CASCADE:  run only the contraction on a workspace filled by an earlier call
@@ -228,7 +230,9 @@ int saga_cqt_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* cl
  * of a full-window transform and `_resize`s it to 8 columns (util_audio.py:431-434, :384-409), so only columns
  * [s, s+8) are ever used.  Same cascade and reflect margins as saga_cqt_exec, but only the `frame_count` (1..8)
  * columns starting at frame_first[c] (device int32, may point past the clip: those columns are written as 0) are
- * contracted.  Output is COMPACT: column j of clip c at C_mag_out + c*out_clip_stride + j*frame_pitch. */
+ * contracted (streamed-bank tcgen05 kernel with rows = those columns; fp32 CUDA-core kernel when the plan does
+ * not fit it or SAGA_CQT_STREAM=0).  Output is COMPACT: column j of clip c at C_mag_out + c*out_clip_stride +
+ * j*frame_pitch. */
 int saga_cqt_frames_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
                          const int64_t* clip_lens, int n_clips, int64_t max_len,
                          const int32_t* frame_first, int frame_count, float* C_mag_out,
