@@ -430,6 +430,35 @@ def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo):
     assert float(fr[2].abs().max()) == 0.0                     # windows past the clip end are all zero
 
 
+@pytest.mark.parametrize("midi,factor", [(69, 4), (57, 8), (45, 16), (33, 32), (21, 64), (12, 128)])
+def test_cqt_polyphase_early_decimator_against_the_generic_one(saga, midi, factor):
+    """decimate_phase_kernel (polyphase form of the early resampy stage for factors >= 4: the note-relative transforms
+    of training.py:366-388 start below the note and decimate by up to 128 first) against the generic tile decimator
+    (SAGA_DEC_NO_PHASE=1), through the fp32 contraction, on a ragged batch with lengths that are not multiples of the
+    factor (librosa's zero-padded last sample), and against the oracle."""
+    ops, _ = saga
+    sr, hop = 44100, 1024
+    fmin = 440.0 * 2.0 ** ((midi - 69) / 12.0)
+    plan = ops.CqtPlan(sr, hop, fmin, 36, 24, filter_scale=2)
+    assert plan.early_factor == factor
+    n = 264600
+    lens = [n, n - 12345, n - 1, 200001]
+    wav = np.zeros((len(lens), n), dtype=np.float32)
+    for i, m in enumerate(lens):
+        wav[i, :m] = piano_clip(80 + i, m, sr=sr)
+    x = dev(wav)
+    got = ops.cqt_batch(x, plan, lens=lens, impl=1, fill=float("nan"))["mag"]
+    with ops.options(SAGA_DEC_NO_PHASE="1"):
+        ref = ops.cqt_batch(x, plan, lens=lens, impl=1, fill=float("nan"))["mag"]
+    for i, m in enumerate(lens):
+        T = plan.num_frames(m)
+        a, b = got[i, :, :T], ref[i, :, :T]
+        assert torch.isfinite(a).all()
+        assert float((a - b).abs().max()) <= 2e-6 * float(b.max())
+    o = np.abs(ocqt.cqt(wav[3, :lens[3]], sr=sr, hop_length=hop, fmin=fmin, n_bins=36, bins_per_octave=24, filter_scale=2))
+    check_mag(got[3, :, :o.shape[1]].cpu().numpy(), o, tol=5e-6)
+
+
 def test_cqt_ragged_batch(saga):
     ops, _ = saga
     sr, hop = 44100, 512
