@@ -201,7 +201,12 @@ class WindowFeaturePipeline:
 
     def host_pcm_buffers(self):
         """Extra buffers of the PCM-ingest variant of the e2e path: the windows and the rendered guesses
-        as int16 PCM plus the float64 factor of util_audio.py:781 per clip (pinned host + device)."""
+        as int16 PCM plus the float64 factor of util_audio.py:781 per clip (pinned host + device).
+        `wav_div` [W] float64: the divisor of each WINDOW.  The reference divides a render by the peak of the whole
+        song before it is cut into windows (util_audio.py:781, then :784 / `section`), so a window's divisor is its
+        song's max|pcm|, which the caller knows and the window alone does not: fill it in.  Entries <= 0 (the default)
+        fall back to the window's own peak, found on the device -- right only for clips that ARE whole renders, like
+        the single-note guesses, which always use their own peak."""
         h = self.host_buffers()
         if "wav_pcm" not in h:
             pin, d = dict(pin_memory=True), self.dev
@@ -209,6 +214,8 @@ class WindowFeaturePipeline:
                 wav_pcm=torch.empty((self.W, self.ns), dtype=torch.int16, **pin),
                 guess_pcm=torch.empty((self.W, self.ng), dtype=torch.int16, **pin),
                 mul=torch.ones((2, self.W), dtype=torch.float64, **pin),
+                wav_div=torch.zeros((self.W,), dtype=torch.float64, **pin),
+                d_wav_div=torch.empty((self.W,), device=d, dtype=torch.float64),
                 d_wav_pcm=torch.empty((self.W, self.ns), device=d, dtype=torch.int16),
                 d_guess_pcm=torch.empty((self.W, self.ng), device=d, dtype=torch.int16),
                 d_mul=torch.empty((2, self.W), device=d, dtype=torch.float64),
@@ -245,10 +252,12 @@ class WindowFeaturePipeline:
         s_out.wait_event(start)
         n = max(1, min(chunks, self.W))
         bounds = [(i * self.W // n, (i + 1) * self.W // n) for i in range(n)]
+        song_div = pcm16 and bool((h["wav_div"] > 0).all())
         ev_in, ev_cmp = [], []
         with torch.cuda.stream(s_in):
             if pcm16:
                 h["d_mul"].copy_(h["mul"], non_blocking=True)
+                h["d_wav_div"].copy_(h["wav_div"], non_blocking=True)
             for a, b in bounds:
                 if pcm16:
                     h["d_wav_pcm"][a:b].copy_(h["wav_pcm"][a:b], non_blocking=True)
@@ -265,8 +274,11 @@ class WindowFeaturePipeline:
                 s_cmp.wait_event(e)
                 if pcm16:
                     for k, (src, dst) in enumerate((("d_wav_pcm", "d_wav"), ("d_guess_pcm", "d_guess"))):
-                        peak = ops.pcm16_absmax(h[src][a:b], out=h["d_peak"][k, a:b])
-                        ops.pcm16_to_wave(h[src][a:b], mul=h["d_mul"][k, a:b], div=peak, out=h[dst][a:b])
+                        if k == 0 and song_div:
+                            div = h["d_wav_div"][a:b]                  # the song's peak (util_audio.py:781)
+                        else:
+                            div = ops.pcm16_absmax(h[src][a:b], out=h["d_peak"][k, a:b])
+                        ops.pcm16_to_wave(h[src][a:b], mul=h["d_mul"][k, a:b], div=div, out=h[dst][a:b])
                 self._run(h["d_wav"], h["d_guess"], h["d_offs"], w0=a, w1=b)
                 if feats:
                     self._reduce_features(h, a, b)
@@ -324,7 +336,7 @@ class WindowFeaturePipeline:
 
     def h2d_bytes(self, pcm16=False):
         if pcm16:
-            return self.W * (2 * (self.ns + self.ng) + 4 + 16)
+            return self.W * (2 * (self.ns + self.ng) + 4 + 16 + 8)
         return 4 * self.W * (self.ns + self.ng + 1)
 
     def d2h_bytes(self, returns="cqt"):

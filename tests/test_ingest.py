@@ -168,3 +168,18 @@ def test_run_host_pcm16_equals_float_path(saga):
         assert torch.equal(h["d_wav"].cpu(), torch.from_numpy(wf))
         assert torch.equal(h["C"], C0) and torch.equal(h["ref"], ref0)
         assert torch.equal(pipe.mag, mag0) and torch.equal(pipe.D[:, :pipe.T], D0[:, :pipe.T])   # row T of D is never written
+    # windows cut from a longer render: the divisor is the SONG's peak (util_audio.py:781 runs before `section`), given
+    # explicitly per window; the guesses keep their own peak
+    song_peak = np.abs(wav_pcm.astype(np.int32)).max(axis=1) + np.arange(W) * 7 + 100
+    wf2 = oin.pcm_to_wave(wav_pcm, mul[0], song_peak).astype(np.float32)
+    h["wav"].copy_(torch.from_numpy(wf2))
+    pipe.run_host(2)
+    torch.cuda.synchronize()
+    C1, ref1 = h["C"].clone(), h["ref"].clone()
+    h["wav_div"].copy_(torch.from_numpy(song_peak.astype(np.float64)))
+    h["C"].zero_(); h["ref"].zero_()
+    pipe.run_host(3, pcm16=True)
+    torch.cuda.synchronize()
+    assert torch.equal(h["d_wav"].cpu(), torch.from_numpy(wf2))
+    assert torch.equal(h["C"], C1) and torch.equal(h["ref"], ref1)
+    assert not torch.equal(C1, C0)
