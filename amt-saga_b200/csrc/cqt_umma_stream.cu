@@ -616,7 +616,11 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   a.parts = st->parts;
   a.bufs = st->bufs;
   a.stages = st->stages;
-  a.load_groups = st->stages >= 4 ? 4 : 2;
+  if (const char* cfg = SAGA_OPT("SAGA_UMMA_CFG")) {      // tuning aid: "stages,x" caps the ring depth
+    const int cap = atoi(cfg);
+    if (cap >= 2 && cap < a.stages) a.stages = cap;
+  }
+  a.load_groups = a.stages >= 4 ? 4 : 2;
   a.error_flag = st->d_error;
   a.prof = st->d_prof;
   {

@@ -302,6 +302,37 @@ def measure_note_step(torch, ops, synth, dev, n_windows=600, steps=5):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_cpus(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end
+    path are allocated (first touch) on the GPU's own NUMA node and the H2D copies of eight ranks do not all cross
+    one inter-socket link.  Best effort: returns a short description for the bench line, None if nothing was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # torch's device `local` is CUDA_VISIBLE_DEVICES-relative: resolve it through the PCI bus id
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        h = None
+        if bus is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                    h = hi
+                    break
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        usable = cpus & set(os.sched_getaffinity(0))
+        if not usable or usable == set(os.sched_getaffinity(0)):
+            return None if not usable else "gpu-local cpus = all usable cpus (%d)" % len(usable)
+        os.sched_setaffinity(0, usable)
+        return "bound to %d gpu-local cpus (NVML affinity)" % len(usable)
+    except Exception as e:      # no NVML, no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
+
+
 def run_saga(args):
     import torch
     import torch.distributed as dist
@@ -321,6 +352,7 @@ def run_saga(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local)      # before any pinned allocation: first touch puts the buffers next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -541,7 +573,9 @@ def run_saga(args):
                 "returns": "per window, reduced on the device by K5: the log-dB image's 8 columns from the guessed note's "
                            "onset [8 x 1025], the CQT's same 8 columns [8 x 84], compress_bands(subtracted mag)/ref [516 x 20], "
                            "post-subtraction ref_mag (the shapes the classifiers take, util_train_test.py:39-59)",
-                "overlap": "%d window chunks on 3 streams (H2D | kernels | D2H)" % args.e2e_chunks},
+                "overlap": "%d window chunks on 3 streams (H2D | kernels | D2H)" % args.e2e_chunks,
+                "h2d_GBps_aggregate": world * pipe.h2d_bytes() / (ms_e2e / e2e_steps * 1e-3) / 1e9,
+                "host_affinity": numa},
         "e2e_pcm16": {"value": world * W / (ms_pcm / e2e_steps * 1e-3), "unit": "window-features/s",
                       "h2d_bytes_per_step": pipe.h2d_bytes(pcm16=True), "d2h_bytes_per_step": pipe.d2h_bytes(RET),
                       "steps": e2e_steps, "ms_per_step": ms_pcm / e2e_steps, "launches_per_step": int(pcm_launches),
