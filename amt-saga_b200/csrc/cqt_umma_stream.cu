@@ -83,6 +83,8 @@ struct UsArgs {
   uint32_t tmem_cols, acc_stride, part_stride;
   int stages;
   int load_groups;              // 4, or 2 when the ring has fewer than 4 stages (see the row loaders)
+  int a_tmem;                   // 1: the A operand (rows, hi and lo) lives in TMEM, not in shared memory (see below)
+  uint32_t a_tmem_col;          // first TMEM column of the A ring: 64 columns per stage (32 hi | 32 lo)
   int parts, bufs;              // partial accumulators per buffer (stage st adds into partial st % parts), buffers
   // split-K (frame windows of small batches: a pitch group of the note-relative transforms is a few dozen clips, a
   // handful of tiles, and one CTA walking an 8192-sample kernel alone takes 220 us): the kernel length is cut into `ks`
@@ -124,36 +126,94 @@ __device__ __forceinline__ UsRow us_row(const UsArgs& a, uint32_t R) {
 // the partial accumulator) and the correction MMA (A_lo x B_hi, N = n_lo).  The correction goes to the hi*lo
 // columns [ncol, ncol + n_lo) -- NOT on top of the main columns as in cqt_umma.cu: every MMA is one truncating add
 // per accumulator element, and the large main sums should see as few of them as possible.
-__device__ __forceinline__ void us_mma_stage(uint32_t d_main, uint32_t d_lo, uint64_t a_hi, uint64_t a_lo, uint64_t b,
-                                             uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate, uint32_t da,
-                                             uint32_t db) {
+// Both stage helpers also PROBE the next stage's `full` barrier: the probe is issued before the MMAs and its result is
+// read after them, so its round trip hides behind the issue instead of preceding it.
+__device__ __forceinline__ uint32_t us_mma_stage(uint32_t d_main, uint32_t d_lo, uint64_t a_hi, uint64_t a_lo, uint64_t b,
+                                                 uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate, uint32_t da,
+                                                 uint32_t db, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ready;
   asm volatile(
       "{\n\t"
-      ".reg .pred e, p, t;\n\t"
+      ".reg .pred e, p, t, nx;\n\t"
       ".reg .b64 ah, al, bb, dda, ddb;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 nx, [%11], %12;\n\t"
       "elect.sync _|e, 0xFFFFFFFF;\n\t"
-      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
       "setp.eq.b32 t, 0, 0;\n\t"
-      "mov.b64 ah, %2;\n\t"
-      "mov.b64 al, %3;\n\t"
-      "mov.b64 bb, %4;\n\t"
-      "cvt.u64.u32 dda, %8;\n\t"
-      "cvt.u64.u32 ddb, %9;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, p;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "mov.b64 ah, %3;\n\t"
+      "mov.b64 al, %4;\n\t"
+      "mov.b64 bb, %5;\n\t"
+      "cvt.u64.u32 dda, %9;\n\t"
+      "cvt.u64.u32 ddb, %10;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bb, %6, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], al, bb, %7, t;\n\t"
       "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], al, bb, %7, t;\n\t"
       "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], al, bb, %7, t;\n\t"
       "add.u64 ah, ah, dda;\n\t add.u64 al, al, dda;\n\t add.u64 bb, bb, ddb;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bb, %5, t;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bb, %6, t;\n\t"
-      "}\n" ::"r"(d_main),
-      "r"(d_lo), "l"(a_hi), "l"(a_lo), "l"(b), "r"(idesc_main), "r"(idesc_lo), "r"(accumulate), "r"(da), "r"(db)
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], al, bb, %7, t;\n\t"
+      "selp.u32 %0, 1, 0, nx;\n\t"
+      "}\n"
+      : "=r"(ready)
+      : "r"(d_main), "r"(d_lo), "l"(a_hi), "l"(a_lo), "l"(b), "r"(idesc_main), "r"(idesc_lo), "r"(accumulate), "r"(da), "r"(db),
+        "r"(next_bar), "r"(next_parity)
       : "memory");
+  return ready;
 }
+
+// The same stage with the A operand in TENSOR MEMORY (lane = row, one 32-bit column per sample: a K-slice is 8
+// columns).  An SS-mode MMA is paced by the shared-memory bytes it reads (A 4 KB + B 32 N bytes per K-slice at
+// 128 B/clk, on top of the loaders' stores and the bank copies through the same port); with A in TMEM only the bank
+// crosses shared memory and the row loaders write straight from registers with tcgen05.st -- no shared-memory
+// stores, no generic -> async proxy fence.
+__device__ __forceinline__ uint32_t us_mma_stage_ts(uint32_t d_main, uint32_t d_lo, uint32_t a_hi, uint32_t a_lo, uint64_t b,
+                                                    uint32_t idesc_main, uint32_t idesc_lo, uint32_t accumulate, uint32_t db,
+                                                    uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, p, t, nx;\n\t"
+      ".reg .b64 bb, ddb;\n\t"
+      ".reg .b32 ah, al;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 nx, [%10], %11;\n\t"
+      "elect.sync _|e, 0xFFFFFFFF;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b32 ah, %3;\n\t"
+      "mov.b32 al, %4;\n\t"
+      "mov.b64 bb, %5;\n\t"
+      "cvt.u64.u32 ddb, %9;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bb, %6, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], [al], bb, %7, t;\n\t"
+      "add.u32 ah, ah, 8;\n\t add.u32 al, al, 8;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], [al], bb, %7, t;\n\t"
+      "add.u32 ah, ah, 8;\n\t add.u32 al, al, 8;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], [al], bb, %7, t;\n\t"
+      "add.u32 ah, ah, 8;\n\t add.u32 al, al, 8;\n\t add.u64 bb, bb, ddb;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bb, %6, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%2], [al], bb, %7, t;\n\t"
+      "selp.u32 %0, 1, 0, nx;\n\t"
+      "}\n"
+      : "=r"(ready)
+      : "r"(d_main), "r"(d_lo), "r"(a_hi), "r"(a_lo), "l"(b), "r"(idesc_main), "r"(idesc_lo), "r"(accumulate), "r"(db),
+        "r"(next_bar), "r"(next_parity)
+      : "memory");
+  return ready;
+}
+// 8 consecutive TMEM columns of this thread's lane <- 8 registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // lane 0 polls, the others wait at the warp barrier and then observe the completed phase themselves (one try_wait
 // that succeeds: acquire for every lane) -- 700 threads polling shared memory slow the barriers down for everybody
@@ -170,10 +230,13 @@ __device__ __forceinline__ bool us_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // test_wait (non-blocking) in a spin loop, NOT try_wait: a thread that try_wait suspends is woken late
 // (measured here: ~1900 cycles per hand-over with try_wait, two hand-overs per stage)
-__device__ __forceinline__ void us_wait(uint64_t* bar, uint32_t parity, int lane, int* error_flag) {
+// `sleep_ns`: waiters that are not on the critical path (row loaders, epilogue) back off between probes -- a warp
+// that spins flat out takes issue slots from the MMA issuer on the same scheduler
+__device__ __forceinline__ void us_wait(uint64_t* bar, uint32_t parity, int lane, int* error_flag, unsigned sleep_ns = 0) {
   if (lane == 0) {
     uint32_t spins = 0;
     while (!us_test_wait(bar, parity)) {
+      if (sleep_ns) __nanosleep(sleep_ns);
       if (++spins > UM_SPIN_LIMIT) {
         if (error_flag) atomicExch(error_flag, 1);
         __trap();
@@ -187,7 +250,8 @@ __device__ __forceinline__ void us_wait(uint64_t* bar, uint32_t parity, int lane
 __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __grid_constant__ UsArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t S = (uint32_t)a.stages;
-  const uint32_t stage_bytes = 2u * US_A_BYTES + a.b_stage_bytes;       // [A_hi | A_lo | B]
+  const uint32_t a_smem = a.a_tmem ? 0u : 2u * US_A_BYTES;
+  const uint32_t stage_bytes = a_smem + a.b_stage_bytes;                // [A_hi | A_lo | B], or [B] with A in TMEM
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S * stage_bytes);
   uint64_t* full = bars + US_MAX_STAGES;           // [S] hi / lo planes written and the bank slab landed
   uint64_t* empty = bars + 2 * US_MAX_STAGES;      // [S] the stage's MMAs retired
@@ -231,7 +295,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       const UsGroup& gr = a.grp[g];
       const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
       const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
-      us_wait(&tfull[acc], acc_ph, lane, a.error_flag);
+      us_wait(&tfull[acc], acc_ph, lane, a.error_flag, 500);
       tc_fence_after();
       const int64_t row = (int64_t)r.clip * a.out_clip_stride + (int64_t)(a.frame_first ? r.j : r.t) * a.frame_pitch;
       const uint32_t tbase = tmem_base + acc * a.acc_stride + ((uint32_t)(ew * 32) << 16);
@@ -287,11 +351,13 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     }
   } else if (warp == US_W_MMA) {
     // =========================== MMA issuer ===========================
-    uint32_t k = 0, it_acc = 0;
+    uint32_t k = 0, it_acc = 0, ring_s = 0, ring_ph = 0;
+    bool next_ready = false;
     const bool prof_on = (a.debug & 16) != 0;
     long long pr_wait = 0, pr_issue = 0, pr_commit = 0, pr_acc = 0, pt = prof_on ? clock64() : 0;
     const long long pt_start = pt;
 #define US_PROF(var) do { if (prof_on) { const long long n_ = clock64(); var += n_ - pt; pt = n_; } } while (0)
+#define US_TL(kk, slot) do { if ((a.debug & 128) && blockIdx.x == 0 && lane == 0 && (kk) < 96u) a.prof[2048 + (kk) * 8 + (slot)] = clock64(); } while (0)
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
       const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
@@ -311,25 +377,55 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       // accumulation steps (measured ~6.6e-9 of peak per kernel sample).  Long kernels therefore alternate between
       // `parts` partial accumulators, which the epilogue adds in fp32.
       for (int st = 0; st < n_st; ++st, ++k) {
-        const uint32_t s = k % S;
+        // ring slot / phase kept incrementally (no divisions), and the NEXT stage's barrier is probed before this
+        // stage's MMAs are issued: an mbarrier probe is a ~150-cycle round trip, and with wait -> issue -> commit -> wait
+        // in series the tensor pipe idled for ~800 cycles per stage although the data had been there for thousands
+        const uint32_t s = ring_s, ph = ring_ph;
         const uint32_t d_tmem = d_tmem0 + (uint32_t)(st & (a.parts - 1)) * a.part_stride;
         const uint32_t accum = st >= a.parts ? 1u : 0u;
-        us_wait(&full[s], (k / S) & 1, lane, a.error_flag);
-        tc_fence_after();
+        if (!next_ready) {
+          uint32_t spins = 0;
+          while (!us_test_wait(&full[s], ph)) {
+            if (++spins > UM_SPIN_LIMIT) {
+              if (a.error_flag) atomicExch(a.error_flag, 1);
+              __trap();
+            }
+          }
+        }
+        ring_s = s + 1 == S ? 0u : s + 1;
+        ring_ph = s + 1 == S ? ph ^ 1u : ph;
+        const uint32_t nbar = smem_u32(&full[ring_s]);
+        // A written by tcgen05.st of other threads needs the tcgen05 fence; operands that came through shared memory
+        // (generic stores + proxy fence, bulk copies) are ordered by the mbarrier alone
+        if (a.a_tmem) tc_fence_after();
         US_PROF(pr_wait);
+        US_TL(k, 0);
         const uint32_t base = smem_u32(smem_raw + s * stage_bytes);
-        const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
-        const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
-        const uint64_t db = smem_desc(base + 2u * US_A_BYTES, bchunk16 * 16u, 128);
+        const uint64_t db = smem_desc(base + a_smem, bchunk16 * 16u, 128);
         // 4 K-slices of 8 samples: planes (0,1), (2,3), (4,5), (6,7) against bank chunks (0,1), ...
-        if (!(a.debug & 1))
-          us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
-                       2u * (US_PLANE_BYTES >> 4), 2u * bchunk16);
+        if (a.debug & 1) {
+          next_ready = false;
+        } else if (a.a_tmem) {
+          const uint32_t ta = tmem_base + a.a_tmem_col + s * 64u;
+          next_ready = us_mma_stage_ts(d_tmem, d_tmem + (uint32_t)gr.ncol, ta, ta + 32u, db, idesc_main, idesc_lo, accum,
+                                       2u * bchunk16, nbar, ring_ph) != 0;
+        } else {
+          const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
+          const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
+          next_ready = us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
+                                    2u * (US_PLANE_BYTES >> 4), 2u * bchunk16, nbar, ring_ph) != 0;
+        }
         US_PROF(pr_issue);
-        tc_commit(&empty[s]);
+        US_TL(k, 1);
+        if (a.debug & 64) {        // timing experiment only (no MMAs in flight): plain arrive instead of tcgen05.commit
+          if (lane == 0) mbar_arrive(&empty[s]);
+        } else {
+          tc_commit(&empty[s]);
+        }
         if (st == n_st - 1) tc_commit(&tfull[acc]);
         __syncwarp();
         US_PROF(pr_commit);
+        US_TL(k, 2);
       }
     }
     if (prof_on && lane == 0) {
@@ -349,10 +445,11 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         const uint8_t* src = reinterpret_cast<const uint8_t*>(gr.b_pack) + (size_t)slice * n_st * bytes;
         for (int st = 0; st < n_st; ++st, ++k) {
           const uint32_t s = k % S;
-          while (!us_test_wait(&empty[s], ((k / S) & 1) ^ 1)) {}
+          while (!us_test_wait(&empty[s], ((k / S) & 1) ^ 1)) __nanosleep(100);
+          US_TL(k, 3);
           if (a.debug & 8) { mbar_arrive(&full[s]); continue; }
           mbar_arrive_expect_tx(&full[s], bytes);
-          bulk_g2s(smem_u32(smem_raw + s * stage_bytes + 2u * US_A_BYTES), src + (size_t)st * bytes, bytes, &full[s]);
+          bulk_g2s(smem_u32(smem_raw + s * stage_bytes + a_smem), src + (size_t)st * bytes, bytes, &full[s]);
         }
       }
     }
@@ -365,6 +462,65 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     // and be fooled by the barrier's phase parity.  lane = plane + 8 * row: a warp instruction reads 4 rows x 128
     // contiguous bytes (4 cache lines) and writes 4 shared-memory wavefronts (padded plane pitch); a thread owns plane
     // (t & 7) of `rpt` rows and keeps its NEXT stage in registers, loaded while the other groups' stages run.
+    if (a.a_tmem) {
+      // ---- A in TMEM: thread = row (TMEM lane 32 * (warp % 4) + lane, the quarter a warp may touch); a group of
+      // `wpg` warps has wpg / 4 warps per quarter, which share the stage's 32 samples of each row
+      const int NGt = a.load_groups, wpgt = US_LOAD_WARPS / NGt, per_q = wpgt / 4;     // per_q = 1 or 2
+      const int lwt = warp - US_W_LOAD0;
+      const int grpt = lwt / wpgt, sub = (lwt - grpt * wpgt) / 4;                       // sub: which part of K
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const int nk = US_KC / per_q;                                                     // samples per thread and stage
+      const int k_off = sub * nk;
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      uint32_t k0t = 0;
+      for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
+        const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
+        const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
+        const UsGroup& gr = a.grp[g];
+        const int n_st = gr.n_fft / US_KC / a.ks;
+        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)row);
+        const int T = a.clip_frames[r.clip];
+        const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
+        const float4* src = reinterpret_cast<const float4*>(gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop +
+                                                            (int)slice * n_st * US_KC + k_off);
+        const bool copy = !(a.debug & 2);
+        float4 x[US_KC / 4];
+#pragma unroll
+        for (int i = 0; i < US_KC / 4; ++i)
+          x[i] = (copy && 4 * i < nk) ? __ldg(src + grpt * (US_KC / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int st = grpt; st < n_st; st += NGt) {
+          const uint32_t k = k0t + (uint32_t)st;
+          const uint32_t s = k % S;
+          us_wait(&empty[s], ((k / S) & 1) ^ 1, lane, a.error_flag, 100);
+          tc_fence_after();
+          const uint32_t ta = tmem_base + lane_addr + a.a_tmem_col + s * 64u + (uint32_t)k_off;
+#pragma unroll
+          for (int i = 0; i < US_KC / 8; ++i) {
+            if (8 * i >= nk) break;
+            const float4 v0 = x[2 * i], v1 = x[2 * i + 1];
+            const float h[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)       // kind::tf32 reads the top 19 bits: raw samples ARE hi, lo = x - trunc13(x)
+              l[j] = (a.debug & 32) ? h[j] : h[j] - __uint_as_float(__float_as_uint(h[j]) & 0xFFFFE000u);
+            tmem_st8(ta + 8u * (uint32_t)i, h);
+            tmem_st8(ta + 32u + 8u * (uint32_t)i, l);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+          US_TL(k, 4 + ((lwt - grpt * wpgt) & 3));
+          if (st + NGt < n_st && copy) {
+#pragma unroll
+            for (int i = 0; i < US_KC / 4; ++i)
+              if (4 * i < nk) x[i] = __ldg(src + (st + NGt) * (US_KC / 4) + i);
+          }
+        }
+        k0t += (uint32_t)n_st;
+      }
+    } else {
     const int NG = a.load_groups, wpg = US_LOAD_WARPS / NG, rpt = 2 * NG, rstep = 64 / NG;
     const int lw = warp - US_W_LOAD0;
     const int grp = lw / wpg, t = (lw - grp * wpg) * 32 + lane;
@@ -394,7 +550,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         const uint32_t k = k0 + (uint32_t)st;
         const uint32_t s = k % S;
         long long lt0 = (a.debug & 16) ? clock64() : 0;
-        us_wait(&empty[s], ((k / S) & 1) ^ 1, lane, a.error_flag);
+        us_wait(&empty[s], ((k / S) & 1) ^ 1, lane, a.error_flag, 100);
         if ((a.debug & 16) && lw == 0 && lane == 0) a.prof[(size_t)blockIdx.x * 8 + 6] += clock64() - lt0;
         lt0 = (a.debug & 16) ? clock64() : 0;
         float4* dh = reinterpret_cast<float4*>(smem_raw + s * stage_bytes + dst_off);
@@ -426,6 +582,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       }
       k0 += (uint32_t)n_st;
     }
+    }   // shared-memory A
   }
 
   tc_fence_before();
@@ -460,6 +617,10 @@ struct CqtStreamState {
   uint32_t b_stage_bytes = 0, tmem_cols = 0, acc_stride = 0, part_stride = 0;
   size_t smem_bytes = 0;
   int stages = 0, num_sms = 0, parts = 1, bufs = 2;
+  // second configuration: A operand in TMEM (ts_stages = 0: the accumulators leave no room for it)
+  int ts_stages = 0;
+  uint32_t ts_col = 0;
+  size_t ts_smem_bytes = 0;
   int* d_error = nullptr;
   long long* d_prof = nullptr;
 };
@@ -544,10 +705,21 @@ void cqt_stream_plan_init(saga_cqt_plan* p) {
   st->tmem_cols = cols;
   st->part_stride = w;
   st->acc_stride = parts * w;
+  // A in TMEM: 64 columns per stage behind the accumulators (the allocation becomes all 512 columns)
+  {
+    const uint32_t acc_cols = (uint32_t)(st->bufs * parts) * w;
+    int ts = acc_cols < 512 ? (int)((512 - acc_cols) / 64) : 0;
+    ts = std::min(ts, std::min(US_MAX_STAGES, (int)((US_SMEM_LIMIT - 512u) / st->b_stage_bytes)));
+    if (ts >= 2) {
+      st->ts_stages = ts;
+      st->ts_col = acc_cols;
+      st->ts_smem_bytes = (size_t)ts * st->b_stage_bytes + 512;
+    }
+  }
   if (cudaMalloc(&st->d_error, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return; }
   cudaMemset(st->d_error, 0, sizeof(int));
-  if (cudaMalloc(&st->d_prof, sizeof(long long) * 256 * 8) != cudaSuccess) { cudaGetLastError(); return; }
-  cudaMemset(st->d_prof, 0, sizeof(long long) * 256 * 8);
+  if (cudaMalloc(&st->d_prof, sizeof(long long) * (2048 + 96 * 8)) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemset(st->d_prof, 0, sizeof(long long) * (2048 + 96 * 8));
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -616,6 +788,15 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   a.parts = st->parts;
   a.bufs = st->bufs;
   a.stages = st->stages;
+  size_t smem_bytes = st->smem_bytes;
+  // default: rows in TMEM when the accumulators leave room (SAGA_CQT_STREAM_SS=1 keeps them in shared memory: A/B)
+  if (st->ts_stages >= 2 && !SAGA_OPT("SAGA_CQT_STREAM_SS")) {
+    a.a_tmem = 1;
+    a.a_tmem_col = st->ts_col;
+    a.tmem_cols = 512;
+    a.stages = st->ts_stages;
+    smem_bytes = st->ts_smem_bytes;
+  }
   if (const char* cfg = SAGA_OPT("SAGA_UMMA_CFG")) {      // tuning aid: "stages,x" caps the ring depth
     const int cap = atoi(cfg);
     if (cap >= 2 && cap < a.stages) a.stages = cap;
@@ -650,9 +831,23 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     SAGA_LAUNCH_CHECK();
   }
   const int grid = (int)std::min<int64_t>(a.total_items, n_sm);
-  if (a.debug & 16) cudaMemsetAsync(st->d_prof, 0, sizeof(long long) * 256 * 8, stream);
-  cqt_umma_stream_kernel<<<grid, US_THREADS, st->smem_bytes, stream>>>(a);
+  if (a.debug & (16 | 128)) cudaMemsetAsync(st->d_prof, 0, sizeof(long long) * (2048 + 96 * 8), stream);
+  cqt_umma_stream_kernel<<<grid, US_THREADS, smem_bytes, stream>>>(a);
   SAGA_LAUNCH_CHECK();
+  if (a.debug & 128) {
+    // profiling aid only: timeline of CTA 0's first 96 stages (cycles relative to the first event)
+    std::vector<long long> h(96 * 8);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), st->d_prof + 2048, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "us_tl stage  mma.full_seen mma.issued mma.committed | bank.empty_seen | arrival of the 4 row-loader warps of the stage\n");
+    for (int kk = 0; kk < 96; ++kk) {
+      fprintf(stderr, "us_tl %3d ", kk);
+      for (int j = 0; j < 8; ++j) fprintf(stderr, " %8lld", h[kk * 8 + j] ? h[kk * 8 + j] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   if (a.debug & 16) {
     // profiling aid only: synchronous read-back of the MMA issuer's cycle split, mean over CTAs
     std::vector<long long> h((size_t)grid * 8);
@@ -660,7 +855,7 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     cudaMemcpy(h.data(), st->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     static const char* names[8] = {"mma.wait_full", "mma.issue", "mma.commit", "mma.wait_tempty", "mma.total", "stages",
                                    "load0.wait_empty", "load0.store_fence_arrive"};
-    fprintf(stderr, "us_prof stages/ring=%d groups=%d parts=%d bufs=%d items=%u\n", a.stages, a.load_groups, a.parts, a.bufs, a.total_items);
+    fprintf(stderr, "us_prof stages/ring=%d groups=%d parts=%d bufs=%d a_tmem=%d items=%u\n", a.stages, a.load_groups, a.parts, a.bufs, a.a_tmem, a.total_items);
     for (int sidx = 0; sidx < 8; ++sidx) {
       double sum = 0;
       for (int c = 0; c < grid; ++c) sum += (double)h[(size_t)c * 8 + sidx];

@@ -390,12 +390,15 @@ def test_cqt_frame_window_equals_columns_of_the_full_transform(saga, sr, hop, lo
                     assert np.abs(got[i, :, j] - ref[:, t]).max() <= tol * ref.max()
 
 
+@pytest.mark.parametrize("rows_in_smem", [False, True], ids=["rows_in_tmem", "rows_in_smem"])
 @pytest.mark.parametrize("low,n_bins,bpo", [("A0", 174, 24), ("A0", 348, 48), ("C4", 348, 192), ("C1", 84, 12)])
-def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo):
+def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo, rows_in_smem):
     """cqt_umma_stream_kernel (gathered rows x streamed bank on tcgen05: the transforms whose bank does not fit the
     resident kernel, and every frame window) against the fp32 CUDA-core kernels (SAGA_CQT_STREAM=0) on a ragged
     batch whose 128-row tiles straddle clips: whole transform (magnitude and complex), an empty-frame clip tail,
-    and 8-column frame windows before the start, inside, across and past the end of the clips."""
+    and 8-column frame windows before the start, inside, across and past the end of the clips.  Both operand
+    placements: rows (A) in tensor memory (default where the accumulators leave room: 24 / 48 per octave) and in
+    shared memory (SAGA_CQT_STREAM_SS=1; the only form at 192 per octave)."""
     ops, _ = saga
     sr, hop = 44100, 1024
     plan = ops.CqtPlan(sr, hop, osp.note_to_hz(low), n_bins, bpo, filter_scale=2)
@@ -406,12 +409,13 @@ def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo):
         wav[i, :m] = piano_clip(70 + i, m, sr=sr)
     x = dev(wav)
     tol = 1e-5 if bpo <= 48 else 2e-5
-    got = ops.cqt_batch(x, plan, lens=lens, want_complex=True, fill=float("nan"))
     firsts = [np.array([-3, 0, 5, 11, 20, 40, 60], dtype=np.int32),
               np.array([plan.num_frames(m) - 4 for m in lens], dtype=np.int32),
               np.array([plan.num_frames(m) + 2 for m in lens], dtype=np.int32)]
-    fr = [ops.cqt_frames_batch(x, plan, f, 8, lens=lens).clone() for f in firsts]
-    fr5 = ops.cqt_frames_batch(x, plan, firsts[0], 5, lens=lens).clone()
+    with ops.options(SAGA_CQT_STREAM_SS="1" if rows_in_smem else None):
+        got = ops.cqt_batch(x, plan, lens=lens, want_complex=True, fill=float("nan"))
+        fr = [ops.cqt_frames_batch(x, plan, f, 8, lens=lens).clone() for f in firsts]
+        fr5 = ops.cqt_frames_batch(x, plan, firsts[0], 5, lens=lens).clone()
     with ops.options(SAGA_CQT_STREAM="0"):
         ref = ops.cqt_batch(x, plan, lens=lens, want_complex=True, impl=1, fill=float("nan"))
         fr_ref = [ops.cqt_frames_batch(x, plan, f, 8, lens=lens).clone() for f in firsts]
