@@ -215,6 +215,31 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Row loads for the TMEM form.  tcgen05.st wants thread = row, but a thread that reads its own row touches 32
+// different cache lines per warp instruction: 1024 tag look-ups per stage, which made the row loaders the bottleneck
+// (every loader warp needed ~4500 cycles per stage of its own).  So the loads are issued coalesced -- P lanes share a
+// row (P consecutive 16-byte pieces), instruction i of lane (g, l) reads piece l of row P*g + i: 32 / P lines per
+// instruction -- and a P x P transpose inside each group of P lanes (log2 P butterfly steps of shuffles) hands
+// thread P*g + l all P pieces of row P*g + l.
+template <int P>
+__device__ __forceinline__ void us_transpose(float4 (&x)[8], int lane) {
+#pragma unroll
+  for (int b = 1; b < P; b <<= 1) {
+    const bool up = (lane & b) != 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      if (i & b) continue;
+      const int j = i | b;
+      float4 t = up ? x[i] : x[j];          // what the partner lane needs from here
+      t.x = __shfl_xor_sync(0xffffffffu, t.x, b);
+      t.y = __shfl_xor_sync(0xffffffffu, t.y, b);
+      t.z = __shfl_xor_sync(0xffffffffu, t.z, b);
+      t.w = __shfl_xor_sync(0xffffffffu, t.w, b);
+      if (up) x[i] = t; else x[j] = t;
+    }
+  }
+}
+
 // lane 0 polls, the others wait at the warp barrier and then observe the completed phase themselves (one try_wait
 // that succeeds: acquire for every lane) -- 700 threads polling shared memory slow the barriers down for everybody
 __device__ __forceinline__ bool us_test_wait(uint64_t* bar, uint32_t parity) {
@@ -482,16 +507,25 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)row);
         const int T = a.clip_frames[r.clip];
         const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
-        const float4* src = reinterpret_cast<const float4*>(gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop +
-                                                            (int)slice * n_st * US_KC + k_off);
-        const bool copy = !(a.debug & 2);
-        float4 x[US_KC / 4];
+        const float* own = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + (int)slice * n_st * US_KC + k_off;
+        // P = pieces per thread and stage (8, or 4 when two warps share a quarter); lane (g, l) = (lane / P, lane % P)
+        // reads piece l of rows P*g + i: fetch those rows' pointers from the lanes that own them
+        const int P = US_KC / 4 / per_q, lg = lane / P, ll = lane % P;
+        const float4* src[8];
 #pragma unroll
-        for (int i = 0; i < US_KC / 4; ++i)
-          x[i] = (copy && 4 * i < nk) ? __ldg(src + grpt * (US_KC / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const unsigned long long pv = __shfl_sync(0xffffffffu, (unsigned long long)own, (P * lg + (i < P ? i : 0)) & 31);
+          src[i] = reinterpret_cast<const float4*>(pv) + ll;
+        }
+        const bool copy = !(a.debug & 2);
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          x[i] = (copy && i < P) ? __ldcg(src[i] + grpt * (US_KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int st = grpt; st < n_st; st += NGt) {
           const uint32_t k = k0t + (uint32_t)st;
           const uint32_t s = k % S;
+          if (P == 8) us_transpose<8>(x, lane); else us_transpose<4>(x, lane);   // now x[0 .. P) = this thread's row
           us_wait(&empty[s], ((k / S) & 1) ^ 1, lane, a.error_flag, 100);
           tc_fence_after();
           const uint32_t ta = tmem_base + lane_addr + a.a_tmem_col + s * 64u + (uint32_t)k_off;
@@ -514,8 +548,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
           US_TL(k, 4 + ((lwt - grpt * wpgt) & 3));
           if (st + NGt < n_st && copy) {
 #pragma unroll
-            for (int i = 0; i < US_KC / 4; ++i)
-              if (4 * i < nk) x[i] = __ldg(src + (st + NGt) * (US_KC / 4) + i);
+            for (int i = 0; i < 8; ++i)
+              if (i < P) x[i] = __ldcg(src[i] + (st + NGt) * (US_KC / 4));
           }
         }
         k0t += (uint32_t)n_st;
