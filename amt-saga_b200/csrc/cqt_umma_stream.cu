@@ -47,7 +47,8 @@ constexpr int US_KC = 32;                                  // samples per stage
 constexpr int US_PLANES = US_KC / 4;
 constexpr int US_W_MMA = 4, US_W_BANK = 5, US_W_LOAD0 = 6;
 constexpr int US_LOAD_WARPS = 16;
-constexpr int US_THREADS = 32 * (US_W_LOAD0 + US_LOAD_WARPS);
+constexpr int US_W_MMA2 = US_W_LOAD0 + US_LOAD_WARPS;       // second MMA issuer (plans with >= 2 partial accumulators)
+constexpr int US_THREADS = 32 * (US_W_MMA2 + 1);
 constexpr int US_MAX_LOAD_GROUPS = 4;                      // stage q is filled by loader group q % groups
 constexpr int US_MAX_RPT = US_PLANES * US_TILE_M / (32 * US_LOAD_WARPS / US_MAX_LOAD_GROUPS);   // 8 pieces per thread
 constexpr int US_MAX_STAGES = 6;
@@ -83,6 +84,8 @@ struct UsArgs {
   uint32_t tmem_cols, acc_stride, part_stride;
   int stages;
   int load_groups;              // 4, or 2 when the ring has fewer than 4 stages (see the row loaders)
+  int issuers;                  // 1 or 2 MMA issuer warps; two take the stages in turn, each owning the partial
+                                // accumulator(s) of its stages (parts % issuers == 0: deterministic)
   int a_tmem;                   // 1: the A operand (rows, hi and lo) lives in TMEM, not in shared memory (see below)
   uint32_t a_tmem_col;          // first TMEM column of the A ring: 64 columns per stage (32 hi | 32 lo)
   int parts, bufs;              // partial accumulators per buffer (stage st adds into partial st % parts), buffers
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull[s], 1);
+      mbar_init(&tfull[s], a.issuers);
       mbar_init(&tempty[s], 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -374,11 +377,17 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-  } else if (warp == US_W_MMA) {
-    // =========================== MMA issuer ===========================
-    uint32_t k = 0, it_acc = 0, ring_s = 0, ring_ph = 0;
+  } else if (warp == US_W_MMA || warp == US_W_MMA2) {
+    // =========================== MMA issuer(s) ===========================
+    // One thread issues a stage's 8 MMAs in ~500 cycles (the tensor pipe's pace) and then spends ~450 on commit, ring
+    // bookkeeping and the fence while the pipe drains.  With two issuer warps that take the stages in turn, one
+    // warp's bookkeeping runs under the other's MMAs.  Issuer w adds stage st (st % 2 == w) into partial accumulator
+    // st % parts, so with parts % 2 == 0 no accumulator is shared between the warps and the sums stay deterministic.
+    const uint32_t iw = warp == US_W_MMA ? 0u : 1u, NI = (uint32_t)a.issuers;
+    if (iw < NI) {
+    uint32_t k = iw, it_acc = 0, ring_s = iw % S, ring_ph = (iw / S) & 1u;
     bool next_ready = false;
-    const bool prof_on = (a.debug & 16) != 0;
+    const bool prof_on = (a.debug & 16) != 0 && iw == 0;
     long long pr_wait = 0, pr_issue = 0, pr_commit = 0, pr_acc = 0, pt = prof_on ? clock64() : 0;
     const long long pt_start = pt;
 #define US_PROF(var) do { if (prof_on) { const long long n_ = clock64(); var += n_ - pt; pt = n_; } } while (0)
@@ -386,6 +395,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
       const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
       const UsGroup& gr = a.grp[g];
+      // (k runs over THIS issuer's stages: iw, iw + NI, ... across items; every item has a multiple of 4 stages)
       // instruction descriptors: D = f32, A = B = tf32, K-major both, M = 128
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(US_TILE_M >> 4) << 24);
       const uint32_t idesc_main = idesc_base | ((uint32_t)(gr.n_main >> 3) << 17);
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       // The tensor core adds into the fp32 accumulator with truncation: the error grows with the number of
       // accumulation steps (measured ~6.6e-9 of peak per kernel sample).  Long kernels therefore alternate between
       // `parts` partial accumulators, which the epilogue adds in fp32.
-      for (int st = 0; st < n_st; ++st, ++k) {
+      for (int st = (int)iw; st < n_st; st += (int)NI, k += NI) {
         // ring slot / phase kept incrementally (no divisions), and the NEXT stage's barrier is probed before this
         // stage's MMAs are issued: an mbarrier probe is a ~150-cycle round trip, and with wait -> issue -> commit -> wait
         // in series the tensor pipe idled for ~800 cycles per stage although the data had been there for thousands
@@ -417,8 +427,10 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
             }
           }
         }
-        ring_s = s + 1 == S ? 0u : s + 1;
-        ring_ph = s + 1 == S ? ph ^ 1u : ph;
+        ring_s = s + NI;                       // this issuer's next stage
+        ring_ph = ph;
+        if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }
+        if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }      // (NI = 2 on a ring of 2 or 3 stages can wrap twice: S >= 2)
         const uint32_t nbar = smem_u32(&full[ring_s]);
         // A written by tcgen05.st of other threads needs the tcgen05 fence; operands that came through shared memory
         // (generic stores + proxy fence, bulk copies) are ordered by the mbarrier alone
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
         } else {
           tc_commit(&empty[s]);
         }
-        if (st == n_st - 1) tc_commit(&tfull[acc]);
+        if (st + (int)NI >= n_st) tc_commit(&tfull[acc]);      // this issuer's last stage of the item
         __syncwarp();
         US_PROF(pr_commit);
         US_TL(k, 2);
@@ -457,6 +469,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       long long* o = a.prof + (size_t)blockIdx.x * 8;
       o[0] = pr_wait; o[1] = pr_issue; o[2] = pr_commit; o[3] = pr_acc; o[4] = clock64() - pt_start; o[5] = k;
     }
+    }   // iw < NI
   } else if (warp == US_W_BANK) {
     // =========================== bank loader ===========================
     if (lane == 0) {
@@ -650,7 +663,7 @@ struct CqtStreamState {
   bool supported = false;
   uint32_t b_stage_bytes = 0, tmem_cols = 0, acc_stride = 0, part_stride = 0;
   size_t smem_bytes = 0;
-  int stages = 0, num_sms = 0, parts = 1, bufs = 2;
+  int stages = 0, num_sms = 0, parts = 1, bufs = 2, issuers = 1;
   // second configuration: A operand in TMEM (ts_stages = 0: the accumulators leave no room for it)
   int ts_stages = 0;
   uint32_t ts_col = 0;
@@ -732,6 +745,7 @@ void cqt_stream_plan_init(saga_cqt_plan* p) {
   const uint32_t w = ((uint32_t)n_main_max + 31u) & ~31u;
   while (parts > 1 && (uint32_t)parts * w > 512) parts /= 2;
   if (w > 512) return;
+  st->issuers = parts >= 2 ? 2 : 1;        // what SAGA_CQT_STREAM_TWO_ISSUERS may use
   st->parts = parts;
   st->bufs = (2u * parts * w <= 512) ? 2 : 1;
   uint32_t cols = 32;
@@ -835,6 +849,14 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     const int cap = atoi(cfg);
     if (cap >= 2 && cap < a.stages) a.stages = cap;
   }
+  // Default: ONE issuer.  Two (SAGA_CQT_STREAM_TWO_ISSUERS=1, plans with two partial accumulators) measured slower:
+  // 348/48 3.78 -> 3.95 ms, 348/192 10.2 -> 15.0 ms per 600 windows (the ring must then be an even number of stages)
+  a.issuers = SAGA_OPT("SAGA_CQT_STREAM_TWO_ISSUERS") ? st->issuers : 1;
+  // Two issuers retire stages out of order with respect to each other.  A row-loader group only knows that the stage
+  // it filled one ring lap ago has retired; for the mbarrier phase parity to stay unambiguous every earlier use of the
+  // slot it waits for must have retired too, which holds when all of them belong to the SAME issuer: ring depth and
+  // loader groups are kept multiples of the issuer count (and groups <= depth).
+  if (a.issuers == 2) a.stages &= ~1;
   a.load_groups = a.stages >= 4 ? 4 : 2;
   a.error_flag = st->d_error;
   a.prof = st->d_prof;
