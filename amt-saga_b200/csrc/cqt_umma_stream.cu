@@ -838,7 +838,9 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   a.stages = st->stages;
   size_t smem_bytes = st->smem_bytes;
   // default: rows in TMEM when the accumulators leave room (SAGA_CQT_STREAM_SS=1 keeps them in shared memory: A/B)
-  if (st->ts_stages >= 2 && !SAGA_OPT("SAGA_CQT_STREAM_SS")) {
+  // (a deeper shared-memory ring beats a 2-stage TMEM ring: 348/48 3.14 against 3.35 ms; at 174/24 both have 5 stages
+  // and tie, and the TMEM form leaves 160 KB of shared memory unused)
+  if (st->ts_stages >= 2 && (st->ts_stages >= 4 || st->ts_stages >= st->stages) && !SAGA_OPT("SAGA_CQT_STREAM_SS")) {
     a.a_tmem = 1;
     a.a_tmem_col = st->ts_col;
     a.tmem_cols = 512;

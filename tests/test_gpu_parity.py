@@ -397,8 +397,8 @@ def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo, 
     resident kernel, and every frame window) against the fp32 CUDA-core kernels (SAGA_CQT_STREAM=0) on a ragged
     batch whose 128-row tiles straddle clips: whole transform (magnitude and complex), an empty-frame clip tail,
     and 8-column frame windows before the start, inside, across and past the end of the clips.  Both operand
-    placements: rows (A) in tensor memory (default where the accumulators leave room: 24 / 48 per octave) and in
-    shared memory (SAGA_CQT_STREAM_SS=1; the only form at 192 per octave)."""
+    placements: rows (A) in tensor memory (default where the accumulators leave room for a deep enough ring: 12 / 24
+    per octave) and in shared memory (SAGA_CQT_STREAM_SS=1; what 48 and 192 per octave use anyway)."""
     ops, _ = saga
     sr, hop = 44100, 1024
     plan = ops.CqtPlan(sr, hop, osp.note_to_hz(low), n_bins, bpo, filter_scale=2)
