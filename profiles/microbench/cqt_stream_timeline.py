@@ -8,11 +8,11 @@ plan = ops.CqtPlan(44100, 1024, note_to_hz("A0"), 174, 24, filter_scale=2)
 ops.cqt_batch(wav, plan); torch.cuda.synchronize()
 import time
 for ss in (None, "1"):
-  for dbg in (128, 128 | 256):
+  for dbg in (128,):
     print("debug", dbg, "smem_A", ss, file=sys.stderr, flush=True)
     with ops.options(SAGA_UMMA_DEBUG=str(dbg), SAGA_CQT_STREAM_SS=ss):
         ops.cqt_batch(wav, plan); torch.cuda.synchronize()
-    with ops.options(SAGA_UMMA_DEBUG=str(dbg & 256), SAGA_CQT_STREAM_SS=ss):
+    with ops.options(SAGA_UMMA_DEBUG=None, SAGA_CQT_STREAM_SS=ss):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ops.cqt_batch(wav, plan); a.record(); ops.cqt_batch(wav, plan); ops.cqt_batch(wav, plan); b.record(); torch.cuda.synchronize()
         print("ms per transform (cascade included): %.3f" % (a.elapsed_time(b) / 2), file=sys.stderr, flush=True)
