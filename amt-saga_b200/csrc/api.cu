@@ -31,7 +31,7 @@ static const char* const OPT_NAMES[] = {
     "SAGA_DEC_NO_FUSE", "SAGA_DEC_FUSE_MASK", "SAGA_CQT_CONTRACT_V1", "SAGA_UMMA_DEBUG", "SAGA_UMMA_CFG",
     "SAGA_UMMA_NO_SHARED_BANK", "SAGA_STFT_FRAMES", "SAGA_STFT_NO_EO", "SAGA_ISTFT_ONE_WARP", "SAGA_STFT_RING",
     "SAGA_STFT_RING_SHAPE", "SAGA_ISTFT_RING", "SAGA_SUB_CLUSTER_MIN_STEPS", "SAGA_SUB_NO_CLUSTER", "SAGA_SUB_NO_FLAT",
-    "SAGA_SUB_FLAT_CHUNKS", "SAGA_DB_LEAN", "SAGA_DB_CHUNKS", "SAGA_CQT_STREAM", "SAGA_DEC_NO_PHASE", "SAGA_ISTFT_RING_RUN", "SAGA_CQT_STREAM_SS", "SAGA_CQT_STREAM_TWO_ISSUERS"};
+    "SAGA_SUB_FLAT_CHUNKS", "SAGA_DB_LEAN", "SAGA_DB_CHUNKS", "SAGA_CQT_STREAM", "SAGA_DEC_NO_PHASE", "SAGA_ISTFT_RING_RUN", "SAGA_CQT_STREAM_SS", "SAGA_CQT_STREAM_TWO_ISSUERS", "SAGA_CQT_STREAM_NO_UNROLL"};
 constexpr int N_OPTS = sizeof(OPT_NAMES) / sizeof(OPT_NAMES[0]);
 static std::atomic<const char*> g_opts[N_OPTS];
 static std::once_flag g_opts_once;

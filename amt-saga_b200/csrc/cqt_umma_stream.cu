@@ -84,6 +84,7 @@ struct UsArgs {
   uint32_t tmem_cols, acc_stride, part_stride;
   int stages;
   int load_groups;              // 4, or 2 when the ring has fewer than 4 stages (see the row loaders)
+  int unroll2;                  // the issuer handles stages in pairs (ring of >= 4 stages)
   int issuers;                  // 1 or 2 MMA issuer warps; two take the stages in turn, each owning the partial
                                 // accumulator(s) of its stages (parts % issuers == 0: deterministic)
   int a_tmem;                   // 1: the A operand (rows, hi and lo) lives in TMEM, not in shared memory (see below)
@@ -411,58 +412,73 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       // The tensor core adds into the fp32 accumulator with truncation: the error grows with the number of
       // accumulation steps (measured ~6.6e-9 of peak per kernel sample).  Long kernels therefore alternate between
       // `parts` partial accumulators, which the epilogue adds in fp32.
-      for (int st = (int)iw; st < n_st; st += (int)NI, k += NI) {
-        // ring slot / phase kept incrementally (no divisions), and the NEXT stage's barrier is probed before this
-        // stage's MMAs are issued: an mbarrier probe is a ~150-cycle round trip, and with wait -> issue -> commit -> wait
-        // in series the tensor pipe idled for ~800 cycles per stage although the data had been there for thousands
-        const uint32_t s = ring_s, ph = ring_ph;
-        const uint32_t d_tmem = d_tmem0 + (uint32_t)(st & (a.parts - 1)) * a.part_stride;
-        const uint32_t accum = st >= a.parts ? 1u : 0u;
-        if (!next_ready) {
-          uint32_t spins = 0;
-          while (!us_test_wait(&full[s], ph)) {
-            if (++spins > UM_SPIN_LIMIT) {
-              if (a.error_flag) atomicExch(a.error_flag, 1);
-              __trap();
+      // Stages are issued in PAIRS when the ring is deep enough (unroll 2): both stages' MMAs go out back to back
+      // and the two commits follow, so the commit / bookkeeping gap in which the tensor pipe drains is paid once per
+      // 16 MMAs instead of once per 8.
+      const int U = (a.unroll2 && NI == 1) ? 2 : 1;
+      for (int st0 = (int)iw; st0 < n_st; st0 += (int)NI * U) {
+        uint32_t slot[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u >= U) break;
+          const int st = st0 + u * (int)NI;
+          // ring slot / phase kept incrementally (no divisions), and the NEXT stage's barrier is probed before this
+          // stage's MMAs are issued: an mbarrier probe is a ~150-cycle round trip, and with wait -> issue -> commit ->
+          // wait in series the tensor pipe idled ~800 cycles per stage although the data had been there for thousands
+          const uint32_t s = ring_s, ph = ring_ph;
+          slot[u] = s;
+          const uint32_t d_tmem = d_tmem0 + (uint32_t)(st & (a.parts - 1)) * a.part_stride;
+          const uint32_t accum = st >= a.parts ? 1u : 0u;
+          if (!next_ready) {
+            uint32_t spins = 0;
+            while (!us_test_wait(&full[s], ph)) {
+              if (++spins > UM_SPIN_LIMIT) {
+                if (a.error_flag) atomicExch(a.error_flag, 1);
+                __trap();
+              }
             }
           }
-        }
-        ring_s = s + NI;                       // this issuer's next stage
-        ring_ph = ph;
-        if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }
-        if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }      // (NI = 2 on a ring of 2 or 3 stages can wrap twice: S >= 2)
-        const uint32_t nbar = smem_u32(&full[ring_s]);
-        // A written by tcgen05.st of other threads needs the tcgen05 fence; operands that came through shared memory
-        // (generic stores + proxy fence, bulk copies) are ordered by the mbarrier alone
-        if (a.a_tmem) tc_fence_after();
-        US_PROF(pr_wait);
-        US_TL(k, 0);
-        const uint32_t base = smem_u32(smem_raw + s * stage_bytes);
-        const uint64_t db = smem_desc(base + a_smem, bchunk16 * 16u, 128);
-        // 4 K-slices of 8 samples: planes (0,1), (2,3), (4,5), (6,7) against bank chunks (0,1), ...
-        if (a.debug & 1) {
-          next_ready = false;
-        } else if (a.a_tmem) {
-          const uint32_t ta = tmem_base + a.a_tmem_col + s * 64u;
-          next_ready = us_mma_stage_ts(d_tmem, d_tmem + (uint32_t)gr.ncol, ta, ta + 32u, db, idesc_main, idesc_lo, accum,
-                                       2u * bchunk16, nbar, ring_ph) != 0;
-        } else {
-          const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
-          const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
-          next_ready = us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
-                                    2u * (US_PLANE_BYTES >> 4), 2u * bchunk16, nbar, ring_ph) != 0;
+          ring_s = s + NI;                       // this issuer's next stage
+          ring_ph = ph;
+          if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }
+          if (ring_s >= S) { ring_s -= S; ring_ph ^= 1u; }      // (NI = 2 on a ring of 2 or 3 stages can wrap twice: S >= 2)
+          const uint32_t nbar = smem_u32(&full[ring_s]);
+          // A written by tcgen05.st of other threads needs the tcgen05 fence; operands that came through shared memory
+          // (generic stores + proxy fence, bulk copies) are ordered by the mbarrier alone
+          if (a.a_tmem) tc_fence_after();
+          if (u == 0) { US_PROF(pr_wait); US_TL(k, 0); }
+          const uint32_t base = smem_u32(smem_raw + s * stage_bytes);
+          const uint64_t db = smem_desc(base + a_smem, bchunk16 * 16u, 128);
+          // 4 K-slices of 8 samples: planes (0,1), (2,3), (4,5), (6,7) against bank chunks (0,1), ...
+          if (a.debug & 1) {
+            next_ready = false;
+          } else if (a.a_tmem) {
+            const uint32_t ta = tmem_base + a.a_tmem_col + s * 64u;
+            next_ready = us_mma_stage_ts(d_tmem, d_tmem + (uint32_t)gr.ncol, ta, ta + 32u, db, idesc_main, idesc_lo, accum,
+                                         2u * bchunk16, nbar, ring_ph) != 0;
+          } else {
+            const uint64_t dah = smem_desc(base, US_PLANE_BYTES, 128);
+            const uint64_t dal = smem_desc(base + US_A_BYTES, US_PLANE_BYTES, 128);
+            next_ready = us_mma_stage(d_tmem, d_tmem + (uint32_t)gr.ncol, dah, dal, db, idesc_main, idesc_lo, accum,
+                                      2u * (US_PLANE_BYTES >> 4), 2u * bchunk16, nbar, ring_ph) != 0;
+          }
         }
         US_PROF(pr_issue);
         US_TL(k, 1);
-        if (a.debug & 64) {        // timing experiment only (no MMAs in flight): plain arrive instead of tcgen05.commit
-          if (lane == 0) mbar_arrive(&empty[s]);
-        } else {
-          tc_commit(&empty[s]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u >= U) break;
+          if (a.debug & 64) {        // timing experiment only (no MMAs in flight): plain arrive instead of tcgen05.commit
+            if (lane == 0) mbar_arrive(&empty[slot[u]]);
+          } else {
+            tc_commit(&empty[slot[u]]);
+          }
         }
-        if (st + (int)NI >= n_st) tc_commit(&tfull[acc]);      // this issuer's last stage of the item
+        if (st0 + (int)NI * U >= n_st) tc_commit(&tfull[acc]);      // this issuer's last stage(s) of the item
         __syncwarp();
         US_PROF(pr_commit);
         US_TL(k, 2);
+        k += NI * (uint32_t)U;
       }
     }
     if (prof_on && lane == 0) {
@@ -859,6 +875,7 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
   // slot it waits for must have retired too, which holds when all of them belong to the SAME issuer: ring depth and
   // loader groups are kept multiples of the issuer count (and groups <= depth).
   if (a.issuers == 2) a.stages &= ~1;
+  a.unroll2 = (a.stages >= 4 && !SAGA_OPT("SAGA_CQT_STREAM_NO_UNROLL")) ? 1 : 0;
   a.load_groups = a.stages >= 4 ? 4 : 2;
   a.error_flag = st->d_error;
   a.prof = st->d_prof;
