@@ -416,6 +416,12 @@ def test_cqt_streamed_bank_kernel_against_its_fp32_twin(saga, low, n_bins, bpo, 
         got = ops.cqt_batch(x, plan, lens=lens, want_complex=True, fill=float("nan"))
         fr = [ops.cqt_frames_batch(x, plan, f, 8, lens=lens).clone() for f in firsts]
         fr5 = ops.cqt_frames_batch(x, plan, firsts[0], 5, lens=lens).clone()
+        # same call again: bit-identical (fixed MMA order per tile, split-K slices added in slice order)
+        again = ops.cqt_batch(x, plan, lens=lens, want_complex=True, fill=float("nan"))
+        for i, m in enumerate(lens):
+            T = plan.num_frames(m)
+            assert torch.equal(again["mag"][i, :, :T], got["mag"][i, :, :T])
+        assert torch.equal(ops.cqt_frames_batch(x, plan, firsts[0], 8, lens=lens), fr[0])
     with ops.options(SAGA_CQT_STREAM="0"):
         ref = ops.cqt_batch(x, plan, lens=lens, want_complex=True, impl=1, fill=float("nan"))
         fr_ref = [ops.cqt_frames_batch(x, plan, f, 8, lens=lens).clone() for f in firsts]
@@ -461,6 +467,37 @@ def test_cqt_polyphase_early_decimator_against_the_generic_one(saga, midi, facto
         assert float((a - b).abs().max()) <= 2e-6 * float(b.max())
     o = np.abs(ocqt.cqt(wav[3, :lens[3]], sr=sr, hop_length=hop, fmin=fmin, n_bins=36, bins_per_octave=24, filter_scale=2))
     check_mag(got[3, :, :o.shape[1]].cpu().numpy(), o, tol=5e-6)
+
+
+def test_cqt_streamed_bank_kernel_small_and_odd_batches(saga):
+    """Edges of the streamed tensor-core contraction: one clip, 129 clips of 3 frames (rows of 43 clips per tile, last
+    tile partly empty), every frame_count 1..8, windows entirely before / after the clip, against the fp32 twin."""
+    ops, _ = saga
+    sr, hop = 44100, 1024
+    plan = ops.CqtPlan(sr, hop, osp.note_to_hz("A0"), 174, 24, filter_scale=2)
+    n_min = 2 * hop + 1
+    while True:
+        try:
+            plan.check_length(n_min)
+            break
+        except Exception:
+            n_min += hop
+    for n_clips, n in ((1, n_min), (1, 50000), (129, n_min + 2 * hop)):
+        wav = np.stack([piano_clip(200 + (i % 7), n, sr=sr) * (1.0 + 0.01 * i) for i in range(n_clips)]).astype(np.float32)
+        x = dev(wav)
+        T = plan.num_frames(n)
+        first = ((np.arange(n_clips) * 5) % (T + 6) - 3).astype(np.int32)
+        res = {}
+        for tag, opt in (("tc", None), ("fp32", "0")):
+            with ops.options(SAGA_CQT_STREAM=opt):
+                res[tag] = (ops.cqt_batch(x, plan, impl=1 if opt else 0)["mag"].clone(),
+                            [ops.cqt_frames_batch(x, plan, first, fc).clone() for fc in range(1, 9)])
+        peak = float(res["fp32"][0].max())
+        assert float((res["tc"][0] - res["fp32"][0]).abs().max()) <= 1e-5 * peak
+        for a, b in zip(res["tc"][1], res["fp32"][1]):
+            assert a.shape == b.shape and torch.isfinite(a).all()
+            assert float((a - b).abs().max()) <= 1e-5 * peak
+            assert bool((a[b == 0] == 0).all())
 
 
 def test_cqt_ragged_batch(saga):
