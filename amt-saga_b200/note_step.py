@@ -48,6 +48,9 @@ class NoteStepBatch:
         self._fft_freq = np.linspace(0, float(sr) / 2, int(1 + self.N // 2), endpoint=True)   # util_audio.py:67
         self.mag = self.ph = self.wav = None
         self.fresh = True
+        self._dirty = None         # frames changed by the last subtract, while `wav` is an iSTFT of the previous magnitudes
+        self._wav_synced = False   # `wav` == iSTFT(magnitudes before the last subtract) (the original audio is not)
+        self.incremental_istft = True   # False: every rebuild of `wav` inverts all T frames (A/B twin)
         self._tone_fft = None
         self.full_cqt = False      # True: every slice_C transforms all 258 columns like the reference (A/B twin)
 
@@ -119,6 +122,7 @@ class NoteStepBatch:
         else:
             self.stale_ref = f32(window_ref_mag)   # `section` copied a cached ref_mag (util_audio.py:323)
         self.fresh = True
+        self._dirty, self._wav_synced = None, False
 
     # ------------------------------------------------------------------ one batched step
     def _cqt_prepare(self, L, lowest_midi, nbins, bpt, s, t, n_cols):
@@ -158,7 +162,7 @@ class NoteStepBatch:
         pitch = np.asarray(pitch, dtype=np.int64).reshape(W)
         if not self.fresh:
             # util_audio.py:88-106: wf is rebuilt from the subtracted magnitude and the original phase
-            self.wav = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb)
+            self._rebuild_wav()
         s, t = self._frames(onset), self._frames(onset + duration)
         out = {}
         L = int(self.wav.shape[1])
@@ -241,6 +245,46 @@ class NoteStepBatch:
             self.subtract(guess_wav, off, guess_lens, offset_dev=d["off"])
         return out
 
+    def _rebuild_wav(self):
+        """`wf` after a subtraction (util_audio.py:88-106: istft of magnitude x phase).  The first rebuild inverts every
+        frame (the window's original audio is not an iSTFT).  From then on `wav` IS the iSTFT of the previous
+        magnitudes and a subtraction changes frames [o, o + tg) only: with n_fft = 4 hops a sample depends on 4
+        frames, so the samples that change are [(o - 2) hop, (o + tg + 2) hop), computed from frames
+        [o - 4, o + tg + 4): gather those rows, invert them (K4 on ~1/4 of the frames) and patch that sample range.
+        Same frames, same accumulation order per sample: the patched waveform equals the full rebuild."""
+        d = self._dirty
+        m = self.N // (2 * self.hl)                      # frames on either side that reach a sample
+        if d is None or not self._wav_synced or not self.incremental_istft or d["F"] >= self.T:
+            self.wav = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb)
+        elif d["any"]:
+            F, hop = d["F"], self.hl
+            rows = d["fa"][:, None] + torch.arange(F, device=self.dev)               # [W, F]
+            w_ix = torch.arange(self.W, device=self.dev)[:, None]
+            y = ops.istft_batch(self.stft, mag=self.mag[w_ix, rows], phase=self.ph[w_ix, rows], n_bins=self.nb)   # [W, (F-1) hop]
+            idx = d["fa"][:, None] * hop + torch.arange(y.shape[1], device=self.dev)   # global sample of every sub sample
+            keep = (idx >= d["lo"][:, None]) & (idx < d["hi"][:, None])
+            self.wav.scatter_(1, idx, torch.where(keep, y, self.wav.gather(1, idx)))
+        self._dirty = None
+        self._wav_synced = True
+
+    def _mark_dirty(self, offset_frames, guess_frames):
+        """Host side of the incremental rebuild: per window the frame range the subtraction touched."""
+        if not self._wav_synced or self._dirty is not None:
+            # `wav` is the original audio, or a second subtraction arrives before the rebuild: invert everything next time
+            self._dirty, self._wav_synced = None, False
+            return
+        m = self.N // (2 * self.hl)
+        T, hop = self.T, self.hl
+        o = np.clip(np.asarray(offset_frames, dtype=np.int64), 0, T)
+        tg = np.minimum(np.asarray(guess_frames, dtype=np.int64), T - o)
+        F = int(min(T, int(tg.max(initial=0)) + 4 * m))
+        fa = np.clip(o - 2 * m, 0, T - F)
+        L = hop * (T - 1)
+        lo = np.clip((o - m) * hop, 0, L)
+        hi = np.where(tg > 0, np.clip((o + tg + m) * hop, 0, L), lo)
+        dev = self._upload({"fa": fa, "lo": lo, "hi": hi})
+        self._dirty = {"F": F, "any": bool((tg > 0).any()), "fa": dev["fa"].long(), "lo": dev["lo"].long(), "hi": dev["hi"].long()}
+
     def subtract(self, guess_wav, offset_frames, guess_lens=None, offset_dev=None):
         """training.py:426 + :449: STFT of the rendered notes (K1), then align / scale / subtract / ReLU (K3)."""
         g = ops.stft_batch(guess_wav, self.stft, lens=guess_lens, want_max=True)
@@ -251,6 +295,8 @@ class NoteStepBatch:
                                      device=self.dev).reshape(self.W, 1)
         if int(np.max(offset_frames)) > self.T:
             raise ValueError("negative dimensions are not allowed")      # numpy's error for zeros((bins, T - off - ...))
+        self._mark_dirty(offset_frames, [self.stft.num_frames(int(n)) for n in np.asarray(guess_lens)] if guess_lens is not None
+                         else np.full(self.W, self.stft.num_frames(int(guess_wav.shape[1]))))
         _, self.ref = ops.subtract_db_batch(
             self.mag, gm.unsqueeze(1),
             (offset_dev if offset_dev is not None else torch.as_tensor(offset_frames, dtype=torch.int32)).reshape(self.W, 1), self.nb,

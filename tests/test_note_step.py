@@ -98,3 +98,46 @@ def test_batched_note_step_matches_reference_class_golden(full_cqt):
     # after a subtraction the next step's waveform is the iSTFT of mag * ph: hop * (T - 1) samples
     batch.step([0.5] * W, [0.5] * W, [60] * W, torch.zeros((W, 8192), device="cuda"), subtract=False)
     assert batch.wav.shape[1] == 1024 * 257 == int(gold["w0_n1_wf_len_after"])
+
+
+@pytest.mark.gpu
+def test_incremental_wave_rebuild_equals_full_istft():
+    """After the first subtraction `wav` is an iSTFT, and a subtraction only changes frames [o, o + tg): the note step
+    then re-inverts just the rows around them and patches the sample range they reach (util_audio.py:88-106 rebuilds
+    everything).  Four steps with ragged guesses, onsets at the window start, in the middle and hanging over the end:
+    the patched waveform and every feature must equal the full rebuild's."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops, synth
+    from amt_saga_b200.note_step import NoteStepBatch
+    dev = torch.device("cuda")
+    W, Lw = 6, 264168
+    wav = synth.piano_batch(range(W), Lw, 44100, seed_base=4000, device=dev)
+    plan = ops.get_stft_plan(4096, 1024, True)
+    r = ops.stft_batch(wav, plan, want_phase=True)
+    guess = synth.piano_batch(range(W), 54277, 44100, n_notes=1, seed_base=7000, device=dev)
+    lens = np.array([54277, 30000, 54277, 8192, 41000, 54277])
+    onsets = [np.array([0.0, 0.5, 2.0, 3.1, 5.6, 5.99]), np.array([5.9, 0.0, 1.0, 4.0, 2.5, 0.2]),
+              np.array([1.5, 5.5, 0.01, 2.2, 0.0, 4.9]), np.array([3.0, 3.0, 3.0, 3.0, 3.0, 3.0])]
+    outs = {}
+    for inc in (True, False):
+        b = NoteStepBatch(W)
+        b.incremental_istft = inc
+        b.load(r["mag_storage"][:, :258].clone(), r["phase_storage"][:, :258].clone(), wav, r["clip_max"], np.ones((W, 3)))
+        seq = []
+        for k, on in enumerate(onsets):
+            o = b.step(on, np.full(W, 0.6), np.array([50, 60, 45, 72, 50, 60]) + k, guess, guess_lens=lens)
+            seq.append((b.wav.clone(), {n: v.clone() for n, v in o.items() if isinstance(v, torch.Tensor)}))
+        outs[inc] = seq
+        used_patch = b._wav_synced
+    assert used_patch
+    for k in range(len(onsets)):
+        wa, fa = outs[True][k]
+        wb, fb = outs[False][k]
+        assert wa.shape == wb.shape
+        assert float((wa - wb).abs().max()) <= 1e-6 * float(wb.abs().max()), k
+        for n in fb:
+            assert torch.allclose(fa[n], fb[n], rtol=0, atol=1e-6 * max(float(fb[n].abs().max()), 1e-30)), (k, n)
+    assert torch.equal(outs[True][1][0], outs[False][1][0])        # step 2 inverts everything in both modes
