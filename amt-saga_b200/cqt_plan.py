@@ -186,6 +186,12 @@ class CqtPlan:
             return 0
         return min(1 + self.level_len(n, o["level"]) // o["hop"] for o in self.octaves)
 
+    def geometry(self):
+        """What the decimation cascade and the level buffers depend on (not the bank): plans of equal geometry can share
+        one cascade (saga_cqt_frames_shared_exec)."""
+        return (self.sr, self.hop, self.early_factor, self.max_level,
+                tuple((o["level"], o["hop"], o["n_fft"], o["n_filters"]) for o in self.octaves))
+
     def check_length(self, n):
         """librosa raises when the signal is too short to decimate."""
         if n < self.early_factor or self.level_len(n, max(self.max_level - 1, 0)) < 2 and self.max_level > 0:

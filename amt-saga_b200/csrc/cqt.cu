@@ -931,12 +931,16 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
                          const int64_t* clip_lens, int n_clips, int64_t max_len, float* C_mag_out,
                          void* C_cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
                          void* workspace, int64_t workspace_bytes, int impl, void* stream,
-                         const int32_t* frame_first, int frame_count) {
+                         const int32_t* frame_first, int frame_count, int ws_clips = 0, int clip_first = 0) {
   if (!p || !wav || !clip_offsets || !C_mag_out || !workspace)
     return set_error(SAGA_ERR_INVALID, "cqt_exec: null argument");
   if (frame_pitch < p->n_bins) return set_error(SAGA_ERR_INVALID, "cqt_exec: frame_pitch < n_bins");
   if (n_clips <= 0 || max_len <= 0) return SAGA_OK;
-  if (workspace_bytes < saga_cqt_workspace_bytes(p, n_clips, max_len))
+  // ws_clips > 0: the workspace was laid out (and its cascade run) for a batch of ws_clips clips, of which this call
+  // contracts clips [clip_first, clip_first + n_clips) -- saga_cqt_frames_shared_exec
+  const int nc_ws = ws_clips > 0 ? ws_clips : n_clips;
+  if (clip_first < 0 || clip_first + n_clips > nc_ws) return set_error(SAGA_ERR_INVALID, "cqt_exec: clip range outside the workspace batch");
+  if (workspace_bytes < saga_cqt_workspace_bytes(p, nc_ws, max_len))
     return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace must be 256-byte aligned");
@@ -948,7 +952,7 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
   // ---- carve the workspace -------------------------------------------------------
   char* ws = (char*)workspace;
   int32_t* clip_frames = (int32_t*)ws;
-  ws += ws_header_bytes(n_clips);
+  ws += ws_header_bytes(nc_ws);
   if (p->max_level + 1 > PAD_MAX_LEVELS) return set_error(SAGA_ERR_UNSUPPORTED, "cqt_exec: too many levels");
   std::vector<float*> lvl(p->max_level + 1, nullptr);   // padded buffers; sample 0 of a clip at + pad[l]
   std::vector<int64_t> pitch(p->max_level + 1, 0);
@@ -956,15 +960,22 @@ static int cqt_exec_impl(const saga_cqt_plan* p, const float* wav, const int64_t
   for (int l = 0; l <= p->max_level; ++l) {
     pitch[l] = cqt_level_pitch(p, l, max_len);
     pad[l] = cqt_level_pad(p, l);
-    lvl[l] = (float*)ws;
-    ws += (int64_t)n_clips * pitch[l] * 4;
+    lvl[l] = (float*)ws + (int64_t)clip_first * pitch[l];
+    ws += (int64_t)nc_ws * pitch[l] * 4;
+  }
+  if (clip_first > 0 || ws_clips > 0) {
+    if (do_cascade && (clip_first != 0 || n_clips != nc_ws))
+      return set_error(SAGA_ERR_INVALID, "cqt_exec: the cascade runs on the whole workspace batch");
+    clip_frames += clip_first;
   }
   const bool raw0 = (p->early_factor == 1);   // level 0 = the caller's wav (copied into lvl[0] by the pad pass)
 
-  cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, max_len, n_clips, p->early_factor,
-                                                           p->d_levels, p->d_hops, (int)p->oct.size(),
-                                                           clip_frames);
-  SAGA_LAUNCH_CHECK();
+  if (do_cascade) {      // (a contraction-only call finds the frame counts of the cascade call in the workspace header)
+    cqt_frames_kernel<<<(n_clips + 127) / 128, 128, 0, st>>>(clip_lens, max_len, n_clips, p->early_factor,
+                                                             p->d_levels, p->d_hops, (int)p->oct.size(),
+                                                             clip_frames);
+    SAGA_LAUNCH_CHECK();
+  }
 
   // ---- decimation cascade ----------------------------------------------------------
   const int tile_out = DEC_THREADS * DEC_PER_THREAD;
@@ -1201,6 +1212,26 @@ extern "C" int saga_cqt_exec(const saga_cqt_plan* p, const float* wav, const int
                              void* workspace, int64_t workspace_bytes, int impl, void* stream) {
   return cqt_exec_impl(p, wav, clip_offsets, clip_lens, n_clips, max_len, C_mag_out, C_cplx_out, frame_pitch,
                        out_clip_stride, workspace, workspace_bytes, impl, stream, nullptr, 0);
+}
+
+extern "C" int saga_cqt_frames_shared_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
+                                           const int64_t* clip_lens, int ws_clips, int64_t max_len, int phase,
+                                           int clip_first, int n_clips, const int32_t* frame_first, int frame_count,
+                                           float* C_mag_out, int64_t frame_pitch, int64_t out_clip_stride,
+                                           void* workspace, int64_t workspace_bytes, void* stream) {
+  if (phase == 1) {           // cascade + reflect margins of the whole batch
+    static float dummy;       // (no output in this phase)
+    return cqt_exec_impl(p, wav, clip_offsets, clip_lens, ws_clips, max_len, C_mag_out ? C_mag_out : &dummy, nullptr,
+                         p ? p->n_bins : 0, 0, workspace, workspace_bytes, 1 | SAGA_CQT_SKIP_CONTRACT, stream, nullptr, 0,
+                         ws_clips, 0);
+  }
+  if (phase != 2) return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_exec: phase must be 1 (cascade) or 2 (contraction)");
+  if (!frame_first) return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_exec: null frame_first");
+  if (frame_count < 1 || frame_count > FW_MAXF)
+    return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_exec: frame_count must be in 1..%d", FW_MAXF);
+  return cqt_exec_impl(p, wav, clip_offsets, clip_lens, n_clips, max_len, C_mag_out, nullptr, frame_pitch,
+                       out_clip_stride, workspace, workspace_bytes, 1 | SAGA_CQT_SKIP_CASCADE, stream, frame_first,
+                       frame_count, ws_clips, clip_first);
 }
 
 extern "C" int saga_cqt_frames_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,

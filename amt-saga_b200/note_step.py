@@ -51,6 +51,7 @@ class NoteStepBatch:
         self._dirty = None         # frames changed by the last subtract, while `wav` is an iSTFT of the previous magnitudes
         self._wav_synced = False   # `wav` == iSTFT(magnitudes before the last subtract) (the original audio is not)
         self.incremental_istft = True   # False: every rebuild of `wav` inverts all T frames (A/B twin)
+        self.share_cascade = True       # False: every pitch group runs its own decimation cascade (A/B twin)
         self._tone_fft = None
         self.full_cqt = False      # True: every slice_C transforms all 258 columns like the reference (A/B twin)
 
@@ -221,21 +222,44 @@ class NoteStepBatch:
         for nbins, bpt, shift in ((self.instrument_bands, self.inst_bpt * 4, 0), (self.bins_velocity, 2, -10)):
             P = ops.frame_pitch(nbins)
             buf = torch.zeros((W, Tc if full else nf, P), device=self.dev, dtype=torch.float32)
-            a = 0
+            # pitch groups [a, b) of the sorted windows with their plans
+            groups, a = [], 0
             while a < W:
                 b = a + int(np.searchsorted(p_s[a:], p_s[a], side="right"))
                 try:
                     plan = ops.get_cqt_plan(self.sr, self.hl, midi_to_hz(int(p_s[a]) + shift), int(nbins),
                                             int(12 * bpt), 2, device=self.dev)
                     plan.check_length(L)
-                    if full:
-                        buf[a:b] = ops.cqt_batch(wav_s[a:b], plan)["mag_storage"]
-                    else:
-                        ops.cqt_frames_batch(wav_s[a:b], plan, d["first_s"][a:b], nf, out=buf[a:b])
+                    groups.append((a, b, plan))
                 except ParameterError:      # librosa: "Filter pass-band lies beyond Nyquist" -> the loop skips the file
                     valid[order[a:b]] = False
                     buf[a:b] = float("nan")
+                    groups.append((a, b, None))
                 a = b
+            i = 0
+            while i < len(groups):
+                a, b, plan = groups[i]
+                if plan is None:
+                    i += 1
+                    continue
+                if full:
+                    buf[a:b] = ops.cqt_batch(wav_s[a:b], plan)["mag_storage"]
+                    i += 1
+                    continue
+                # consecutive pitches of equal geometry (early factor, levels, kernel length) decimate the audio the same
+                # way: ONE cascade for the whole run, then one contraction per pitch with its own bank
+                j = i
+                while self.share_cascade and j + 1 < len(groups) and groups[j + 1][2] is not None and \
+                        groups[j + 1][2].geometry() == plan.geometry():
+                    j += 1
+                if j == i:
+                    ops.cqt_frames_batch(wav_s[a:b], plan, d["first_s"][a:b], nf, out=buf[a:b])
+                else:
+                    A, B = a, groups[j][1]
+                    token = ops.cqt_cascade_shared(wav_s[A:B], plan)
+                    for (ga, gb, gp) in groups[i:j + 1]:
+                        ops.cqt_frames_from_cascade(token, gp, ga - A, gb - ga, d["first_s"][ga:gb], nf, buf[ga:gb])
+                i = j + 1
             g = ops.gather_frames_batch(buf, nbins, d["rel_s"], inv_ref_s)
             res.append(g.index_select(0, d["inv_order"]))
         foc, vel = res

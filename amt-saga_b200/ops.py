@@ -331,6 +331,43 @@ def cqt_frames_batch(wav, plan, frame_first, frame_count=8, lens=None, out=None)
     return out
 
 
+def cqt_cascade_shared(wav, plan, lens=None):
+    """Phase 1 of saga_cqt_frames_shared_exec: decimation cascade + reflect margins of the whole batch, once, for every
+    plan of `plan.geometry()`.  Returns the token `cqt_frames_from_cascade` takes; the (per-device, shared) workspace
+    must not be used by another CQT call in between."""
+    wav, offs, lens_dev, max_len = _clip_table(wav, lens)
+    n_clips = wav.shape[0]
+    lib = _lib.lib()
+    nbytes = lib.saga_cqt_workspace_bytes(plan.handle, n_clips, max_len)
+    ws = _workspace(nbytes, wav.device)
+    lens_ptr = _ptr(lens_dev) if lens is not None else None
+    with _on(wav, plan):
+        _lib.check(lib.saga_cqt_frames_shared_exec(plan.handle, _ptr(wav), _ptr(offs), lens_ptr, n_clips, max_len, 1, 0, n_clips,
+                                                   None, 0, None, 0, 0, _ptr(ws), ws.numel(), _stream(wav)), ParameterError)
+    return dict(wav=wav, offs=offs, lens_ptr=lens_ptr, n_clips=n_clips, max_len=max_len, ws=ws, geometry=plan.geometry(),
+                keep=lens_dev)
+
+
+def cqt_frames_from_cascade(token, plan, clip_first, n_clips, frame_first, frame_count, out):
+    """Phase 2: `frame_count` columns from frame_first[c] for clips [clip_first, clip_first + n_clips) of the cascade
+    batch, with THIS plan's bank.  frame_first: int32 device tensor [n_clips]; out: contiguous [n_clips, frame_count, P]."""
+    if plan.geometry() != token["geometry"]:
+        raise ValueError("plan geometry differs from the cascade's")
+    P = frame_pitch(plan.n_bins)
+    if out.shape != (n_clips, int(frame_count), P) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out must be contiguous float32 [clips, frame_count, %d]" % P)
+    first = frame_first.to(device=out.device, dtype=torch.int32).contiguous()
+    if first.shape != (n_clips,):
+        raise ValueError("frame_first must be [clips]")
+    wav = token["wav"]
+    with _on(wav, plan):
+        _lib.check(_lib.lib().saga_cqt_frames_shared_exec(
+            plan.handle, _ptr(wav), _ptr(token["offs"]), token["lens_ptr"], token["n_clips"], token["max_len"], 2,
+            int(clip_first), int(n_clips), _ptr(first), int(frame_count), _ptr(out), P, int(frame_count) * P,
+            _ptr(token["ws"]), token["ws"].numel(), _stream(wav)), ParameterError)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # K3
 # ---------------------------------------------------------------------------

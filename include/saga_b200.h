@@ -239,6 +239,21 @@ int saga_cqt_frames_exec(const saga_cqt_plan* plan, const float* wav, const int6
                          int64_t frame_pitch, int64_t out_clip_stride, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
+/* The same in two phases, for several plans that share ONE decimation cascade: the two note-relative transforms of a
+ * per-note iteration (training.py:366-388) have a kernel bank per pitch, but pitches of equal geometry (early
+ * factor, levels, kernel length) decimate the audio identically.
+ *   phase 1: cascade + reflect margins for a batch of `ws_clips` clips (any plan of that geometry); frame_first /
+ *            C_mag_out unused.
+ *   phase 2: contraction of `frame_count` columns for clips [clip_first, clip_first + n_clips) of that batch with
+ *            THIS plan's bank; frame_first / C_mag_out point at the first of those clips.
+ * The caller keeps the workspace untouched between the phases and passes the same wav / clip_offsets / clip_lens /
+ * max_len / workspace to both.  Plans of different geometry in one batch are the caller's error (not detectable). */
+int saga_cqt_frames_shared_exec(const saga_cqt_plan* plan, const float* wav, const int64_t* clip_offsets,
+                                const int64_t* clip_lens, int ws_clips, int64_t max_len, int phase,
+                                int clip_first, int n_clips, const int32_t* frame_first, int frame_count,
+                                float* C_mag_out, int64_t frame_pitch, int64_t out_clip_stride,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * K5  feature gather for the classifiers (training.py:333-388)
  * ---------------------------------------------------------------------- */

@@ -141,3 +141,43 @@ def test_incremental_wave_rebuild_equals_full_istft():
         for n in fb:
             assert torch.allclose(fa[n], fb[n], rtol=0, atol=1e-6 * max(float(fb[n].abs().max()), 1e-30)), (k, n)
     assert torch.equal(outs[True][1][0], outs[False][1][0])        # step 2 inverts everything in both modes
+
+
+@pytest.mark.gpu
+def test_shared_cascade_across_pitches_is_bit_identical():
+    """Pitches of equal CQT geometry share one decimation cascade in the batched step (saga_cqt_frames_shared_exec:
+    cascade once for the run of windows, one contraction per pitch on its clip range); with `share_cascade = False`
+    every pitch group runs the whole transform on its own.  Same kernels on the same data: the two must be equal
+    bit for bit, for 40 windows over 23 pitches in every geometry class the note-relative transforms meet."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops, synth
+    from amt_saga_b200.note_step import NoteStepBatch
+    dev = torch.device("cuda")
+    W, Lw = 40, 264168
+    wav = synth.piano_batch(range(W), Lw, 44100, seed_base=8000, device=dev)
+    plan = ops.get_stft_plan(4096, 1024, True)
+    r = ops.stft_batch(wav, plan, want_phase=True)
+    guess = synth.piano_batch(range(W), 54277, 44100, n_notes=1, seed_base=9000, device=dev)
+    rng = np.random.default_rng(5)
+    pitch = np.concatenate([np.arange(30, 96, 3), rng.integers(30, 96, W - 22)])
+    onset = rng.uniform(0, 5.5, W)
+    geoms = set()
+    outs = {}
+    for share in (True, False):
+        b = NoteStepBatch(W)
+        b.share_cascade = share
+        b.load(r["mag_storage"][:, :258].clone(), r["phase_storage"][:, :258].clone(), wav, r["clip_max"], np.ones((W, 3)))
+        o1 = b.step(onset, np.full(W, 0.5), pitch, guess)
+        o2 = b.step(onset[::-1].copy(), np.full(W, 0.7), pitch[::-1].copy(), guess)
+        outs[share] = (o1, o2)
+    for p in np.unique(pitch):
+        geoms.add(ops.get_cqt_plan(44100, 1024, 440.0 * 2.0 ** ((int(p) - 69) / 12.0), 348, 192, 2).geometry())
+    assert 1 < len(geoms) < len(np.unique(pitch))        # several pitches per geometry, several geometries
+    for k in range(2):
+        assert (outs[True][k]["valid"] == outs[False][k]["valid"]).all()
+        for n in ("C_sw_inst_foc", "C_velocity", "C_sw_pitch"):
+            a_, b_ = outs[True][k][n], outs[False][k][n]
+            assert torch.equal(torch.nan_to_num(a_), torch.nan_to_num(b_)), (k, n)
