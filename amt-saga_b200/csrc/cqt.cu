@@ -1234,6 +1234,82 @@ extern "C" int saga_cqt_frames_shared_exec(const saga_cqt_plan* p, const float* 
                        frame_count, ws_clips, clip_first);
 }
 
+extern "C" int saga_cqt_frames_shared_multi_exec(const saga_cqt_plan* const* plans, int n_plans, const int32_t* clip_first,
+                                                 const int32_t* clip_count, const float* wav, const int64_t* clip_offsets,
+                                                 const int64_t* clip_lens, int ws_clips, int64_t max_len,
+                                                 const int32_t* frame_first, int frame_count, float* C_mag_out,
+                                                 int64_t frame_pitch, int64_t out_clip_stride, void* workspace,
+                                                 int64_t workspace_bytes, void* stream) {
+  if (!plans || n_plans < 1 || !clip_first || !clip_count || !frame_first || !C_mag_out || !workspace)
+    return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: null argument");
+  if (frame_count < 1 || frame_count > FW_MAXF)
+    return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: frame_count must be in 1..%d", FW_MAXF);
+  const saga_cqt_plan* p = plans[0];
+  const bool stream_on = cqt_stream_supported(p) && !(SAGA_OPT("SAGA_CQT_STREAM") && atoi(SAGA_OPT("SAGA_CQT_STREAM")) == 0);
+  bool same = stream_on;
+  for (int i = 0; i < n_plans && same; ++i) same = plans[i] && cqt_stream_supported(plans[i]);
+  if (!same) {     // plan by plan (fp32 kernels, or a plan outside the tensor path's constraints)
+    for (int i = 0; i < n_plans; ++i) {
+      const int rc = saga_cqt_frames_shared_exec(plans[i], wav, clip_offsets, clip_lens, ws_clips, max_len, 2, clip_first[i],
+                                                 clip_count[i], frame_first + clip_first[i], frame_count,
+                                                 C_mag_out + (int64_t)clip_first[i] * out_clip_stride, frame_pitch,
+                                                 out_clip_stride, workspace, workspace_bytes, stream);
+      if (rc != SAGA_OK) return rc;
+    }
+    return SAGA_OK;
+  }
+  if (frame_pitch < p->n_bins) return set_error(SAGA_ERR_INVALID, "cqt_exec: frame_pitch < n_bins");
+  if (ws_clips <= 0 || max_len <= 0) return SAGA_OK;
+  if (workspace_bytes < saga_cqt_workspace_bytes(p, ws_clips, max_len))
+    return set_error(SAGA_ERR_INVALID, "cqt_exec: workspace too small");
+  if ((int)p->oct.size() > FW_MAX_OCT || p->max_level + 1 > PAD_MAX_LEVELS)
+    return set_error(SAGA_ERR_UNSUPPORTED, "cqt_frames_shared_multi_exec: too many octaves / levels");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the workspace layout of cqt_exec_impl for a batch of ws_clips clips
+  char* ws = (char*)workspace;
+  int32_t* clip_frames = (int32_t*)ws;
+  ws += ws_header_bytes(ws_clips);
+  std::vector<float*> lvl(p->max_level + 1, nullptr);
+  std::vector<int64_t> pitch(p->max_level + 1, 0);
+  std::vector<int> pad(p->max_level + 1, 0);
+  for (int l = 0; l <= p->max_level; ++l) {
+    pitch[l] = cqt_level_pitch(p, l, max_len);
+    pad[l] = cqt_level_pad(p, l);
+    lvl[l] = (float*)ws;
+    ws += (int64_t)ws_clips * pitch[l] * 4;
+  }
+  CqtLevels lv;
+  lv.wav = wav; lv.clip_offsets = clip_offsets; lv.clip_lens = clip_lens; lv.max_len = max_len;
+  lv.lvl = lvl.data(); lv.pitch = pitch.data(); lv.pad = pad.data(); lv.clip_frames = clip_frames;
+  int max_filt = 0;
+  FrameWinArgs fa;
+  for (size_t i = 0; i < p->oct.size(); ++i) {
+    const auto& o = p->oct[i];
+    fa.sig[i] = nullptr; fa.sig_stride[i] = 0; fa.bank[i] = nullptr;
+    fa.n_fft[i] = o.n_fft; fa.n_filt[i] = o.n_filters; fa.hop[i] = o.hop; fa.first_bin[i] = o.first_bin;
+    max_filt = std::max(max_filt, o.n_filters);
+  }
+  fa.n_bins = p->n_bins; fa.frame_count = frame_count;
+  fa.frame_first = frame_first; fa.clip_frames = clip_frames;
+  fa.mag_out = C_mag_out; fa.frame_pitch = frame_pitch; fa.out_clip_stride = out_clip_stride;
+  fa.n_clips = ws_clips; fa.n_oct = (int)p->oct.size();
+  fa.pstride = (max_filt + 31) & ~31;
+  fa.partial = (float*)ws;
+  int max_slices = 1;
+  while (2 * max_slices <= FW_MAX_KS && (int64_t)2 * max_slices * ws_clips * fa.n_oct <= 2 * FW_TARGET_CTAS) max_slices *= 2;
+  int ks = 1;
+  std::vector<int> c0(clip_first, clip_first + n_plans), cn(clip_count, clip_count + n_plans);
+  const int rc = cqt_stream_exec_multi(plans, n_plans, c0.data(), cn.data(), lv, ws_clips, saga_cqt_num_frames(p, max_len),
+                                       frame_first, frame_count, C_mag_out, nullptr, frame_pitch, out_clip_stride, st,
+                                       max_slices, fa.partial, fa.pstride, &ks);
+  if (rc != SAGA_OK || ks == 1) return rc;
+  fa.ks = ks;
+  dim3 g2((unsigned)((max_filt + 255) / 256), (unsigned)p->oct.size(), ws_clips);
+  cqt_frame_window_finish_kernel<<<g2, 256, 0, st>>>(fa);
+  SAGA_LAUNCH_CHECK();
+  return SAGA_OK;
+}
+
 extern "C" int saga_cqt_frames_exec(const saga_cqt_plan* p, const float* wav, const int64_t* clip_offsets,
                                     const int64_t* clip_lens, int n_clips, int64_t max_len,
                                     const int32_t* frame_first, int frame_count, float* C_mag_out,

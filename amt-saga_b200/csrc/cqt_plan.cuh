@@ -65,5 +65,11 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
                     const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
                     int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t st, int max_slices = 1,
                     float* partial = nullptr, int pstride = 0, int* slices_out = nullptr);
+// several plans of equal geometry, plan i on clips [clip0[i], clip0[i] + nclips[i]) of the batch `lv` describes
+int cqt_stream_exec_multi(const saga_cqt_plan* const* plans, int n_plans, const int* clip0, const int* nclips,
+                          const CqtLevels& lv, int n_clips, int64_t T_max, const int32_t* frame_first, int frame_count,
+                          float* mag_out, float2* cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                          cudaStream_t st, int max_slices = 1, float* partial = nullptr, int pstride = 0,
+                          int* slices_out = nullptr);
 
 }  // namespace saga

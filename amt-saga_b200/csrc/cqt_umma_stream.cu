@@ -67,6 +67,10 @@ struct UsGroup {
   int hop, n_fft, ncol, first_bin;   // first_bin of THIS column group
   int n_main, n_lo;
   int oct, filt0;         // octave index and first filter of the group within it (split-K partial sums)
+  // rows of this group: a launch may carry the groups of SEVERAL plans of equal geometry (one kernel bank per pitch),
+  // each contracting its own clips [clip0, clip0 + rows / rows_per_clip) of the batch
+  int clip0;
+  uint32_t n_rows, tiles, item0;   // rows, 128-row tiles, and first work item of the group (items: ks * tiles)
 };
 
 struct UsArgs {
@@ -76,7 +80,7 @@ struct UsArgs {
   int frame_count;              // frame window: rows j < frame_count are stored
   const int32_t* frame_first;   // NULL = whole transform
   const int32_t* clip_frames;
-  uint32_t m_tiles, total_items, total_rows;
+  uint32_t total_items;
   float* mag_out;
   float2* cplx_out;
   int64_t frame_pitch, out_clip_stride;
@@ -106,14 +110,29 @@ struct UsRow {
   int clip, j, t;
   bool store, live;
 };
-__device__ __forceinline__ UsRow us_row(const UsArgs& a, uint32_t R) {
+// work item -> (group, K slice, tile): groups are laid out one after the other, ks * tiles items each
+struct UsItem {
+  uint32_t g, slice, tile;
+};
+__device__ __forceinline__ UsItem us_item(const UsArgs& a, uint32_t item) {
+  UsItem it;
+  uint32_t g = 0;
+  while (g + 1 < (uint32_t)a.n_groups && item >= a.grp[g + 1].item0) ++g;
+  const uint32_t local = item - a.grp[g].item0, tiles = a.grp[g].tiles;
+  it.g = g;
+  it.slice = local / tiles;
+  it.tile = local - it.slice * tiles;
+  return it;
+}
+__device__ __forceinline__ UsRow us_row(const UsArgs& a, const UsGroup& gr, uint32_t R) {
   UsRow r;
-  if (R >= a.total_rows) {
-    r.clip = a.n_clips - 1; r.j = 0; r.t = 0; r.store = false; r.live = false;
+  if (R >= gr.n_rows) {
+    r.clip = gr.clip0; r.j = 0; r.t = 0; r.store = false; r.live = false;
     return r;
   }
-  r.clip = (int)(R / (uint32_t)a.rows_per_clip);
-  r.j = (int)(R - (uint32_t)r.clip * (uint32_t)a.rows_per_clip);
+  const int c = (int)(R / (uint32_t)a.rows_per_clip);
+  r.clip = gr.clip0 + c;
+  r.j = (int)(R - (uint32_t)c * (uint32_t)a.rows_per_clip);
   const int T = a.clip_frames[r.clip];
   if (a.frame_first) {
     r.t = a.frame_first[r.clip] + r.j;
@@ -319,11 +338,11 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     const int ew = warp;
     uint32_t it_acc = 0;
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
-      const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
-      const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
+      const UsItem wi = us_item(a, item);
+      const uint32_t g = wi.g, slice = wi.slice, tile = wi.tile;
       const UsGroup& gr = a.grp[g];
       const uint32_t acc = a.bufs == 2 ? (it_acc & 1) : 0, acc_ph = a.bufs == 2 ? ((it_acc >> 1) & 1) : (it_acc & 1);
-      const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
+      const UsRow r = us_row(a, gr, tile * US_TILE_M + (uint32_t)(ew * 32 + lane));
       us_wait(&tfull[acc], acc_ph, lane, a.error_flag, 500);
       tc_fence_after();
       const int64_t row = (int64_t)r.clip * a.out_clip_stride + (int64_t)(a.frame_first ? r.j : r.t) * a.frame_pitch;
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
 #define US_PROF(var) do { if (prof_on) { const long long n_ = clock64(); var += n_ - pt; pt = n_; } } while (0)
 #define US_TL(kk, slot) do { if ((a.debug & 128) && blockIdx.x == 0 && lane == 0 && (kk) < 96u) a.prof[2048 + (kk) * 8 + (slot)] = clock64(); } while (0)
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G, ++it_acc) {
-      const uint32_t g = item / a.m_tiles / (uint32_t)a.ks;
+      const uint32_t g = us_item(a, item).g;
       const UsGroup& gr = a.grp[g];
       // (k runs over THIS issuer's stages: iw, iw + NI, ... across items; every item has a multiple of 4 stages)
       // instruction descriptors: D = f32, A = B = tf32, K-major both, M = 128
@@ -491,8 +510,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     if (lane == 0) {
       uint32_t k = 0;
       for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-        const uint32_t gs = item / a.m_tiles;
-        const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
+        const UsItem wi = us_item(a, item);
+        const uint32_t g = wi.g, slice = wi.slice;
         const UsGroup& gr = a.grp[g];
         const uint32_t bytes = (uint32_t)gr.n_main * (US_PLANES * 16u);
         const int n_st = gr.n_fft / US_KC / a.ks;
@@ -529,11 +548,11 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       uint32_t k0t = 0;
       for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-        const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
-        const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
+        const UsItem wi = us_item(a, item);
+        const uint32_t g = wi.g, slice = wi.slice, tile = wi.tile;
         const UsGroup& gr = a.grp[g];
         const int n_st = gr.n_fft / US_KC / a.ks;
-        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)row);
+        const UsRow r = us_row(a, gr, tile * US_TILE_M + (uint32_t)row);
         const int T = a.clip_frames[r.clip];
         const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
         const float* own = gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + (int)slice * n_st * US_KC + k_off;
@@ -591,14 +610,14 @@ __global__ void __launch_bounds__(US_THREADS, 1) cqt_umma_stream_kernel(const __
     const uint32_t dst_off = (uint32_t)plane * US_PLANE_BYTES + (uint32_t)row0 * 16u;
     uint32_t k0 = 0;                                   // ring index of the item's first stage
     for (uint32_t item = blockIdx.x; item < a.total_items; item += G) {
-      const uint32_t gs = item / a.m_tiles, tile = item - gs * a.m_tiles;
-      const uint32_t g = gs / (uint32_t)a.ks, slice = gs - g * (uint32_t)a.ks;
+      const UsItem wi = us_item(a, item);
+      const uint32_t g = wi.g, slice = wi.slice, tile = wi.tile;
       const UsGroup& gr = a.grp[g];
       const int n_st = gr.n_fft / US_KC / a.ks;
       const float4* src[US_MAX_RPT];
 #pragma unroll
       for (int i = 0; i < US_MAX_RPT; ++i) {
-        const UsRow r = us_row(a, tile * US_TILE_M + (uint32_t)(row0 + rstep * (i < rpt ? i : 0)));
+        const UsRow r = us_row(a, gr, tile * US_TILE_M + (uint32_t)(row0 + rstep * (i < rpt ? i : 0)));
         const int T = a.clip_frames[r.clip];
         const int tc = max(min(r.t, T - 1), 0);      // frames outside the clip re-read an existing one (never stored)
         src[i] = reinterpret_cast<const float4*>(gr.sig + (int64_t)r.clip * gr.sig_stride + (int64_t)tc * gr.hop + 4 * plane +
@@ -810,37 +829,101 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
                     const int32_t* frame_first, int frame_count, float* mag_out, float2* cplx_out,
                     int64_t frame_pitch, int64_t out_clip_stride, cudaStream_t stream, int max_slices,
                     float* partial, int pstride, int* slices_out) {
+  const int zero = 0;
+  return cqt_stream_exec_multi(&p, 1, &zero, &n_clips, lv, n_clips, T_max, frame_first, frame_count, mag_out, cplx_out,
+                               frame_pitch, out_clip_stride, stream, max_slices, partial, pstride, slices_out);
+}
+
+// Several plans of EQUAL geometry (one kernel bank per pitch: the note-relative transforms of a per-note iteration) in
+// as few launches as the 64-group argument block allows: plan i contracts clips [clip0[i], clip0[i] + nclips[i]) of the
+// batch whose cascade `lv` describes.  All launches use the same K split (the caller's finish kernel runs once).
+int cqt_stream_exec_multi(const saga_cqt_plan* const* plans, int n_plans, const int* clip0, const int* nclips,
+                          const CqtLevels& lv, int n_clips, int64_t T_max, const int32_t* frame_first, int frame_count,
+                          float* mag_out, float2* cplx_out, int64_t frame_pitch, int64_t out_clip_stride,
+                          cudaStream_t stream, int max_slices, float* partial, int pstride, int* slices_out) {
+  if (n_plans < 1) return SAGA_OK;
+  const saga_cqt_plan* p = plans[0];
   const CqtStreamState* st = p->stream_tc;
   if (!st || !st->supported) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: plan does not fit the streamed tcgen05 path");
+  for (int i = 1; i < n_plans; ++i) {
+    const CqtStreamState* si = plans[i]->stream_tc;
+    if (!si || !si->supported || si->packs.size() != st->packs.size() || si->b_stage_bytes != st->b_stage_bytes ||
+        si->parts != st->parts || si->bufs != st->bufs || plans[i]->oct.size() != p->oct.size())
+      return set_error(SAGA_ERR_INVALID, "cqt: plans of one shared-cascade launch must have the same geometry");
+  }
+  const int gpp = (int)st->packs.size();                       // groups per plan
+  if (gpp > US_MAX_GROUPS) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: too many column groups");
+  const int plans_per_launch = US_MAX_GROUPS / gpp;
+  const int rows_per_clip = frame_first ? 8 : (int)T_max;
+  if ((int64_t)n_clips * rows_per_clip >= ((int64_t)1 << 31)) return set_error(SAGA_ERR_UNSUPPORTED, "cqt: batch too large for one launch");
+  int min_st = 1 << 30;
+  for (auto& o : p->oct) min_st = std::min(min_st, o.n_fft / US_KC);
+  const int n_sm = st->num_sms > 0 ? st->num_sms : 148;
+  // work items of the first launch decide the K split (split-K: frame windows only, the caller provides the scratch
+  // and runs the finish kernel): until the launch covers most of the SMs, with >= 8 stages per slice
+  int ks = 1;
+  {
+    int64_t items = 0;
+    for (int i = 0; i < std::min(n_plans, plans_per_launch); ++i)
+      items += (((int64_t)nclips[i] * rows_per_clip + US_TILE_M - 1) / US_TILE_M) * gpp;
+    if (frame_first && partial)
+      while (2 * ks <= max_slices && items * ks < n_sm && min_st / (2 * ks) >= 8 && min_st % (2 * ks) == 0) ks *= 2;
+  }
+  if (slices_out) *slices_out = ks;
+  if (frame_pitch > p->n_bins && ks == 1) {      // (the split-K finish kernel writes the padding itself)
+    dim3 grid(frame_first ? 1 : 8, n_clips), block(32, 8);
+    cqt_stream_zero_cols_kernel<<<grid, block, 0, stream>>>(mag_out, cplx_out, lv.clip_frames, frame_first ? frame_count : 0,
+                                                            p->n_bins, frame_pitch, out_clip_stride);
+    SAGA_LAUNCH_CHECK();
+  }
+  for (int p0 = 0; p0 < n_plans; p0 += plans_per_launch) {
+  const int p1 = std::min(n_plans, p0 + plans_per_launch);
   UsArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.n_groups = (int)st->packs.size();
   a.n_clips = n_clips;
   a.n_bins = p->n_bins;
-  a.rows_per_clip = frame_first ? 8 : (int)T_max;
+  a.rows_per_clip = rows_per_clip;
   a.frame_count = frame_count;
   a.frame_first = frame_first;
   a.clip_frames = lv.clip_frames;
-  const int64_t rows = (int64_t)n_clips * a.rows_per_clip;
-  const int64_t m_tiles = (rows + US_TILE_M - 1) / US_TILE_M;
-  if (rows <= 0) return SAGA_OK;
-  if (rows >= ((int64_t)1 << 31) || m_tiles * a.n_groups >= ((int64_t)1 << 31))
-    return set_error(SAGA_ERR_UNSUPPORTED, "cqt: batch too large for one launch");
-  // split-K (frame windows only, the caller provides the scratch and runs the finish kernel): until the launch
-  // covers most of the SMs, with at least 8 stages (and every partial accumulator used) per slice
-  int ks = 1, min_st = 1 << 30;
-  for (auto& o : p->oct) min_st = std::min(min_st, o.n_fft / US_KC);
-  const int n_sm = st->num_sms > 0 ? st->num_sms : 148;
-  if (frame_first && partial)
-    while (2 * ks <= max_slices && m_tiles * a.n_groups * ks < n_sm && min_st / (2 * ks) >= 8 && min_st % (2 * ks) == 0) ks *= 2;
-  if (slices_out) *slices_out = ks;
   a.ks = ks;
   a.n_oct = (int)p->oct.size();
   a.pstride = pstride;
   a.partial = partial;
-  a.total_rows = (uint32_t)rows;
-  a.m_tiles = (uint32_t)m_tiles;
-  a.total_items = (uint32_t)(m_tiles * a.n_groups * ks);
+  uint32_t item0 = 0;
+  int ng = 0;
+  for (int pi = p0; pi < p1; ++pi) {
+    const saga_cqt_plan* pp = plans[pi];
+    const CqtStreamState* sp = pp->stream_tc;
+    const int64_t rows = (int64_t)nclips[pi] * rows_per_clip;
+    if (rows <= 0) continue;
+    if (clip0[pi] < 0 || clip0[pi] + nclips[pi] > n_clips) return set_error(SAGA_ERR_INVALID, "cqt: clip range outside the batch");
+    const uint32_t tiles = (uint32_t)((rows + US_TILE_M - 1) / US_TILE_M);
+    for (int i = 0; i < gpp; ++i) {
+      const StreamPack& pk = sp->packs[i];
+      const CqtOctaveDev& o = pp->oct[pk.oct];
+      UsGroup& g = a.grp[ng++];
+      g.sig = lv.lvl[o.level] + (lv.pad[o.level] - o.n_fft / 2);
+      g.sig_stride = lv.pitch[o.level];
+      g.b_pack = pk.d_pack;
+      g.hop = o.hop;
+      g.n_fft = o.n_fft;
+      g.ncol = pk.ncol;
+      g.first_bin = o.first_bin + pk.col0 / 2;
+      g.n_main = pk.n_main;
+      g.n_lo = pk.n_lo;
+      g.oct = pk.oct;
+      g.filt0 = pk.col0 / 2;
+      g.clip0 = clip0[pi];
+      g.n_rows = (uint32_t)rows;
+      g.tiles = tiles;
+      g.item0 = item0;
+      item0 += tiles * (uint32_t)ks;
+    }
+  }
+  if (ng == 0) continue;
+  a.n_groups = ng;
+  a.total_items = item0;
   a.mag_out = mag_out;
   a.cplx_out = cplx_out;
   a.frame_pitch = frame_pitch;
@@ -883,28 +966,6 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
     const char* dbg = SAGA_OPT("SAGA_UMMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
   }
-  for (int i = 0; i < a.n_groups; ++i) {
-    const StreamPack& pk = st->packs[i];
-    const CqtOctaveDev& o = p->oct[pk.oct];
-    UsGroup& g = a.grp[i];
-    g.sig = lv.lvl[o.level] + (lv.pad[o.level] - o.n_fft / 2);
-    g.sig_stride = lv.pitch[o.level];
-    g.b_pack = pk.d_pack;
-    g.hop = o.hop;
-    g.n_fft = o.n_fft;
-    g.ncol = pk.ncol;
-    g.first_bin = o.first_bin + pk.col0 / 2;
-    g.n_main = pk.n_main;
-    g.n_lo = pk.n_lo;
-    g.oct = pk.oct;
-    g.filt0 = pk.col0 / 2;
-  }
-  if (frame_pitch > p->n_bins && ks == 1) {      // (the split-K finish kernel writes the padding itself)
-    dim3 grid(frame_first ? 1 : 8, n_clips), block(32, 8);
-    cqt_stream_zero_cols_kernel<<<grid, block, 0, stream>>>(mag_out, cplx_out, lv.clip_frames, frame_first ? frame_count : 0,
-                                                            p->n_bins, frame_pitch, out_clip_stride);
-    SAGA_LAUNCH_CHECK();
-  }
   const int grid = (int)std::min<int64_t>(a.total_items, n_sm);
   if (a.debug & (16 | 128)) cudaMemsetAsync(st->d_prof, 0, sizeof(long long) * (2048 + 96 * 8), stream);
   cqt_umma_stream_kernel<<<grid, US_THREADS, smem_bytes, stream>>>(a);
@@ -937,6 +998,7 @@ int cqt_stream_exec(const saga_cqt_plan* p, const CqtLevels& lv, int n_clips, in
       fprintf(stderr, "us_prof %-26s %12.0f per CTA\n", names[sidx], sum / grid);
     }
   }
+  }   // launches
   return SAGA_OK;
 }
 

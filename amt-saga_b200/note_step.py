@@ -51,7 +51,8 @@ class NoteStepBatch:
         self._dirty = None         # frames changed by the last subtract, while `wav` is an iSTFT of the previous magnitudes
         self._wav_synced = False   # `wav` == iSTFT(magnitudes before the last subtract) (the original audio is not)
         self.incremental_istft = True   # False: every rebuild of `wav` inverts all T frames (A/B twin)
-        self.share_cascade = True       # False: every pitch group runs its own decimation cascade (A/B twin)
+        self.share_cascade = True       # False: every pitch group runs its own decimation cascade; "per_plan": shared
+                                        # cascade but one contraction launch per pitch (A/B twins)
         self._tone_fft = None
         self.full_cqt = False      # True: every slice_C transforms all 258 columns like the reference (A/B twin)
 
@@ -257,8 +258,13 @@ class NoteStepBatch:
                 else:
                     A, B = a, groups[j][1]
                     token = ops.cqt_cascade_shared(wav_s[A:B], plan)
-                    for (ga, gb, gp) in groups[i:j + 1]:
-                        ops.cqt_frames_from_cascade(token, gp, ga - A, gb - ga, d["first_s"][ga:gb], nf, buf[ga:gb])
+                    run = groups[i:j + 1]
+                    if self.share_cascade == "per_plan":      # one contraction launch per pitch (A/B twin)
+                        for (ga, gb, gp) in run:
+                            ops.cqt_frames_from_cascade(token, gp, ga - A, gb - ga, d["first_s"][ga:gb], nf, buf[ga:gb])
+                    else:                                     # all pitches of the run in ~one launch per 10 banks
+                        ops.cqt_frames_from_cascade_multi(token, [g_[2] for g_ in run], [g_[0] - A for g_ in run],
+                                                          [g_[1] - g_[0] for g_ in run], d["first_s"][A:B], nf, buf[A:B])
                 i = j + 1
             g = ops.gather_frames_batch(buf, nbins, d["rel_s"], inv_ref_s)
             res.append(g.index_select(0, d["inv_order"]))

@@ -368,6 +368,35 @@ def cqt_frames_from_cascade(token, plan, clip_first, n_clips, frame_first, frame
     return out
 
 
+def cqt_frames_from_cascade_multi(token, plans, clip_first, clip_count, frame_first, frame_count, out):
+    """Phase 2 for several plans of the cascade's geometry in one call (saga_cqt_frames_shared_multi_exec): plan i
+    contracts clips [clip_first[i], clip_first[i] + clip_count[i]) of the cascade batch; together they must cover every
+    clip once.  frame_first: int32 device tensor [batch]; out: contiguous [batch, frame_count, P]."""
+    n = token["n_clips"]
+    P = frame_pitch(plans[0].n_bins)
+    for pl in plans:
+        if pl.geometry() != token["geometry"]:
+            raise ValueError("plan geometry differs from the cascade's")
+    if out.shape != (n, int(frame_count), P) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out must be contiguous float32 [batch, frame_count, %d]" % P)
+    first = frame_first.to(device=out.device, dtype=torch.int32).contiguous()
+    if first.shape != (n,):
+        raise ValueError("frame_first must be [batch]")
+    cf = np.ascontiguousarray(clip_first, dtype=np.int32)
+    cc = np.ascontiguousarray(clip_count, dtype=np.int32)
+    order = np.argsort(cf)
+    if len(cf) != len(plans) or int(cc.sum()) != n or np.any(np.cumsum(cc[order]) - cc[order] != cf[order]):
+        raise ValueError("the plans' clip ranges must tile the batch")
+    handles = (C.c_void_p * len(plans))(*[pl.handle for pl in plans])
+    wav = token["wav"]
+    with _on(wav, plans[0]):
+        _lib.check(_lib.lib().saga_cqt_frames_shared_multi_exec(
+            handles, len(plans), cf.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p), _ptr(wav), _ptr(token["offs"]),
+            token["lens_ptr"], n, token["max_len"], _ptr(first), int(frame_count), _ptr(out), P, int(frame_count) * P,
+            _ptr(token["ws"]), token["ws"].numel(), _stream(wav)), ParameterError)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # K3
 # ---------------------------------------------------------------------------

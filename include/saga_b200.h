@@ -254,6 +254,17 @@ int saga_cqt_frames_shared_exec(const saga_cqt_plan* plan, const float* wav, con
                                 float* C_mag_out, int64_t frame_pitch, int64_t out_clip_stride,
                                 void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Phase 2 for SEVERAL plans of that geometry at once: plan i contracts clips [clip_first[i], clip_first[i] + clip_count[i])
+ * (host arrays) of the phase-1 batch; frame_first / C_mag_out are those of the WHOLE batch (clip 0).  One tensor-core
+ * launch per ~10 plans and one finish launch instead of two launches per plan.  The plans must cover every clip of the
+ * batch exactly once (the finish pass of a K-split launch writes all of them). */
+int saga_cqt_frames_shared_multi_exec(const saga_cqt_plan* const* plans, int n_plans, const int32_t* clip_first,
+                                      const int32_t* clip_count, const float* wav, const int64_t* clip_offsets,
+                                      const int64_t* clip_lens, int ws_clips, int64_t max_len,
+                                      const int32_t* frame_first, int frame_count, float* C_mag_out,
+                                      int64_t frame_pitch, int64_t out_clip_stride, void* workspace,
+                                      int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * K5  feature gather for the classifiers (training.py:333-388)
  * ---------------------------------------------------------------------- */

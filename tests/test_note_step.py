@@ -147,8 +147,10 @@ def test_incremental_wave_rebuild_equals_full_istft():
 def test_shared_cascade_across_pitches_is_bit_identical():
     """Pitches of equal CQT geometry share one decimation cascade in the batched step (saga_cqt_frames_shared_exec:
     cascade once for the run of windows, one contraction per pitch on its clip range); with `share_cascade = False`
-    every pitch group runs the whole transform on its own.  Same kernels on the same data: the two must be equal
-    bit for bit, for 40 windows over 23 pitches in every geometry class the note-relative transforms meet."""
+    every pitch group runs the whole transform on its own.  Same kernels on the same data: equal bit for bit when
+    every pitch still gets its own contraction launch ("per_plan"); the default packs a run's pitches into one launch
+    (saga_cqt_frames_shared_multi_exec), whose K split and hence summation order differ: 2e-6 of peak.  40 windows over
+    23 pitches in every geometry class the note-relative transforms meet."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -166,7 +168,7 @@ def test_shared_cascade_across_pitches_is_bit_identical():
     onset = rng.uniform(0, 5.5, W)
     geoms = set()
     outs = {}
-    for share in (True, False):
+    for share in (True, "per_plan", False):
         b = NoteStepBatch(W)
         b.share_cascade = share
         b.load(r["mag_storage"][:, :258].clone(), r["phase_storage"][:, :258].clone(), wav, r["clip_max"], np.ones((W, 3)))
@@ -176,8 +178,12 @@ def test_shared_cascade_across_pitches_is_bit_identical():
     for p in np.unique(pitch):
         geoms.add(ops.get_cqt_plan(44100, 1024, 440.0 * 2.0 ** ((int(p) - 69) / 12.0), 348, 192, 2).geometry())
     assert 1 < len(geoms) < len(np.unique(pitch))        # several pitches per geometry, several geometries
-    for k in range(2):
-        assert (outs[True][k]["valid"] == outs[False][k]["valid"]).all()
-        for n in ("C_sw_inst_foc", "C_velocity", "C_sw_pitch"):
-            a_, b_ = outs[True][k][n], outs[False][k][n]
-            assert torch.equal(torch.nan_to_num(a_), torch.nan_to_num(b_)), (k, n)
+    for mode in (True, "per_plan"):
+        for k in range(2):
+            assert (outs[mode][k]["valid"] == outs[False][k]["valid"]).all()
+            for n in ("C_sw_inst_foc", "C_velocity", "C_sw_pitch"):
+                a_, b_ = torch.nan_to_num(outs[mode][k][n]), torch.nan_to_num(outs[False][k][n])
+                if mode == "per_plan":      # same launches on the same data
+                    assert torch.equal(a_, b_), (mode, k, n)
+                else:                       # one launch for a run of pitches: a different K split, i.e. summation order
+                    assert float((a_ - b_).abs().max()) <= 2e-6 * float(b_.abs().max()), (mode, k, n)
