@@ -8,8 +8,10 @@
 // have banks of 0.4 / 1.5 / 25 MB.  Here the bank is streamed: the K loop runs in stages of 32 samples and a
 // stage is
 //     A_hi, A_lo : 128 rows x 32 samples, row r = 32 contiguous samples of ONE frame, gathered from the padded
-//                  level signal (16 B pieces into the K-major SWIZZLE_NONE core-matrix layout: plane g = samples
-//                  4g..4g+3 of every row, 16 B per row)
+//                  level signal -- in SHARED MEMORY (16 B pieces into the K-major SWIZZLE_NONE core-matrix layout:
+//                  plane g = samples 4g..4g+3 of every row, 16 B per row), or in TENSOR MEMORY (lane = row, one
+//                  column per sample, written with tcgen05.st) where the accumulators leave room for a ring at
+//                  least as deep: then only the bank crosses the shared-memory port
 //     B          : the bank's 32 rows x n_main columns for this stage, ONE bulk copy from the pre-packed
 //                  [n_fft/4][n_main][4] image (TF32 hi | lo side by side along N)
 // and costs 4 K-slices x (main MMA N = n_main, correction MMA N = n_lo) issued by one thread: 3xTF32 split as in
@@ -21,15 +23,18 @@
 //   * frame windows     : rows = frames [first[clip], first[clip] + 8) of every clip (saga_cqt_frames_exec: the
 //                         producer loop keeps 8 columns of each per-note transform), 16 clips per tile.
 // Column groups of <= 128 real columns (64 filters) are separate work items, ordered (octave, group)-major so
-// that all CTAs stream the same bank slab out of L2 at the same time.
+// that all CTAs stream the same bank slab out of L2 at the same time.  A work item's group also names its clip
+// range and bank, so one launch can contract several plans of equal geometry (one bank per pitch:
+// cqt_stream_exec_multi); frame windows of small batches are split along K (finish kernel in cqt.cu).
 //
-// Warp roles of the persistent CTA (one per SM): 0-3 epilogue (TMEM lanes 32w..32w+31), 4 MMA issuer, 5 bank
-// loader (bulk copies), 6-21 row loaders in four groups that take the stages in turn: global -> registers (the group's
-// next stage, loaded while the other groups' stages run, so the L2 round trip is not on the shared-memory ring's
-// critical path) -> hi and lo planes in shared memory, ONE mbarrier arrive per warp.  (The first
-// version copied rows with cp.async and split them in separate converter warps: 256 per-thread barrier arrivals and
-// an extra hand-over per stage cost more than the copies -- the barrier skeleton alone ran at 540 cycles per stage.)
-// Every wait is polled by lane 0 only; the other lanes park at __syncwarp.
+// Warp roles of the persistent CTA (one per SM): 0-3 epilogue (TMEM lanes 32w..32w+31), 4 MMA issuer (stages in
+// pairs on rings of >= 4 stages, the next stage's barrier probed inside the issue block), 5 bank loader (bulk
+// copies), 6-21 row loaders in groups that take the stages in turn: global -> registers (the group's next stage,
+// loaded while the other groups' stages run, so the L2 round trip is not on the ring's critical path) -> hi and lo
+// planes, ONE mbarrier arrive per warp; 22 an optional second issuer (measured slower, off).  (The first version
+// copied rows with cp.async and split them in separate converter warps: 256 per-thread barrier arrivals and an extra
+// hand-over per stage cost more than the copies.)  Waiters off the critical path are polled by lane 0 with back-off.
+// DESIGN.md section 4 / K2 (5) has the measurements behind each of these choices.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
