@@ -47,6 +47,7 @@ SIGNATURES = {
     "saga_stft_num_frames": (_L, [_P, _L]),
     "saga_stft_exec": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P, _L, _L, _P, _P, _P]),
     "saga_istft_exec": (_I, [_P, _P, _P, _P, _I, _I, _L, _L, _P, _L, _P]),
+    "saga_istft_rows_exec": (_I, [_P, _P, _P, _P, _I, _P, _I, _L, _L, _P, _L, _P]),
     "saga_subtract_db_exec": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P,
                                    _I, _I, _I, _I, _L, _F, _F, _P]),
     "saga_amplitude_to_db_exec": (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _P]),

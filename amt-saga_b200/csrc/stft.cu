@@ -566,6 +566,7 @@ struct IstftArgs {
   const float2* twN;
   int64_t frame_pitch, in_clip_stride, wav_clip_stride;
   int hop, center, n_frames, FO, nbuf, tiles_per_clip;
+  const int32_t* frame0;    // optional: clip c inverts rows [frame0[c], frame0[c] + n_frames) of its spectrogram
 };
 
 // threads sharing one frame of the inverse transform: 64 for n_fft 4096 when the CTA has the 16 warps for it
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(WARPS * 32, (M <= 1024 ? 2 : 1)) istft_kernel(
   const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
   for (int f = group; f < nfr; f += GROUPS) {
     float2* buf = bufs + f * BUF;
-    const int64_t row = (int64_t)clip * a.in_clip_stride + (t_lo + f) * a.frame_pitch;
+    const int64_t row = (int64_t)clip * a.in_clip_stride + (t_lo + f + (a.frame0 ? a.frame0[clip] : 0)) * a.frame_pitch;
     // rebuild conj(Z[k]),  Z = E + iO  from the half spectrum X[0..M]; four bins per lane in flight (the loads
     // of a bin pair are six independent global reads: one pair at a time left the warp waiting on DRAM latency)
     constexpr int U = 4;
@@ -934,10 +935,10 @@ extern "C" int saga_stft_exec(const saga_stft_plan* p, const float* wav, const i
   return set_error(SAGA_ERR_UNSUPPORTED, "stft_exec: unsupported n_fft");
 }
 
-extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, const float* mag_in,
-                               const void* phase_in, int n_clips, int n_frames, int64_t frame_pitch,
-                               int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
-                               void* stream) {
+static int istft_exec_impl(const saga_stft_plan* p, const void* cplx_in, const float* mag_in,
+                           const void* phase_in, int n_clips, int n_frames, int64_t frame_pitch,
+                           int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
+                           const int32_t* frame0, void* stream) {
   if (!p || !wav_out || (!cplx_in && !(mag_in && phase_in)))
     return set_error(SAGA_ERR_INVALID, "istft_exec: null argument");
   if (frame_pitch < p->M + 1) return set_error(SAGA_ERR_INVALID, "istft_exec: frame_pitch < n_bins");
@@ -957,6 +958,7 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
   a.hop = p->hop;
   a.center = p->center;
   a.n_frames = n_frames;
+  a.frame0 = frame0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (p->M) {
     case 128: return launch_istft<128, 16, 8, 1, 8>(p, a, n_clips, st);
@@ -973,7 +975,7 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
       const bool aligned = (wav_clip_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(wav_out) & 7) == 0 &&
                            (in_bits & 15) == 0 && (frame_pitch & 3) == 0 && frame_pitch >= p->M + 4 &&
                            (in_clip_stride & 3) == 0;
-      if (ring_mode > 0 && aligned && saga::istft_ring_supported(p))
+      if (ring_mode > 0 && aligned && !frame0 && saga::istft_ring_supported(p))
         return saga::launch_istft_ring(p, cplx_in, mag_in, phase_in, n_clips, n_frames, frame_pitch, in_clip_stride,
                                        wav_out, wav_clip_stride, st);
       return launch_istft<1024, 32, 32, 1, 8>(p, a, n_clips, st);
@@ -984,4 +986,21 @@ extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, con
     case 4096: return launch_istft<4096, 16, 16, 16, 4>(p, a, n_clips, st);
   }
   return set_error(SAGA_ERR_UNSUPPORTED, "istft_exec: unsupported n_fft");
+}
+
+extern "C" int saga_istft_exec(const saga_stft_plan* p, const void* cplx_in, const float* mag_in,
+                               const void* phase_in, int n_clips, int n_frames, int64_t frame_pitch,
+                               int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
+                               void* stream) {
+  return istft_exec_impl(p, cplx_in, mag_in, phase_in, n_clips, n_frames, frame_pitch, in_clip_stride, wav_out,
+                         wav_clip_stride, nullptr, stream);
+}
+
+extern "C" int saga_istft_rows_exec(const saga_stft_plan* p, const void* cplx_in, const float* mag_in,
+                                    const void* phase_in, int n_clips, const int32_t* frame0, int n_frames,
+                                    int64_t frame_pitch, int64_t in_clip_stride, float* wav_out,
+                                    int64_t wav_clip_stride, void* stream) {
+  if (!frame0) return set_error(SAGA_ERR_INVALID, "istft_rows_exec: null frame0");
+  return istft_exec_impl(p, cplx_in, mag_in, phase_in, n_clips, n_frames, frame_pitch, in_clip_stride, wav_out,
+                         wav_clip_stride, frame0, stream);
 }

@@ -288,9 +288,7 @@ class NoteStepBatch:
             self.wav = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb)
         elif d["any"]:
             F, hop = d["F"], self.hl
-            rows = d["fa"][:, None] + torch.arange(F, device=self.dev)               # [W, F]
-            w_ix = torch.arange(self.W, device=self.dev)[:, None]
-            y = ops.istft_batch(self.stft, mag=self.mag[w_ix, rows], phase=self.ph[w_ix, rows], n_bins=self.nb)   # [W, (F-1) hop]
+            y = ops.istft_batch(self.stft, mag=self.mag, phase=self.ph, n_bins=self.nb, frame0=d["fa32"], n_frames=F)   # [W, (F-1) hop]
             idx = d["fa"][:, None] * hop + torch.arange(y.shape[1], device=self.dev)   # global sample of every sub sample
             keep = (idx >= d["lo"][:, None]) & (idx < d["hi"][:, None])
             self.wav.scatter_(1, idx, torch.where(keep, y, self.wav.gather(1, idx)))
@@ -313,7 +311,8 @@ class NoteStepBatch:
         lo = np.clip((o - m) * hop, 0, L)
         hi = np.where(tg > 0, np.clip((o + tg + m) * hop, 0, L), lo)
         dev = self._upload({"fa": fa, "lo": lo, "hi": hi})
-        self._dirty = {"F": F, "any": bool((tg > 0).any()), "fa": dev["fa"].long(), "lo": dev["lo"].long(), "hi": dev["hi"].long()}
+        self._dirty = {"F": F, "any": bool((tg > 0).any()), "fa32": dev["fa"], "fa": dev["fa"].long(), "lo": dev["lo"].long(),
+                       "hi": dev["hi"].long()}
 
     def subtract(self, guess_wav, offset_frames, guess_lens=None, offset_dev=None):
         """training.py:426 + :449: STFT of the rendered notes (K1), then align / scale / subtract / ReLU (K3)."""

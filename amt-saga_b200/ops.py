@@ -220,10 +220,12 @@ def stft_batch(wav, plan, lens=None, want_phase=False, want_complex=False, want_
     return out
 
 
-def istft_batch(plan, F=None, mag=None, phase=None, n_bins=None):
+def istft_batch(plan, F=None, mag=None, phase=None, n_bins=None, frame0=None, n_frames=None):
     """K4 on frame-major storage [clips, T, P] (rows = frames).  Either complex
     `F`, or float `mag` and complex unit-phasor `phase` with identical strides.
-    Returns [clips, hop*(T-1)] (centred) float32."""
+    Returns [clips, hop*(T-1)] (centred) float32.
+    frame0 (int32 device tensor [clips]) + n_frames: invert only rows [frame0[c], frame0[c] + n_frames) of every clip
+    (saga_istft_rows_exec); the caller guarantees frame0[c] + n_frames <= T."""
     n_bins = plan.n_bins if n_bins is None else n_bins
     if n_bins != plan.n_bins:
         raise ValueError("spectrogram has %d bins, plan expects %d" % (n_bins, plan.n_bins))
@@ -252,11 +254,21 @@ def istft_batch(plan, F=None, mag=None, phase=None, n_bins=None):
     n_clips, T, _ = s.shape
     pitch = s.stride(1) if T > 1 else s.shape[2]
     cstride = s.stride(0) if n_clips > 1 else T * pitch
-    out_len = plan.hop * (T - 1) + (0 if plan.center else plan.n_fft)
+    Tn = T if frame0 is None else int(n_frames)
+    if frame0 is not None and not (0 < Tn <= T):
+        raise ValueError("n_frames must be in 1..T")
+    out_len = plan.hop * (Tn - 1) + (0 if plan.center else plan.n_fft)
     wav = torch.empty((n_clips, max(out_len, 0)), device=s.device, dtype=torch.float32)
     with _on(s, plan):
-        _lib.check(_lib.lib().saga_istft_exec(plan.handle, args[0], args[1], args[2], n_clips, T, pitch,
-                                              cstride, _ptr(wav), wav.stride(0), _stream(s)))
+        if frame0 is None:
+            _lib.check(_lib.lib().saga_istft_exec(plan.handle, args[0], args[1], args[2], n_clips, T, pitch,
+                                                  cstride, _ptr(wav), wav.stride(0), _stream(s)))
+        else:
+            f0 = frame0.to(device=s.device, dtype=torch.int32).contiguous()
+            if f0.shape != (n_clips,):
+                raise ValueError("frame0 must be [clips]")
+            _lib.check(_lib.lib().saga_istft_rows_exec(plan.handle, args[0], args[1], args[2], n_clips, _ptr(f0), Tn, pitch,
+                                                       cstride, _ptr(wav), wav.stride(0), _stream(s)))
     return wav
 
 

@@ -109,6 +109,14 @@ int saga_istft_exec(const saga_stft_plan* plan, const void* cplx_in, const float
                     int64_t in_clip_stride, float* wav_out, int64_t wav_clip_stride,
                     void* stream);
 
+/* The same for a ROW RANGE per clip: clip c inverts rows [frame0[c], frame0[c] + n_frames) of its spectrogram as if
+ * they were a clip of their own (frame0: device int32 [n_clips]).  The batched per-note step uses it to re-invert only
+ * the frames a subtraction touched (util_audio.py:88-106 rebuilds the whole waveform) without first gathering them. */
+int saga_istft_rows_exec(const saga_stft_plan* plan, const void* cplx_in, const float* mag_in,
+                         const void* phase_in, int n_clips, const int32_t* frame0, int n_frames,
+                         int64_t frame_pitch, int64_t in_clip_stride, float* wav_out,
+                         int64_t wav_clip_stride, void* stream);
+
 /* ------------------------------------------------------------------------
  * K3  generative-subtractive chain + dB epilogue, replaces
  *   util_audio.py:221-259 (subtract), :170-174 (ref_mag), :176-180 (D)
