@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), "libsaga_b200.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding missing for %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.saga_abi_version() == 2
+    assert lib.saga_abi_version() == 3
 
 
 def test_no_cpu_fallback(lib):
