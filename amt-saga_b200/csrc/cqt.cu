@@ -1246,8 +1246,21 @@ extern "C" int saga_cqt_frames_shared_multi_exec(const saga_cqt_plan* const* pla
     return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: frame_count must be in 1..%d", FW_MAXF);
   const saga_cqt_plan* p = plans[0];
   const bool stream_on = cqt_stream_supported(p) && !(SAGA_OPT("SAGA_CQT_STREAM") && atoi(SAGA_OPT("SAGA_CQT_STREAM")) == 0);
+  // every plan must have the geometry the cascade was run for (levels, hops, kernel lengths, filter counts, early stage)
+  for (int i = 0; i < n_plans; ++i) {
+    const saga_cqt_plan* q = plans[i];
+    if (!q || q->oct.size() != p->oct.size() || q->early_factor != p->early_factor || q->max_level != p->max_level ||
+        q->n_bins != p->n_bins || q->hop != p->hop)
+      return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: plan %d has another geometry", i);
+    for (size_t o = 0; o < p->oct.size(); ++o)
+      if (q->oct[o].level != p->oct[o].level || q->oct[o].hop != p->oct[o].hop || q->oct[o].n_fft != p->oct[o].n_fft ||
+          q->oct[o].n_filters != p->oct[o].n_filters || q->oct[o].first_bin != p->oct[o].first_bin)
+        return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: plan %d has another geometry", i);
+    if (clip_first[i] < 0 || clip_count[i] < 0 || clip_first[i] + clip_count[i] > ws_clips)
+      return set_error(SAGA_ERR_INVALID, "cqt_frames_shared_multi_exec: clip range of plan %d outside the batch", i);
+  }
   bool same = stream_on;
-  for (int i = 0; i < n_plans && same; ++i) same = plans[i] && cqt_stream_supported(plans[i]);
+  for (int i = 0; i < n_plans && same; ++i) same = cqt_stream_supported(plans[i]);
   if (!same) {     // plan by plan (fp32 kernels, or a plan outside the tensor path's constraints)
     for (int i = 0; i < n_plans; ++i) {
       const int rc = saga_cqt_frames_shared_exec(plans[i], wav, clip_offsets, clip_lens, ws_clips, max_len, 2, clip_first[i],

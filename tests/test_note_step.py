@@ -187,3 +187,41 @@ def test_shared_cascade_across_pitches_is_bit_identical():
                     assert torch.equal(a_, b_), (mode, k, n)
                 else:                       # one launch for a run of pitches: a different K split, i.e. summation order
                     assert float((a_ - b_).abs().max()) <= 2e-6 * float(b_.abs().max()), (mode, k, n)
+
+
+@pytest.mark.gpu
+def test_shared_cascade_entry_points_reject_mismatched_plans():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200 import ops, synth, _lib
+    wav = synth.piano_batch(range(4), 264168, 44100, seed_base=1, device="cuda")
+    hz = lambda m: 440.0 * 2.0 ** ((m - 69) / 12.0)
+    p_a, p_b = ops.get_cqt_plan(44100, 1024, hz(50), 36, 24, 2), ops.get_cqt_plan(44100, 1024, hz(51), 36, 24, 2)
+    p_far = ops.get_cqt_plan(44100, 1024, hz(80), 36, 24, 2)
+    assert p_a.geometry() == p_b.geometry() != p_far.geometry()
+    tok = ops.cqt_cascade_shared(wav, p_a)
+    first = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = torch.zeros((4, 8, ops.frame_pitch(36)), device="cuda")
+    ops.cqt_frames_from_cascade_multi(tok, [p_a, p_b], [0, 2], [2, 2], first, 8, out)
+    ref = torch.cat([ops.cqt_frames_batch(wav[:2], p_a, first[:2]), ops.cqt_frames_batch(wav[2:], p_b, first[2:])])
+    assert float((out - ref).abs().max()) <= 2e-6 * float(ref.max())
+    tok = ops.cqt_cascade_shared(wav, p_a)
+    with pytest.raises(ValueError):
+        ops.cqt_frames_from_cascade_multi(tok, [p_a, p_far], [0, 2], [2, 2], first, 8, out)       # another geometry
+    with pytest.raises(ValueError):
+        ops.cqt_frames_from_cascade_multi(tok, [p_a, p_b], [0, 1], [2, 2], first, 8, out)         # ranges do not tile
+    with pytest.raises(ValueError):
+        ops.cqt_frames_from_cascade(tok, p_far, 0, 4, first, 8, out)
+    # the C entry checks the geometry itself (a caller that bypasses the wrapper)
+    lib = _lib.lib()
+    handles = (C.c_void_p * 2)(p_a.handle, p_far.handle)
+    cf, cc = np.array([0, 2], dtype=np.int32), np.array([2, 2], dtype=np.int32)
+    rc = lib.saga_cqt_frames_shared_multi_exec(handles, 2, cf.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p),
+                                               C.c_void_p(tok["wav"].data_ptr()), C.c_void_p(tok["offs"].data_ptr()), None, 4,
+                                               tok["max_len"], C.c_void_p(first.data_ptr()), 8, C.c_void_p(out.data_ptr()),
+                                               out.shape[2], 8 * out.shape[2], C.c_void_p(tok["ws"].data_ptr()),
+                                               tok["ws"].numel(), None)
+    assert rc == -1 and b"geometry" in lib.saga_last_error_string()
