@@ -90,7 +90,7 @@ decimate_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_off
 constexpr int DECP_Q = 16;      // taps per side and phase (kaiser_fast: 16 zero crossings)
 constexpr int DECP_R = 8;       // outputs per lane
 constexpr int DECP_WARPS = 8;
-__global__ void __launch_bounds__(32 * DECP_WARPS, 2)
+__global__ void __launch_bounds__(32 * DECP_WARPS, 3)
 decimate_phase_kernel(const float* __restrict__ in, const int64_t* __restrict__ in_offsets, int64_t in_stride,
                       const int64_t* __restrict__ clip_lens, int64_t max_len, float* __restrict__ out,
                       int64_t out_stride, const float* __restrict__ g, int factor) {
@@ -109,9 +109,6 @@ decimate_phase_kernel(const float* __restrict__ in, const int64_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < DECP_R; ++i) acc[i] = 0.f;
   for (int r = r0; r < factor; r += 32) {
-    float tap[2 * DECP_Q];
-#pragma unroll
-    for (int t = 0; t < 2 * DECP_Q; ++t) tap[t] = __ldg(g + t * factor + r);
     float xw[DECP_R + 2 * DECP_Q - 1];
     const int s0 = ((int)o0 - DECP_Q) * factor + r, n = (int)len;     // clips are far shorter than 2^31 samples
 #pragma unroll
@@ -119,10 +116,13 @@ decimate_phase_kernel(const float* __restrict__ in, const int64_t* __restrict__ 
       const int s = s0 + w * factor;
       xw[w] = ((unsigned)s < (unsigned)n) ? __ldg(x + s) : 0.f;
     }
+    // tap by tap (each is one L1-resident load used 8 times): keeps the 32 taps out of the live register set
 #pragma unroll
-    for (int i = 0; i < DECP_R; ++i)
+    for (int t = 0; t < 2 * DECP_Q; ++t) {
+      const float tap = __ldg(g + t * factor + r);
 #pragma unroll
-      for (int t = 0; t < 2 * DECP_Q; ++t) acc[i] = fmaf(tap[t], xw[i + t], acc[i]);
+      for (int i = 0; i < DECP_R; ++i) acc[i] = fmaf(tap, xw[i + t], acc[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < DECP_R; ++i)
