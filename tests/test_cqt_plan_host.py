@@ -92,3 +92,25 @@ def test_errors_like_librosa():
     with pytest.raises(ocqt.ParameterError):
         ocqt.cqt(np.zeros(4000), sr=8000, hop_length=512, fmin=note_to_hz("C1"), n_bins=96,
                  filter_scale=2)
+
+
+def test_note_relative_plans_fall_into_few_contiguous_geometry_classes():
+    """The batched per-note step shares one decimation cascade between pitches whose plans have the same geometry
+    (CqtPlan.geometry(): early factor, levels, hops, kernel lengths) and walks the windows in pitch order: over the 88
+    keys the two note-relative shapes of training.py:366-388 must fall into a handful of classes, each a contiguous
+    pitch range (a class that came back later would only cost an extra cascade, never a wrong result)."""
+    from amt_saga_b200.cqt_plan import CqtPlan, ParameterError
+    for nbins, bpo, shift in ((348, 192, 0), (36, 24, -10)):
+        seq = []
+        for midi in range(21, 109):
+            try:
+                seq.append(CqtPlan(44100, 1024, 440.0 * 2.0 ** ((midi + shift - 69) / 12.0), nbins, bpo, filter_scale=2,
+                                   create_device_plan=False).geometry())
+            except ParameterError:
+                seq.append(None)            # pass-band beyond Nyquist: the producer loop skips the note
+        runs = [g for i, g in enumerate(seq) if g is not None and (i == 0 or seq[i - 1] != g)]
+        classes = {g for g in seq if g is not None}
+        assert 2 <= len(classes) <= 16, len(classes)
+        assert len(runs) == len(classes)                      # contiguous: every class is ONE run in pitch order
+        valid = [g for g in seq if g is not None]
+        assert len(valid) >= 40
