@@ -295,14 +295,13 @@ class NoteStepBatch:
         self._dirty = None
         self._wav_synced = True
 
-    def _mark_dirty(self, offset_frames, guess_frames):
-        """Host side of the incremental rebuild: per window the frame range the subtraction touched."""
-        if not self._wav_synced or self._dirty is not None:
-            # `wav` is the original audio, or a second subtraction arrives before the rebuild: invert everything next time
-            self._dirty, self._wav_synced = None, False
-            return
-        m = self.N // (2 * self.hl)
-        T, hop = self.T, self.hl
+    @staticmethod
+    def _dirty_ranges(offset_frames, guess_frames, T, N, hop):
+        """Frames [o, o + tg) of a T-frame centred STFT (n_fft N, hop) changed.  Returns (F, fa, lo, hi, tg): the
+        samples [lo, hi) of the hop (T - 1)-sample iSTFT that depend on them, and per window the first row fa of an
+        F-row block whose own iSTFT reproduces those samples exactly (every frame that reaches them is in the block,
+        or the block touches the true edge of the window)."""
+        m = N // (2 * hop)                               # frames on either side of floor(n / hop) that reach sample n
         o = np.clip(np.asarray(offset_frames, dtype=np.int64), 0, T)
         tg = np.minimum(np.asarray(guess_frames, dtype=np.int64), T - o)
         F = int(min(T, int(tg.max(initial=0)) + 4 * m))
@@ -310,6 +309,15 @@ class NoteStepBatch:
         L = hop * (T - 1)
         lo = np.clip((o - m) * hop, 0, L)
         hi = np.where(tg > 0, np.clip((o + tg + m) * hop, 0, L), lo)
+        return F, fa, lo, hi, tg
+
+    def _mark_dirty(self, offset_frames, guess_frames):
+        """Host side of the incremental rebuild: per window the frame range the subtraction touched."""
+        if not self._wav_synced or self._dirty is not None:
+            # `wav` is the original audio, or a second subtraction arrives before the rebuild: invert everything next time
+            self._dirty, self._wav_synced = None, False
+            return
+        F, fa, lo, hi, tg = self._dirty_ranges(offset_frames, guess_frames, self.T, self.N, self.hl)
         dev = self._upload({"fa": fa, "lo": lo, "hi": hi})
         self._dirty = {"F": F, "any": bool((tg > 0).any()), "fa32": dev["fa"], "fa": dev["fa"].long(), "lo": dev["lo"].long(),
                        "hi": dev["hi"].long()}

@@ -225,3 +225,31 @@ def test_shared_cascade_entry_points_reject_mismatched_plans():
                                                out.shape[2], 8 * out.shape[2], C.c_void_p(tok["ws"].data_ptr()),
                                                tok["ws"].numel(), None)
     assert rc == -1 and b"geometry" in lib.saga_last_error_string()
+
+
+def test_dirty_ranges_cover_exactly_what_a_changed_frame_range_reaches():
+    """Host logic of the incremental waveform rebuild, against a brute-force dependency map of the centred iSTFT:
+    sample n of the trimmed output sums the frames t with t hop <= n + N/2 < t hop + N."""
+    import amt_saga_b200  # noqa: F401
+    from amt_saga_b200.note_step import NoteStepBatch
+    rng = np.random.default_rng(3)
+    for N, hop, T in ((4096, 1024, 258), (2048, 512, 40), (4096, 1024, 9), (1024, 256, 33)):
+        L = hop * (T - 1)
+        n = np.arange(L)
+        t_lo = np.maximum(0, -(-(n + N // 2 - N + 1) // hop))                    # first / last frame reaching sample n
+        t_hi = np.minimum(T - 1, (n + N // 2) // hop)
+        o = np.concatenate([[0, 0, T - 1, T, T + 3, 1], rng.integers(0, T + 2, 40)])
+        tg = np.concatenate([[1, T, 5, 4, 2, 0], rng.integers(0, 60, 40)])
+        F, fa, lo, hi, tg_c = NoteStepBatch._dirty_ranges(o, tg, T, N, hop)
+        assert 1 <= F <= T and np.all(fa >= 0) and np.all(fa + F <= T)
+        for i in range(len(o)):
+            oc, tc = min(int(o[i]), T), int(tg_c[i])
+            touched = (t_hi >= oc) & (t_lo <= oc + tc - 1) if tc > 0 else np.zeros(L, dtype=bool)
+            if touched.any():
+                assert lo[i] <= n[touched].min() and n[touched].max() < hi[i]          # every affected sample is patched
+                # and every patched sample is computable from the block: all frames reaching it lie inside
+                # [fa, fa + F), or the missing ones do not exist (true window edge)
+                p = n[lo[i]:hi[i]]
+                assert np.all(t_lo[p] >= fa[i]) and np.all(t_hi[p] <= fa[i] + F - 1)
+            else:
+                assert hi[i] <= lo[i] or tc > 0
