@@ -93,6 +93,14 @@ def sparsify_rows(x, quantile=0.01):
     return out
 
 
+def _basis_fft(basis, n_fft):
+    try:
+        from scipy import fftpack
+        return fftpack.fft(basis, n=n_fft, axis=1)
+    except ImportError:        # numpy >= 2.0 keeps complex64 as well
+        return np.fft.fft(basis, n=n_fft, axis=1)
+
+
 def cqt_filter_fft(sr, fmin, n_bins, bins_per_octave, tuning, filter_scale,
                    norm, sparsity):
     basis, lengths = constant_q(sr, fmin, n_bins, bins_per_octave, tuning,
@@ -100,7 +108,12 @@ def cqt_filter_fft(sr, fmin, n_bins, bins_per_octave, tuning, filter_scale,
     n_fft = basis.shape[1]
     # in-place `basis *= float64` on a complex64 array: computed wide, stored complex64
     basis = (basis.astype(np.complex128) * (lengths[:, np.newaxis] / float(n_fft))).astype(np.complex64)
-    fft_basis = np.fft.fft(basis, n=n_fft, axis=1)[:, : (n_fft // 2) + 1]
+    # librosa 0.6.3 (core/constantq.py, `import scipy.fftpack as fft`) transforms the complex64 basis with
+    # scipy.fftpack.fft, which computes and returns SINGLE precision for complex64 input; so does numpy >= 2.0's
+    # np.fft.fft (the two agree to 1e-7 of the basis peak and to the same sparsity pattern at every shape the
+    # reference uses: tests/test_oracle_pins.py::test_basis_fft_precision).  Use the reference's own function
+    # where it is importable.
+    fft_basis = _basis_fft(basis, n_fft)[:, : (n_fft // 2) + 1]
     fft_basis = sparsify_rows(fft_basis, quantile=sparsity)
     return fft_basis, n_fft, lengths
 

@@ -175,3 +175,24 @@ def test_golden_vectors_still_reproduced(cfg1):
         w.subtract(s["guesses"][j], offset=w._frames_to_seconds(int(s["offsets"][j])) + 1e-9)
     assert np.array_equal(w.mag, s["result"])
     assert np.allclose(w.D, s["D"], atol=1e-5)
+
+
+def test_basis_fft_precision():
+    """librosa 0.6.3 transforms the complex64 constant-Q basis with scipy.fftpack.fft, i.e. in SINGLE precision; the
+    oracle calls the same function (numpy >= 2.0's np.fft.fft keeps complex64 as well).  The precision of that
+    transform is not a parity risk: single (either library) and double precision agree to 2e-7 of the basis peak and
+    select the SAME 1 % sparsity pattern at every (octave rate, bins per octave) the reference's calls produce."""
+    from scipy import fftpack
+    assert ocqt._basis_fft(np.zeros((2, 8), dtype=np.complex64), 8).dtype == np.complex64
+    for sr, fmin, nf, bpo in ((22050, 1046.5, 12, 12), (22050, 1046.5, 24, 24), (22050, 1046.5, 48, 48), (11025, 523.25, 192, 192)):
+        basis, lengths = ocqt.constant_q(sr, fmin, nf, bpo, 0.0, 2, 1)
+        n_fft = basis.shape[1]
+        basis = (basis.astype(np.complex128) * (lengths[:, None] / float(n_fft))).astype(np.complex64)
+        half = slice(0, n_fft // 2 + 1)
+        single_sp = fftpack.fft(basis, n=n_fft, axis=1)[:, half]
+        single_np = np.fft.fft(basis, n=n_fft, axis=1)[:, half]
+        double = np.fft.fft(basis.astype(np.complex128), n=n_fft, axis=1)[:, half]
+        peak = np.abs(double).max()
+        assert np.abs(single_sp - double).max() <= 2e-7 * peak and np.abs(single_np - double).max() <= 2e-7 * peak
+        keep = [ocqt.sparsify_rows(x, quantile=0.01) != 0 for x in (single_sp, single_np, double)]
+        assert np.array_equal(keep[0], keep[1]) and np.array_equal(keep[0], keep[2])
