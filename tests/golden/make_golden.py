@@ -1,12 +1,10 @@
-"""Generates tests/golden/*.npz.
+"""Generates tests/golden/{cfg1,cqt87,istft,subtract_chain}.npz from the CPU oracle (oracle/).
 
-The reference (RobertKajnak/AMT-SAGA) cannot be imported in this container
-(librosa, magenta, soundfile, matplotlib, fluidsynth absent; `np.int` removed
-from numpy 2.x) and it ships no numerical fixtures, so these vectors come from
-the CPU oracle (oracle/), which restates the reference's algorithm -- PARITY
-UNPINNED against the literal reference.  They pin the oracle against silent
-drift and give the GPU tests fixed targets that do not depend on re-running
-the oracle.  Run from the repo root:  python tests/golden/make_golden.py
+These vectors pin the oracle against silent drift and give the GPU tests fixed targets that do not depend on
+re-running it.  The oracle's container is checked bit for bit against the reference's own `audio_complete`
+(oracle/ref_class.py, tests/test_ref_class.py; golden vectors of THAT class: make_ref_class_golden.py); the librosa /
+resampy layer underneath is a restatement (no wheel, no network), so CQT and dB values here are unpinned against
+reference outputs -- none exist.  Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys
