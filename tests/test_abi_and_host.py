@@ -101,6 +101,27 @@ def test_options_table_replaces_the_environment_on_the_hot_path():
     assert lib.saga_get_option(b"SAGA_DB_CHUNKS") == before
 
 
+def test_every_switch_the_docs_and_sources_name_is_in_the_options_table():
+    """DESIGN.md lists the tuning / A-B switches and the CUDA sources read them with SAGA_OPT("..."): every such name
+    must be known to saga_set_option (a name missing from the table would silently read as unset)."""
+    import re
+    from amt_saga_b200 import _lib
+    lib = _lib.lib()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    csrc = os.path.join(root, "amt-saga_b200", "csrc")
+    for f in os.listdir(csrc):
+        names |= set(re.findall(r'SAGA_OPT\("(SAGA_[A-Z0-9_]+)"\)', open(os.path.join(csrc, f)).read()))
+    doc = open(os.path.join(root, "DESIGN.md")).read()
+    table = doc[doc.index("Tuning / A-B switches"):doc.index("No launcher calls `getenv`")]
+    names |= set(re.findall(r"`(SAGA_[A-Z0-9_]+)`", table))
+    names.discard("SAGA_X")            # the placeholder in the macro's own comment (saga_common.cuh)
+    assert len(names) >= 20
+    for n in sorted(names):
+        cur = lib.saga_get_option(n.encode())
+        assert lib.saga_set_option(n.encode(), cur) == 0, n
+
+
 def test_plan_cache_drops_handles_of_another_process():
     """The reference forks its producers (training.py:623-630).  Plans are cached per (pid, device); entries that
     belong to another process are dropped WITHOUT calling *_destroy on them (their handles live in the parent's
